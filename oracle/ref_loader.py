@@ -1,0 +1,104 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product path (values_b200/).
+
+Imports the UNMODIFIED reference (IML-DKFZ/values) in place from /root/reference so
+that (a) the oracle restatement in oracle/values_oracle.py can be pinned against it and
+(b) golden vectors can be generated (tests/golden/make_golden.py).
+
+The reference imports several third-party packages at module scope that are not
+installed in this image (hydra, medpy, batchgenerators, torchmetrics,
+pytorch_lightning, albumentations, jsbeautifier, ...).  None of the hot-path function
+bodies touch them, so they are replaced by MagicMock modules.
+
+/root/reference does not exist on the GPU box: callers must check `available()`.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+REFERENCE_ROOT = os.environ.get("VALUES_REFERENCE_ROOT", "/root/reference")
+
+_STUBBED = [
+    "hydra", "hydra.utils", "omegaconf", "medpy", "medpy.io", "batchgenerators",
+    "batchgenerators.dataloading", "batchgenerators.dataloading.data_loader",
+    "batchgenerators.dataloading.multi_threaded_augmenter",
+    "batchgenerators.dataloading.single_threaded_augmenter",
+    "batchgenerators.transforms", "batchgenerators.transforms.abstract_transforms",
+    "batchgenerators.transforms.noise_transforms",
+    "batchgenerators.transforms.spatial_transforms",
+    "batchgenerators.transforms.color_transforms",
+    "batchgenerators.transforms.crop_and_pad_transforms",
+    "batchgenerators.transforms.utility_transforms",
+    "batchgenerators.transforms.sample_normalization_transforms",
+    "batchgenerators.augmentations", "batchgenerators.augmentations.utils",
+    "torchmetrics", "torchmetrics.functional", "torchmetrics.functional.classification",
+    "pytorch_lightning", "pytorch_lightning.loggers", "pytorch_lightning.callbacks",
+    "albumentations", "albumentations.pytorch", "jsbeautifier", "SimpleITK", "nibabel",
+    "matplotlib", "matplotlib.pyplot", "seaborn", "tifffile", "skimage", "tqdm",
+    "pydantic",
+]
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "uncertainty_modeling"))
+
+
+class _Anything(types.ModuleType):
+    """A module whose every attribute is a MagicMock (so `from x import y` works)."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        m = MagicMock(name=f"{self.__name__}.{name}")
+        setattr(self, name, m)
+        return m
+
+
+_loaded = {}
+
+
+def load():
+    """Return a namespace with the reference's hot-path callables (unmodified)."""
+    if _loaded:
+        return types.SimpleNamespace(**_loaded)
+    if not available():
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    for name in _STUBBED:
+        try:
+            importlib.import_module(name)
+        except Exception:
+            mod = _Anything(name)
+            mod.__path__ = []  # behave like a package
+            sys.modules[name] = mod
+    # tqdm is used as `for x in tqdm(iterable)`: make it the identity.
+    if isinstance(sys.modules.get("tqdm"), _Anything):
+        sys.modules["tqdm"].tqdm = lambda it, *a, **k: it
+    for p in (
+        REFERENCE_ROOT,
+        os.path.join(REFERENCE_ROOT, "uncertainty_modeling"),
+        os.path.join(REFERENCE_ROOT, "evaluation"),
+    ):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    t3d = importlib.import_module("uncertainty_modeling.test_3D")
+    dc = importlib.import_module("uncertainty_modeling.data_carrier_3D")
+    agg = importlib.import_module(
+        "evaluation.uncertainty_aggregation.aggregate_uncertainties"
+    )
+    thr = importlib.import_module("evaluation.uncertainty_aggregation.find_threshold")
+    _loaded.update(
+        calculate_uncertainty=t3d.calculate_uncertainty,
+        calculate_one_minus_msr=t3d.calculate_one_minus_msr,
+        caculcate_uncertainty_multiple_pred=t3d.caculcate_uncertainty_multiple_pred,
+        DataCarrier3D=dc.DataCarrier3D,
+        patch_level_aggregation=agg.patch_level_aggregation,
+        image_level_aggregation=agg.image_level_aggregation,
+        threshold_aggregation=agg.threshold_aggregation,
+        calculate_foreground_quantile_image=thr.calculate_foreground_quantile_image,
+        modules=dict(test_3D=t3d, data_carrier_3D=dc, aggregate_uncertainties=agg,
+                     find_threshold=thr),
+    )
+    return types.SimpleNamespace(**_loaded)

@@ -1,0 +1,46 @@
+"""Build container only: the oracle against the UNMODIFIED reference imported in place
+(oracle/ref_loader.py).  Skipped where /root/reference is absent (the GPU box)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader
+from oracle import values_oracle as vo
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize("n,c,spatial,dtype", [
+    (5, 2, (12, 12, 12), torch.float64),
+    (16, 4, (10, 9, 8), torch.float32),
+    (10, 20, (24, 30), torch.float32),
+    (3, 7, (17,), torch.float32),
+])
+def test_c2_bit_exact(ref, n, c, spatial, dtype):
+    g = torch.Generator().manual_seed(n * 100 + c)
+    x = torch.softmax(3 * torch.randn(n, c, *spatial, generator=g, dtype=torch.float64), 1).to(dtype)
+    x[0, 0].view(-1)[:3] = 0.0
+    a, b = ref.calculate_uncertainty(x), vo.calculate_uncertainty(x)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    a, b = ref.calculate_uncertainty(x, ssn=True), vo.calculate_uncertainty(x, ssn=True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_c3_random(ref):
+    rng = np.random.default_rng(3)
+    for shape, p in [((20, 21, 22), 10), ((40, 33), 10), ((11, 12, 13), [2, 3, 4])]:
+        m = rng.random(shape)
+        a = ref.patch_level_aggregation(m, p)
+        b = vo.patch_level_aggregation(m, p)
+        assert a["bounding_box"] == b["bounding_box"]
+        np.testing.assert_allclose(a["max_score"], b["max_score"], rtol=1e-12)
+        assert ref.image_level_aggregation(m) == vo.image_level_aggregation(m)
+        ra, rb = ref.threshold_aggregation(m, threshold=0.7), vo.threshold_aggregation(m, threshold=0.7)
+        assert float(ra["max_score"]) == float(rb["max_score"])
