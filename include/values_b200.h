@@ -1,0 +1,131 @@
+/* values_b200.h -- C-ABI of the B200-native ValUES C2+C3 uncertainty hot path.
+ *
+ * The reference (IML-DKFZ/values) is pure Python and has no FFI layer; its boundary for
+ * this path is a set of Python callables.  Every entry point below
+ * names the reference callable it replaces.  Conventions:
+ *   - all data pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - sizes / strides are in ELEMENTS, int64_t; the voxel axis is contiguous (stride 1);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - nothing is allocated or owned by the library: outputs and workspaces belong to the
+ *     caller; workspace sizes come from the matching *_workspace_bytes function;
+ *   - return value: VALUES_OK or a negative VALUES_ERR_* code; values_last_error() gives
+ *     a thread-local message.  No entry point synchronises the device.
+ * There is deliberately NO CPU fallback: without a CUDA device every compute entry point
+ * returns VALUES_ERR_CUDA.
+ */
+#ifndef VALUES_B200_H
+#define VALUES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VALUES_ABI_VERSION 1
+
+typedef enum { VALUES_F32 = 0, VALUES_F64 = 1, VALUES_BF16 = 2 } values_dtype_t;
+
+#define VALUES_OK 0
+#define VALUES_ERR_INVALID_ARG (-1) /* -> ValueError on the Python side            */
+#define VALUES_ERR_UNSUPPORTED (-2) /* shape outside what the kernels tile for      */
+#define VALUES_ERR_CUDA (-3)        /* a CUDA runtime call / launch failed          */
+#define VALUES_ERR_WORKSPACE (-4)   /* workspace pointer NULL or too small          */
+
+int values_abi_version(void);
+const char* values_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py reports it). */
+int64_t values_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1: fused N x C reduction.
+ * Replaces calculate_uncertainty(softmax_preds, ssn)  uncertainty_modeling/test_3D.py:486-518
+ * (PE / EE / MI with the NaN-skip rule, fp32 accumulators in class order) and the arg-max
+ * of the mean / of each sample taken at save time (data_carrier_3D.py:253-259, 281-285;
+ * test_2D.py:119-127).  One sweep over HBM.
+ *
+ *   probs   [B, N, C, V] with element strides (stride_b, stride_n, stride_c, 1)
+ *   pe/ee/mi      float [B, V]   predictive entropy / expected entropy / mutual information
+ *                               (the `ssn` key swap is a host-side relabelling)
+ *   mean_argmax   uint8 [B, V]      or NULL
+ *   sample_argmax uint8 [B, N, V]   or NULL
+ *   scores  double [B, 3, 3] or NULL: per map (pe, ee, mi): {sum, sum over v>=thr, count v>=thr}
+ *           = image_level_aggregation / threshold_aggregation numerators fused into the sweep
+ *           (evaluation/uncertainty_aggregation/aggregate_uncertainties.py:34-37, 61-62).
+ *   thresholds_host  3 doubles (pe, ee, mi) or NULL (then thr columns are 0).
+ *   workspace: values_uncertainty_workspace_bytes(B, V, dtype) bytes when scores != NULL.
+ */
+size_t values_uncertainty_workspace_bytes(int64_t B, int64_t V, int dtype);
+int values_uncertainty_fused(const void* probs, int dtype, int64_t B, int64_t N, int64_t C,
+                             int64_t V, int64_t stride_b, int64_t stride_n, int64_t stride_c,
+                             float* pe, float* ee, float* mi, uint8_t* mean_argmax,
+                             uint8_t* sample_argmax, double* scores,
+                             const double* thresholds_host, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* Replaces calculate_one_minus_msr(softmax_pred)  test_3D.py:521-525 and
+ * ExperimentDataloader.get_max_softmax_pred  evaluation/experiment_dataloader.py:38-49.
+ *   probs [B, C, V] (strides stride_b, stride_c, 1) -> out [B, V] of the same dtype = 1 - max_c p. */
+int values_one_minus_msr(const void* probs, int dtype, int64_t B, int64_t C, int64_t V,
+                         int64_t stride_b, int64_t stride_c, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2a: image-level and threshold aggregation of M stored maps (f32 or f64).
+ * Replaces image_level_aggregation (aggregate_uncertainties.py:34-37) and
+ * threshold_aggregation (:40-67; mask is `>=`).  Deterministic block-then-grid reduction.
+ *   maps [M, V] (stride_m, 1); thresholds_host[n_thresholds] (<= 16), map m uses entry
+ *   m % n_thresholds; NULL / 0 -> no threshold.
+ *   out double [M, 3] = {sum, sum over v>=thr, count v>=thr}
+ */
+size_t values_map_reduce_workspace_bytes(int64_t M, int64_t V);
+int values_map_reduce(const void* maps, int dtype, int64_t M, int64_t V, int64_t stride_m,
+                      const double* thresholds_host, int n_thresholds, double* out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* K2b: patch-level aggregation.
+ * Replaces patch_level_aggregation(image, patch_size, mean)  aggregate_uncertainties.py:13-31:
+ * fp64 box-sum over every fully-inside window (scipy convolve mode="valid" with a ones
+ * kernel), max_score = max, bbox_lo = FIRST C-order window index with
+ * |sum - max| <= atol + rtol*|max| (np.isclose defaults rtol 1e-5, atol 1e-8).
+ *   maps [M, shape[0], shape[1], shape[2]] (stride_m between maps; last axis contiguous);
+ *   ndim in {1,2,3}: unused leading axes must have shape 1 and patch 1.
+ *   max_score double [M]; bbox_lo int64 [M, 3] (leading unused axes report 0).
+ * Returns VALUES_ERR_INVALID_ARG if any patch > shape (the reference raises ValueError).
+ */
+size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* shape3_host,
+                                        const int64_t* patch3_host);
+int values_patch_max(const void* maps, int dtype, int64_t M, int64_t stride_m,
+                     const int64_t* shape3_host, const int64_t* patch3_host, int mean_flag,
+                     double rtol, double atol, double* max_score, int64_t* bbox_lo,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3: sliding-window stitch accumulator (atomic-free, output-stationary).
+ * Replaces the `+=` slab updates of DataCarrier3D.concat_data
+ * (uncertainty_modeling/data_carrier_3D.py:154-179): uniform weights, patches summed in
+ * list order, count incremented once per covering patch.
+ *   patches  [N, n_patches_total, C, p0, p1, p2]; element strides patch_stride_n (between
+ *            samples) and patch_stride_p (between patches); [C, p0, p1, p2] contiguous.
+ *   patch_index int32 [n_sel] (device) or NULL (= 0..n_sel-1): which patches to use
+ *   crop_lo  int32 [n_sel, 3] (device): lower corner (x0, y0, z0) of each selected patch
+ *   out_sum  [N, C, vol0, vol1, vol2] contiguous, dtype out_dtype (F64 parity / F32)
+ *   out_count double [vol0, vol1, vol2] or NULL (written when non-NULL; `accumulate` applies)
+ *   accumulate != 0: out += (read-modify-write of every voxel);  == 0: out = (uncovered -> 0)
+ */
+int values_stitch_accumulate(const void* patches, int patch_dtype, int64_t patch_stride_n,
+                             int64_t patch_stride_p, const int32_t* patch_index,
+                             const int32_t* crop_lo, int64_t n_sel, int64_t N, int64_t C,
+                             const int64_t* patch3_host, const int64_t* vol3_host,
+                             void* out_sum, int out_dtype, double* out_count, int accumulate,
+                             void* stream);
+
+/* Save-time normalisation (data_carrier_3D.py:215-217, 326-329):
+ *   out[m, v] = (double) maps[m, v] / max(count[v], 1)   -> fp64 as written to NIfTI. */
+int values_normalize_maps(const void* maps, int dtype, int64_t M, int64_t V, int64_t stride_m,
+                          const double* count, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VALUES_B200_H */

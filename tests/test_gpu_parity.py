@@ -1,0 +1,401 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same
+seeded inputs and against the golden vectors produced by the reference itself.
+
+Tolerances (BASELINE.json north_star): arg-max / threshold counts / patch indices bit-exact;
+fp32 maps and scores within 1e-5 relative (+1e-6 absolute for the PE-EE cancellation, SURVEY
+H1); bf16 inputs within 1e-3.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+MAPS = ("pred_entropy", "aleatoric_uncertainty", "epistemic_uncertainty")
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+C2_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "c2_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import values_b200
+
+    return values_b200
+
+
+@pytest.fixture(scope="module")
+def vo():
+    from oracle import values_oracle
+
+    return values_oracle
+
+
+def softmax_stack(seed, n, c, spatial, dtype=torch.float32, shared=False, sharp=3.0):
+    g = torch.Generator().manual_seed(seed)
+    if shared:
+        logits = sharp * torch.randn(1, c, *spatial, generator=g, dtype=torch.float64) + \
+            0.3 * torch.randn(n, c, *spatial, generator=g, dtype=torch.float64)
+    else:
+        logits = sharp * torch.randn(n, c, *spatial, generator=g, dtype=torch.float64)
+    return torch.softmax(logits, dim=1).to(dtype)
+
+
+def assert_maps_close(got, ref, rtol=RTOL, atol=ATOL):
+    for k in MAPS:
+        a, b = got[k].detach().cpu().numpy(), ref[k].detach().cpu().numpy() if hasattr(ref[k], "detach") else ref[k]
+        assert a.dtype == np.float32 and a.shape == b.shape, k
+        np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=k)
+
+
+def assert_argmax(got_u8, stack, exact_ref):
+    """bit-exact, except where the two largest class means are within 2 ulp (the reference's
+    own mean rounds differently in torch's vector tail vs numpy)."""
+    got = got_u8.cpu().numpy()
+    ref = np.asarray(exact_ref)
+    bad = got != ref
+    if bad.any():
+        m = np.sort(np.mean(stack.double().numpy(), axis=0), axis=0)
+        gap = (m[-1] - m[-2])[bad]
+        assert np.all(gap <= 4e-7 * np.abs(m[-1][bad])), f"{bad.sum()} arg-max mismatches beyond near-ties"
+
+
+def test_native_library_loaded(vb):
+    with open("/proc/self/maps") as f:
+        assert "libvalues_b200.so" in f.read()
+    assert vb._lib.lib.values_abi_version() == 1
+
+
+@pytest.mark.parametrize("name", C2_CASES)
+def test_c2_golden(vb, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    x = torch.from_numpy(g["softmax"])
+    before = vb._lib.launch_count()
+    d = vb.calculate_uncertainty(x, ssn=bool(g["ssn"]))
+    assert vb._lib.launch_count() > before
+    assert all(v.device.type == "cpu" for v in d.values())  # same device as the input
+    assert_maps_close(d, {k: g[k] for k in MAPS})
+    res = vb.uncertainty_fused(x.cuda().unsqueeze(0), mean_argmax=True, sample_argmax=True)
+    assert_argmax(res.mean_argmax[0], x, g["mean_argmax"])
+    np.testing.assert_array_equal(res.sample_argmax[0].cpu().numpy(), g["sample_argmax"])
+
+
+@pytest.mark.parametrize("n,c,spatial,dtype", [
+    (5, 2, (64, 64, 64), torch.float32),      # cfg1/2 shape
+    (5, 2, (33, 31, 29), torch.float64),      # 3D path dtype, odd sizes -> scalar path
+    (16, 4, (40, 40, 40), torch.float32),     # cfg5 class/sample counts
+    (10, 20, (96, 128), torch.float32),       # cfg4 class count -> shared-memory class sums
+    (10, 25, (61, 77), torch.float32),        # reference-true GTA class count, odd width
+    (8, 2, (48, 48, 48), torch.float64),      # cfg3 stitched stack dtype
+    (3, 7, (1000,), torch.float32),
+    (17, 3, (24, 24, 24), torch.float32),     # N > 16
+    (1, 4, (32, 32), torch.float32),
+    (6, 8, (20, 20, 20), torch.float64),
+    (4, 11, (30, 30), torch.float64),
+])
+def test_c2_vs_oracle(vb, vo, n, c, spatial, dtype):
+    x = softmax_stack(1000 + n * 31 + c, n, c, spatial, dtype)
+    x.view(n, c, -1)[0, 0, :5] = 0.0
+    ref = vo.calculate_uncertainty(x)
+    res = vb.uncertainty_fused(x.cuda().unsqueeze(0), mean_argmax=True, sample_argmax=True)
+    assert_maps_close(res.as_dict(0), ref)
+    assert_argmax(res.mean_argmax[0], x, np.argmax(np.mean(x.numpy(), axis=0), axis=0))
+    np.testing.assert_array_equal(res.sample_argmax[0].cpu().numpy(), vo.sample_argmax(x).numpy())
+
+
+def test_c2_low_mi_regime(vb, vo):
+    x = softmax_stack(5, 5, 2, (48, 48, 48), torch.float32, shared=True)
+    ref = vo.calculate_uncertainty(x)
+    got = vb.calculate_uncertainty(x.cuda())
+    assert got["pred_entropy"].device.type == "cuda"
+    assert_maps_close(got, ref)
+    # PE and EE themselves (no cancellation) hold 1e-5 relative with a tiny absolute floor
+    for k in MAPS[:2]:
+        np.testing.assert_allclose(got[k].cpu().numpy(), ref[k].numpy(), rtol=1e-5, atol=1e-9)
+
+
+def test_c2_bf16(vb, vo):
+    x = softmax_stack(9, 8, 4, (32, 32, 32), torch.float32).to(torch.bfloat16)
+    ref = vo.calculate_uncertainty(x.float())  # bf16 is widened exactly, then the fp32 algorithm
+    res = vb.uncertainty_fused(x.cuda().unsqueeze(0), mean_argmax=True)
+    assert_maps_close(res.as_dict(0), ref, rtol=1e-3, atol=1e-5)
+    assert_argmax(res.mean_argmax[0], x.float(), vo.mean_argmax(x.float()).numpy())
+    x = softmax_stack(10, 6, 19, (40, 56), torch.float32).to(torch.bfloat16)  # smem path
+    ref = vo.calculate_uncertainty(x.float())
+    assert_maps_close(vb.calculate_uncertainty(x.cuda()), ref, rtol=1e-3, atol=1e-5)
+
+
+def test_c2_strided_2d_layout_and_ssn(vb, vo):
+    """[N, B, C, H, W] stack sliced per image as test_2D.py:223-227 does (strided in N)."""
+    n, b, c, h, w = 6, 3, 5, 24, 40
+    full = softmax_stack(77, n * b, c, (h, w)).reshape(n, b, c, h, w)
+    full = torch.cat([full, torch.zeros(n, b, 1, h, w)], dim=2)  # zero channel, test_2D.py:208-218
+    dev = full.cuda()
+    res = vb.uncertainty_fused(dev.permute(1, 0, 2, 3, 4))  # batched, no copy
+    for i in range(b):
+        ref = vo.calculate_uncertainty(full[:, i], ssn=True)
+        assert_maps_close(vb.calculate_uncertainty(dev[:, i], ssn=True), ref)
+        assert_maps_close(res.as_dict(i, ssn=True), ref)
+
+
+def test_c2_properties(vb):
+    x = softmax_stack(3, 10, 4, (64, 64)).cuda()
+    base = vb.calculate_uncertainty(x)
+    # appended all-zero channel leaves every map bit-identical (NaN-skip rule)
+    xz = torch.cat([x, torch.zeros(10, 1, 64, 64, device="cuda")], dim=1)
+    withz = vb.calculate_uncertainty(xz)
+    for k in MAPS:
+        assert torch.equal(base[k], withz[k])
+    # identical samples -> MI == 0 up to one rounding of PE
+    same = x[:1].expand(10, -1, -1, -1).contiguous()
+    d = vb.calculate_uncertainty(same)
+    assert d["epistemic_uncertainty"].abs().max().item() <= 5e-7
+    # uniform p -> PE = EE = log C
+    u = torch.full((4, 5, 16, 16), 0.2, device="cuda")
+    d = vb.calculate_uncertainty(u)
+    np.testing.assert_allclose(d["pred_entropy"].cpu().numpy(), np.log(5.0), rtol=1e-6)
+    # one-hot samples cycling over K classes -> PE = log K, EE = 0 exactly
+    oh = torch.zeros(4, 4, 8, 8, device="cuda")
+    for i in range(4):
+        oh[i, i] = 1.0
+    d = vb.calculate_uncertainty(oh)
+    np.testing.assert_allclose(d["pred_entropy"].cpu().numpy(), np.log(4.0), rtol=1e-6)
+    assert d["aleatoric_uncertainty"].abs().max().item() == 0.0
+    # empty volume
+    e = vb.uncertainty_fused(torch.zeros(1, 3, 2, 0, 4, device="cuda"))
+    assert e.pred_entropy.shape == (1, 0, 4)
+
+
+@pytest.mark.parametrize("name", ["msr_f32", "msr_f64"])
+def test_msr_golden(vb, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = vb.calculate_one_minus_msr(torch.from_numpy(g["softmax"]))
+    np.testing.assert_array_equal(d["pred_entropy"].numpy(), g["pred_entropy"])  # bit-exact
+
+
+def test_fused_scores_vs_oracle(vb, vo):
+    B, n, c, spatial = 3, 5, 3, (20, 24, 28)
+    x = softmax_stack(21, B * n, c, spatial).reshape(B, n, c, *spatial)
+    thr = (0.5, 0.4, 0.05)
+    res = vb.uncertainty_fused(x.cuda(), scores=True, thresholds=thr)
+    sc = res.scores.cpu().numpy()
+    for b in range(B):
+        ref = vo.calculate_uncertainty(x[b])
+        for k, key in enumerate(MAPS):
+            got_map = res.as_dict(b)[key].cpu().numpy().astype(np.float64)
+            # counts are exact w.r.t. the map this kernel produced
+            assert sc[b, k, 2] == float((got_map >= thr[k]).sum())
+            np.testing.assert_allclose(sc[b, k, 0], vo.image_level_aggregation(ref[key].numpy())["max_score"], rtol=1e-5)
+            np.testing.assert_allclose(sc[b, k, 0], got_map.sum(), rtol=1e-12)
+            np.testing.assert_allclose(sc[b, k, 1], got_map[got_map >= thr[k]].sum(), rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------ C3
+def test_c3_golden(vb):
+    g = np.load(os.path.join(GOLDEN, "c3_aggregations.npz"))
+    for i in range(int(g["n_patch_cases"])):
+        for mean in (0, 1):
+            key = f"patch_{i}_{mean}"
+            m = g["map_" + str(g[key + "_map"])]
+            p = g[key + "_patch"].tolist()
+            p = p[0] if len(p) == 1 else p
+            r = vb.patch_level_aggregation(m, p, mean=bool(mean))
+            rtol = 1e-12 if m.dtype == np.float64 else 1e-6  # reference FFT runs fp32 images in complex64
+            np.testing.assert_allclose(r["max_score"], float(g[key + "_score"]), rtol=rtol, atol=1e-300)
+            assert [list(b) for b in r["bounding_box"]] == g[key + "_bbox"].tolist(), key
+            assert all(isinstance(v, int) for b in r["bounding_box"] for v in b)
+    for mname in ("m3d_f64", "m2d_f32", "m3d_zero", "m3d_planted"):
+        m = g["map_" + mname]
+        rt = 1e-12 if m.dtype == np.float64 else 1e-6
+        np.testing.assert_allclose(vb.image_level_aggregation(m)["max_score"], float(g["image_sum_" + mname]), rtol=rt)
+        np.testing.assert_allclose(vb.image_level_aggregation(m, mean=True), float(g["image_mean_" + mname]), rtol=rt)
+        for j, thr in enumerate(g["thresholds"].tolist()):
+            for mean in (1, 0):
+                r = vb.threshold_aggregation(m, threshold=thr, mean=bool(mean))
+                np.testing.assert_allclose(r["max_score"], float(g[f"thr_{mname}_{j}_{mean}"]), rtol=rt)
+                assert r["threshold"] == thr and isinstance(r["max_score"], float)
+
+
+@pytest.mark.parametrize("shape,patch,dtype", [
+    ((64, 64, 64), 10, np.float64), ((70, 45, 33), 10, np.float32), ((128, 96), 10, np.float32),
+    ((40, 50, 60), [3, 7, 12], np.float64), ((10, 10, 10), 10, np.float64), ((300,), 10, np.float32),
+    ((35, 200, 37), [20, 1, 30], np.float32), ((256, 478), 10, np.float32),
+])
+def test_c3_patch_vs_oracle(vb, vo, shape, patch, dtype):
+    rng = np.random.default_rng(sum(shape) * 7 + len(shape))
+    m = rng.random(shape).astype(dtype)
+    for mean in (False, True):
+        a = vb.patch_level_aggregation(m, patch, mean=mean)
+        b = vo.patch_level_aggregation(m, patch, mean=mean)
+        assert a["bounding_box"] == b["bounding_box"]
+        np.testing.assert_allclose(a["max_score"], b["max_score"], rtol=1e-12)
+
+
+def test_c3_batched_and_isclose_rule(vb, vo):
+    rng = np.random.default_rng(11)
+    maps = rng.random((7, 30, 31, 32)).astype(np.float32)
+    maps[3] = 0.0                                   # all-zero map -> score 0, box at origin
+    maps[4, 5:15, 5:15, 5:15] += 1.0
+    maps[5] = maps[4] * (1 - 4e-6)                  # everything scales: same bbox
+    score, bbox = vb.patch_max(torch.from_numpy(maps).cuda(), 10)
+    for i in range(7):
+        r = vo.patch_level_aggregation(maps[i], 10)
+        np.testing.assert_allclose(score[i].item(), r["max_score"], rtol=1e-12)
+        assert bbox[i].tolist() == [b[0] for b in r["bounding_box"]]
+    assert bbox[3].tolist() == [0, 0, 0] and score[3].item() == 0.0
+
+
+def test_c3_errors(vb):
+    img = np.ones((8, 8))
+    with pytest.raises(ValueError):
+        vb.patch_level_aggregation(img, 9)
+    with pytest.raises(Exception, match="A threshold needs to be provided"):
+        vb.threshold_aggregation(img)
+    r = vb.threshold_aggregation(img.astype(np.float32), threshold=2.0)  # empty selection
+    assert r == {"max_score": 0.0, "threshold": 2.0}
+    assert vb.image_level_aggregation(np.ones((33, 35, 37)))["max_score"] == 33 * 35 * 37
+    # extra kwargs the reference always passes (aggregate_uncertainties.py:81-86)
+    vb.patch_level_aggregation(img, 4, pred_model="Softmax", unc_type="pred_entropy")
+    vb.image_level_aggregation(img, pred_model="Softmax", unc_type="pred_entropy")
+
+
+def test_c3_map_reduce_vs_oracle(vb, vo):
+    rng = np.random.default_rng(5)
+    for shape, dtype in [((64, 64, 64), np.float64), ((1024, 513), np.float32), ((7,), np.float32)]:
+        m = rng.random(shape).astype(dtype)
+        np.testing.assert_allclose(vb.image_level_aggregation(m)["max_score"],
+                                   vo.image_level_aggregation(m)["max_score"], rtol=1e-6)
+        for thr in (0.0, 0.3, 0.999, 1.5):
+            a = vb.threshold_aggregation(m, threshold=thr)
+            b = vo.threshold_aggregation(m, threshold=thr)
+            np.testing.assert_allclose(a["max_score"], float(b["max_score"]), rtol=1e-6)
+        out = vb.map_reduce(torch.from_numpy(m).cuda().unsqueeze(0), [0.3])[0].tolist()
+        assert out[2] == float((m >= 0.3).sum())  # count bit-exact
+
+
+# --------------------------------------------------------------------------------- stitch
+def test_stitch_golden(vb, vo):
+    g = np.load(os.path.join(GOLDEN, "stitch_3d.npz"))
+    shape, p = tuple(g["shape"].tolist()), int(g["patch"])
+    crops = vb.patch_grid(shape, p, float(g["overlap"]))
+    assert np.array(crops).tolist() == g["crops"].tolist()
+    patches = torch.from_numpy(g["patches"])
+    n_pred = patches.shape[0]
+    # (a) drop-in DataCarrier3D.concat_data, batched like the reference's loop
+    carrier = vb.DataCarrier3D()
+    for pred_idx in range(n_pred):
+        for s in range(0, len(crops), 5):
+            idx = list(range(s, min(s + 5, len(crops))))
+            batch = {"image_paths": ["vol_a.npy"] * len(idx), "label_paths": [["lab"]] * len(idx),
+                     "org_image_size": [shape] * len(idx), "crop_idx": [crops[i] for i in idx],
+                     "data": torch.ones(len(idx), 1, p, p, p),
+                     "seg": torch.ones(1, len(idx), p, p, p, dtype=torch.int32)}
+            carrier.concat_data(batch, patches[pred_idx, idx], n_pred=n_pred, pred_idx=pred_idx)
+    v = carrier.data["vol_a.npy"]
+    np.testing.assert_array_equal(v["softmax_pred"].cpu().numpy(), g["softmax_sum"])  # bit-exact fp64
+    np.testing.assert_array_equal(v["num_predictions"].cpu().numpy(), g["num_predictions"])
+    np.testing.assert_array_equal(v["data"].cpu().numpy(), g["num_predictions"][0])
+    np.testing.assert_array_equal(v["seg"][0].cpu().numpy(), g["num_predictions"][0].astype(np.int32))
+    vb.caculcate_uncertainty_multiple_pred(carrier)
+    assert_maps_close({k: v[k] for k in MAPS}, {k: g[k] for k in MAPS})
+    norm = carrier.normalized("vol_a.npy")
+    np.testing.assert_allclose(norm["pred_entropy"].cpu().numpy(), g["pred_entropy_saved"], rtol=RTOL, atol=ATOL)
+    assert_argmax(norm["mean_seg"], torch.from_numpy(g["softmax_sum"] / np.clip(g["num_predictions"], 1, None)), g["mean_seg"])
+    ref_layout = carrier.numpy_data()["vol_a.npy"]
+    assert ref_layout["softmax_pred"].dtype == np.float64 and ref_layout["num_predictions"].shape == (2,) + shape
+    # (b) all patches at once, written exactly once
+    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape)
+    np.testing.assert_array_equal(total.cpu().numpy(), g["softmax_sum"])
+    np.testing.assert_array_equal(cnt.cpu().numpy(), g["num_predictions"][0])
+
+
+@pytest.mark.parametrize("shape,p,overlap,dtype", [
+    ((64, 64, 64), 64, 1.0, torch.float64),      # shipped settings: one patch per volume
+    ((96, 80, 72), 32, 0.5, torch.float32),
+    ((50, 50, 40), 16, 0.75, torch.float32),     # non-multiple size -> uncovered remainder
+    ((40, 24, 200), 8, 1.0, torch.bfloat16),
+])
+def test_stitch_vs_oracle(vb, vo, shape, p, overlap, dtype):
+    crops = vo.patch_grid(shape, p, overlap)
+    assert crops == vb.patch_grid(shape, p, overlap)
+    n_pred, c = 2, 3
+    g = torch.Generator().manual_seed(len(crops))
+    patches = torch.rand(n_pred, len(crops), c, p, p, p, generator=g, dtype=torch.float64).to(dtype)
+    st = vo.StitchOracle(n_classes=c)
+    for pi in range(n_pred):
+        st.concat_data({"image_paths": ["v"] * len(crops), "org_image_size": [shape] * len(crops),
+                        "crop_idx": crops}, patches[pi].double(), n_pred=n_pred, pred_idx=pi)
+    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape)
+    np.testing.assert_array_equal(total.cpu().numpy(), st.data["v"]["softmax_pred"])
+    np.testing.assert_array_equal(cnt.cpu().numpy(), st.data["v"]["num_predictions"][0])
+    if dtype == torch.float32:
+        t32, _ = vb.stitch_volume(patches.cuda(), crops, shape, out_dtype=torch.float32)
+        np.testing.assert_allclose(t32.cpu().numpy(), st.data["v"]["softmax_pred"], rtol=1e-6)
+
+
+def test_stitch_many_patches_chunked_list(vb, vo):
+    shape, p = (44, 44, 44), 8
+    crops = vo.patch_grid(shape, p, 0.25)  # stride 2 -> 19^3 = 6859 patches > list chunk
+    g = torch.Generator().manual_seed(1)
+    patches = torch.rand(1, len(crops), 1, p, p, p, generator=g, dtype=torch.float32)
+    st = vo.StitchOracle(n_classes=1)
+    st.concat_data({"image_paths": ["v"] * len(crops), "org_image_size": [shape] * len(crops),
+                    "crop_idx": crops}, patches[0], pred_idx=0)
+    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape)
+    np.testing.assert_allclose(total.cpu().numpy(), st.data["v"]["softmax_pred"], rtol=1e-14)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), st.data["v"]["num_predictions"][0])
+
+
+# ------------------------------------------------------------------------------- pipeline
+def test_pipeline_vs_oracle(vb, vo):
+    B, n, c, spatial = 5, 5, 2, (32, 36, 40)
+    x = softmax_stack(99, B * n, c, spatial).reshape(B, n, c, *spatial)
+    thr = (0.45, 0.4, 0.03)
+    cfg = vb.AggregationConfig(patch_size=10, thresholds=thr, l2_budget_bytes=3 * 32 * 36 * 40 * 4 * 2)
+    res = vb.UncertaintyPipeline(cfg).run(x.cuda(), keep_maps=True, mean_argmax=True)
+    ids = [f"img{b}" for b in range(B)]
+    dicts = res.to_dicts(ids)
+    for b in range(B):
+        ref = vo.calculate_uncertainty(x[b])
+        for k, key in enumerate(MAPS):
+            got_map = res.maps[k, b].cpu().numpy()
+            np.testing.assert_allclose(got_map, ref[key].numpy(), rtol=RTOL, atol=ATOL)
+            e = dicts[key][ids[b]]
+            # aggregations of OUR map against the oracle's aggregation of the same map: tight
+            m64 = got_map.astype(np.float64)
+            pl = vo.patch_level_aggregation(m64, 10)
+            assert e["patch_level"]["bounding_box"] == pl["bounding_box"]
+            np.testing.assert_allclose(e["patch_level"]["max_score"], pl["max_score"], rtol=1e-12)
+            np.testing.assert_allclose(e["image_level"]["max_score"], m64.sum(), rtol=1e-12)
+            th = vo.threshold_aggregation(m64, threshold=thr[k])
+            np.testing.assert_allclose(e["threshold"]["max_score"], float(th["max_score"]), rtol=1e-12)
+            # and against the oracle end to end (reference maps): within the float tolerance
+            np.testing.assert_allclose(e["patch_level"]["max_score"],
+                                       vo.patch_level_aggregation(ref[key].numpy().astype(np.float64), 10)["max_score"], rtol=1e-5)
+        assert_argmax(res.mean_argmax[b], x[b], np.argmax(np.mean(x[b].numpy(), axis=0), axis=0))
+
+
+def test_full_size_properties(vb):
+    """BASELINE sizes, checked through size-independent properties (no oracle at this size)."""
+    n, c, s = 16, 4, (128, 128, 128)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.softmax(3 * torch.randn(1, n, c, *s, generator=g, device="cuda"), dim=2)
+    pipe = vb.UncertaintyPipeline(vb.AggregationConfig(patch_size=10, thresholds=(0.0, 0.0, -1.0)))
+    r = pipe.run(x, keep_maps=True)
+    pe, ee, mi = r.maps[0, 0], r.maps[1, 0], r.maps[2, 0]
+    assert torch.equal(mi, pe - ee)
+    assert pe.min().item() >= 0 and pe.max().item() <= np.log(4) * (1 + 1e-6)
+    assert mi.min().item() >= -1e-6  # Jensen: MI >= 0 up to rounding
+    sc = r.scores.cpu().numpy()[0]
+    V = float(np.prod(s))
+    assert sc[0, 2] == V and sc[2, 2] == V            # threshold 0 / -1 keeps every voxel
+    np.testing.assert_allclose(sc[:, 0], sc[:, 1], rtol=1e-15)  # so thr_sum == image sum
+    np.testing.assert_allclose(sc[:, 0], r.maps[:, 0].double().sum(dim=(1, 2, 3)).cpu().numpy(), rtol=1e-9)
+    # patch score bounded by 1000 * map max and >= mean box; sample permutation invariance
+    assert np.all(sc[:, 3] <= 1000 * r.maps[:, 0].amax(dim=(1, 2, 3)).cpu().numpy() * (1 + 1e-12))
+    assert np.all(sc[:, 3] >= sc[:, 0] / V * 1000 * (1 - 1e-9))
+    r2 = pipe.run(x[:, torch.randperm(n, device="cuda")], keep_maps=True)
+    np.testing.assert_allclose(r2.maps.cpu().numpy(), r.maps.cpu().numpy(), rtol=1e-5, atol=1e-6)

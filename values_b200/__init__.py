@@ -1,0 +1,28 @@
+"""values_b200 -- B200-native (sm_100a) implementation of the ValUES C2+C3 uncertainty hot
+path: fused PE/EE/MI maps, the evaluation/uncertainty_aggregation strategies and the
+sliding-window stitch accumulator, behind the reference's own Python entry points.
+
+Importing this package loads values_b200/lib/libvalues_b200.so and fails loudly if it is
+missing (there is no CPU fallback).  Build it with `python -m values_b200.build`.
+"""
+from . import _lib  # noqa: F401  (raises ValuesExtensionMissing when the .so is absent)
+from .aggregation import (aggregate_uncertainties, image_level_aggregation, map_reduce,
+                          normalize_maps, patch_level_aggregation, patch_max,
+                          threshold_aggregation)
+from .data_carrier import DataCarrier3D
+from .pipeline import AggregationConfig, PipelineResult, UncertaintyPipeline
+from .sharding import gather_scores, shard_range, shard_sizes
+from .stitching import patch_grid, stitch_accumulate, stitch_volume
+from .uncertainty import (FusedResult, caculcate_uncertainty_multiple_pred,
+                          calculate_one_minus_msr, calculate_uncertainty,
+                          calculate_uncertainty_multiple_pred, uncertainty_fused)
+
+__all__ = [
+    "calculate_uncertainty", "calculate_one_minus_msr", "caculcate_uncertainty_multiple_pred",
+    "calculate_uncertainty_multiple_pred", "uncertainty_fused", "FusedResult",
+    "patch_level_aggregation", "image_level_aggregation", "threshold_aggregation",
+    "aggregate_uncertainties", "patch_max", "map_reduce", "normalize_maps",
+    "DataCarrier3D", "patch_grid", "stitch_accumulate", "stitch_volume",
+    "UncertaintyPipeline", "AggregationConfig", "PipelineResult",
+    "shard_range", "shard_sizes", "gather_scores",
+]

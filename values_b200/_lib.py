@@ -1,0 +1,115 @@
+"""ctypes binding of libvalues_b200.so (the C-ABI declared in include/values_b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device is present
+when a compute entry point is called, this module raises -- loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libvalues_b200.so")
+
+F32, F64, BF16 = 0, 1, 2
+_DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
+
+OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
+
+
+class ValuesExtensionMissing(ImportError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ValuesExtensionMissing(
+            f"{LIB_PATH} not found. The values_b200 CUDA extension is required (there is no CPU "
+            "fallback); build it with `python -m values_b200.build` or `__graft_entry__.build()`."
+        )
+    lib = C.CDLL(LIB_PATH)
+    i64, vp, sz, dbl = C.c_int64, C.c_void_p, C.c_size_t, C.c_double
+    pi64, pdbl = C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    sig = {
+        "values_abi_version": (C.c_int, []),
+        "values_last_error": (C.c_char_p, []),
+        "values_launch_count": (i64, []),
+        "values_uncertainty_workspace_bytes": (sz, [i64, i64, C.c_int]),
+        "values_uncertainty_fused": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, i64, i64, i64,
+                                               vp, vp, vp, vp, vp, vp, pdbl, vp, sz, vp]),
+        "values_one_minus_msr": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, i64, vp, vp]),
+        "values_map_reduce_workspace_bytes": (sz, [i64, i64]),
+        "values_map_reduce": (C.c_int, [vp, C.c_int, i64, i64, i64, pdbl, C.c_int, vp, vp, sz, vp]),
+        "values_patch_max_workspace_bytes": (sz, [i64, pi64, pi64]),
+        "values_patch_max": (C.c_int, [vp, C.c_int, i64, i64, pi64, pi64, C.c_int, dbl, dbl,
+                                       vp, vp, vp, sz, vp]),
+        "values_stitch_accumulate": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, i64, i64, i64,
+                                               pi64, pi64, vp, C.c_int, vp, C.c_int, vp]),
+        "values_normalize_maps": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
+        fn.restype, fn.argtypes = res, args
+    if lib.values_abi_version() != 1:
+        raise ValuesExtensionMissing("libvalues_b200.so ABI version mismatch; rebuild it")
+    return lib
+
+
+lib = _load()
+EXPORTED = [
+    "values_abi_version", "values_last_error", "values_launch_count",
+    "values_uncertainty_workspace_bytes", "values_uncertainty_fused", "values_one_minus_msr",
+    "values_map_reduce_workspace_bytes", "values_map_reduce",
+    "values_patch_max_workspace_bytes", "values_patch_max", "values_stitch_accumulate",
+    "values_normalize_maps",
+]
+
+
+def check(rc: int) -> None:
+    if rc == OK:
+        return
+    msg = (lib.values_last_error() or b"").decode()
+    if rc == ERR_INVALID_ARG:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"values_b200 error {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib.values_launch_count())
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise TypeError(f"values_b200: unsupported dtype {dt} (float32, float64, bfloat16)") from None
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "values_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback. "
+            "For a CPU oracle see oracle/values_oracle.py (test infrastructure only)."
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def i64x3(vals):
+    return (C.c_int64 * 3)(*[int(v) for v in vals])
+
+
+def dbl_array(vals):
+    vals = [float(v) for v in vals]
+    return (C.c_double * len(vals))(*vals)

@@ -1,0 +1,230 @@
+"""C3 aggregation strategies on B200: drop-in mirrors of
+evaluation/uncertainty_aggregation/aggregate_uncertainties.py over kernels K2a / K2b.
+
+    patch_level_aggregation(image, patch_size, mean=False, **kwargs)     :13-31
+    image_level_aggregation(image, mean=False, **kwargs)                 :34-37
+    threshold_aggregation(image, threshold=None, threshold_path=None,
+                          pred_model=None, unc_type=None, mean=True)     :40-67
+    aggregate_uncertainties(exp_dataloader, aggregations)                :70-96
+
+`image` may be a numpy array (as medpy hands it to the reference) or a torch tensor; CUDA
+tensors are used in place.  Batched device-side forms (`patch_max`, `map_reduce`) return
+tensors and never synchronise.
+"""
+from __future__ import annotations
+
+import importlib
+import json
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ISCLOSE_RTOL, ISCLOSE_ATOL = 1e-5, 1e-8  # np.isclose defaults (aggregate_uncertainties.py:20)
+
+
+def _as_map(image, device: torch.device) -> torch.Tensor:
+    """numpy / torch -> contiguous CUDA fp32 or fp64 tensor (other dtypes widen to fp64,
+    as numpy/scipy would when combining with their fp64 ones-kernel)."""
+    if isinstance(image, np.ndarray):
+        if image.dtype not in (np.float32, np.float64):
+            image = image.astype(np.float64)
+        image = torch.from_numpy(np.ascontiguousarray(image))
+    if not isinstance(image, torch.Tensor):
+        raise TypeError(f"image must be a numpy array or torch tensor, got {type(image)}")
+    if image.dtype not in (torch.float32, torch.float64):
+        image = image.to(torch.float64)
+    if image.device.type != "cuda":
+        image = image.to(device, non_blocking=True)
+    return image.contiguous()
+
+
+# ------------------------------------------------------------------ device-side batched ops
+def patch_max(maps: torch.Tensor, patch_size, mean: bool = False,
+              rtol: float = ISCLOSE_RTOL, atol: float = ISCLOSE_ATOL
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """maps [M, *S] (CUDA fp32/fp64, 1 <= len(S) <= 3) -> (max_score fp64 [M], bbox_lo int64 [M, len(S)])."""
+    if maps.device.type != "cuda":
+        raise RuntimeError("patch_max expects a CUDA tensor (no CPU fallback)")
+    nd = maps.dim() - 1
+    if not 1 <= nd <= 3:
+        raise NotImplementedError("patch_level_aggregation supports 1-, 2- and 3-D images")
+    if isinstance(patch_size, (int, np.integer)):
+        patch_size = nd * [int(patch_size)]
+    if len(patch_size) != nd:
+        raise ValueError("patch_size must have one entry per image dimension")
+    maps = maps.contiguous()
+    M = maps.shape[0]
+    shape3 = [1] * (3 - nd) + list(maps.shape[1:])
+    patch3 = [1] * (3 - nd) + [int(p) for p in patch_size]
+    dev = maps.device
+    score = torch.empty(M, dtype=torch.float64, device=dev)
+    bbox = torch.empty((M, 3), dtype=torch.int64, device=dev)
+    sh, pa = _lib.i64x3(shape3), _lib.i64x3(patch3)
+    ws_bytes = _lib.lib.values_patch_max_workspace_bytes(M, sh, pa)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+    V = int(np.prod(shape3))
+    with torch.cuda.device(dev):
+        rc = _lib.lib.values_patch_max(maps.data_ptr(), _lib.dtype_code(maps.dtype), M, V, sh, pa,
+                                       int(bool(mean)), float(rtol), float(atol), score.data_ptr(),
+                                       bbox.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(dev))
+    _lib.check(rc)
+    return score, bbox[:, 3 - nd:]
+
+
+def map_reduce(maps: torch.Tensor, thresholds: Optional[Sequence[float]] = None) -> torch.Tensor:
+    """maps [M, *S] (CUDA fp32/fp64) -> fp64 [M, 3] = {sum, sum over v>=thr, count v>=thr};
+    map m uses thresholds[m % len(thresholds)]."""
+    if maps.device.type != "cuda":
+        raise RuntimeError("map_reduce expects a CUDA tensor (no CPU fallback)")
+    maps = maps.contiguous()
+    M = maps.shape[0]
+    V = int(np.prod(maps.shape[1:])) if maps.dim() > 1 else 1
+    dev = maps.device
+    out = torch.empty((M, 3), dtype=torch.float64, device=dev)
+    ws_bytes = _lib.lib.values_map_reduce_workspace_bytes(M, V)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+    thr, n_thr = None, 0
+    if thresholds is not None:
+        n_thr = len(thresholds)
+        thr = _lib.dbl_array(thresholds)
+    with torch.cuda.device(dev):
+        rc = _lib.lib.values_map_reduce(maps.data_ptr(), _lib.dtype_code(maps.dtype), M, V, V, thr,
+                                        n_thr, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                        _lib.stream_ptr(dev))
+    _lib.check(rc)
+    return out
+
+
+def normalize_maps(maps: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
+    """maps [M, *S] / clip(count [*S], 1) -> fp64 [M, *S] (data_carrier_3D.py:215-217, 326-329)."""
+    maps = maps.contiguous()
+    count = count.to(torch.float64).contiguous()
+    M = maps.shape[0]
+    V = count.numel()
+    if maps[0].numel() != V:
+        raise ValueError("count must match the spatial shape of the maps")
+    out = torch.empty(maps.shape, dtype=torch.float64, device=maps.device)
+    with torch.cuda.device(maps.device):
+        rc = _lib.lib.values_normalize_maps(maps.data_ptr(), _lib.dtype_code(maps.dtype), M, V, V,
+                                            count.data_ptr(), out.data_ptr(),
+                                            _lib.stream_ptr(maps.device))
+    _lib.check(rc)
+    return out
+
+
+# ------------------------------------------------------------------ reference entry points
+def patch_level_aggregation(image, patch_size, mean: bool = False, **kwargs) -> Dict:
+    """Drop-in for aggregate_uncertainties.py:13-31."""
+    dev = _lib.require_cuda()
+    img = _as_map(image, dev)
+    try:
+        score, bbox = patch_max(img.unsqueeze(0), patch_size, mean=mean)
+    except ValueError as e:  # image smaller than the patch: scipy's message (probe)
+        raise ValueError(str(e)) from None
+    lo = bbox[0].tolist()
+    if lo and lo[0] < 0:  # NaN map: the reference's np.where(...)[0] raises IndexError
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+    if isinstance(patch_size, (int, np.integer)):
+        patch_size = len(lo) * [int(patch_size)]
+    return {
+        "max_score": float(score[0].item()),
+        "bounding_box": [(int(i), int(i + patch_size[d])) for d, i in enumerate(lo)],
+    }
+
+
+def image_level_aggregation(image, mean: bool = False, **kwargs):
+    """Drop-in for aggregate_uncertainties.py:34-37 (bare float when mean=True)."""
+    dev = _lib.require_cuda()
+    img = _as_map(image, dev)
+    total = float(map_reduce(img.unsqueeze(0))[0, 0].item())
+    if mean:
+        return float(total / img.numel())
+    return {"max_score": total}
+
+
+def _resolve_threshold(threshold, threshold_path, pred_model, unc_type):
+    if threshold is None:  # aggregate_uncertainties.py:48-60
+        if threshold_path is None:
+            raise Exception("A threshold needs to be provided for threshold aggregation!")
+        with open(threshold_path) as f:
+            threshold_json = json.load(f)
+        if pred_model is None or unc_type is None:
+            raise Exception(
+                "If you want to load the threshold from a json file, you have to provide the "
+                "prediction model and the uncertainty type"
+            )
+        unc_type_split = unc_type.split("_")[0]
+        threshold = threshold_json[pred_model][f"Mean {unc_type_split} threshold"]
+    return threshold
+
+
+def threshold_aggregation(image, threshold=None, threshold_path=None, pred_model=None,
+                          unc_type=None, mean: bool = True) -> Dict:
+    """Drop-in for aggregate_uncertainties.py:40-67.  `max_score` is a Python float (the
+    reference returns numpy scalars, np.float32(0.0) on an empty fp32 selection, which
+    json.dumps cannot serialise -- SURVEY.md section 8a9)."""
+    threshold = _resolve_threshold(threshold, threshold_path, pred_model, unc_type)
+    dev = _lib.require_cuda()
+    img = _as_map(image, dev)
+    _, s, n = map_reduce(img.unsqueeze(0), [threshold])[0].tolist()
+    if mean and n > 0:
+        return {"max_score": s / n, "threshold": threshold}
+    return {"max_score": s, "threshold": threshold}
+
+
+# dotted paths the reference's hydra configs use (evaluation/configs/tasks/*.yaml) -> ours
+_REF_MODULE = "evaluation.uncertainty_aggregation.aggregate_uncertainties"
+TARGETS = {
+    f"{_REF_MODULE}.patch_level_aggregation": patch_level_aggregation,
+    f"{_REF_MODULE}.image_level_aggregation": image_level_aggregation,
+    f"{_REF_MODULE}.threshold_aggregation": threshold_aggregation,
+}
+
+
+def _instantiate(cfg, **kwargs):
+    """Minimal stand-in for hydra.utils.instantiate(cfg, **kwargs) for `_target_` callables
+    (aggregate_uncertainties.py:81-86).  Reference dotted paths resolve to this module."""
+    cfg = dict(cfg)
+    target = cfg.pop("_target_")
+    fn = TARGETS.get(target)
+    if fn is None:
+        mod, _, name = target.rpartition(".")
+        fn = getattr(importlib.import_module(mod), name)
+    cfg.update(kwargs)
+    return fn(**cfg)
+
+
+def aggregate_uncertainties(exp_dataloader, aggregations, load_fn=None, save: bool = True) -> Dict:
+    """Drop-in for aggregate_uncertainties.py:70-96: for every uncertainty type and image, run
+    every configured aggregation and write `aggregated_<unc>.json`.
+
+    `load_fn(path) -> ndarray` defaults to medpy.io.load (as the reference) when medpy is
+    installed.  Unlike the reference the image is loaded and uploaded ONCE per image, not once
+    per aggregation (:77-79).  Returns {unc: {image_key: {aggregation: result}}}.
+    """
+    if load_fn is None:
+        from medpy.io import load as _medpy_load  # not installed in the build image
+
+        def load_fn(path):
+            return _medpy_load(path)[0]
+
+    dev = _lib.require_cuda()
+    results = {}
+    for unc, unc_path in exp_dataloader.unc_path_dict.items():
+        all_uncs = {}
+        for image_id in exp_dataloader.image_ids:
+            key = f"{image_id}{exp_dataloader.exp_version.unc_ending}"
+            all_uncs[key] = {}
+            unc_image = _as_map(load_fn(unc_path / key), dev)
+            for aggregation in aggregations:
+                all_uncs[key][aggregation] = _instantiate(
+                    aggregations[aggregation], image=unc_image,
+                    pred_model=exp_dataloader.exp_version.pred_model, unc_type=unc)
+        results[unc] = all_uncs
+        if save:
+            with open(exp_dataloader.dataset_path / f"aggregated_{unc}.json", "w") as f:
+                json.dump(all_uncs, f, indent=4)
+    return results

@@ -1,0 +1,415 @@
+// K2: the evaluation/uncertainty_aggregation strategies on stored uncertainty maps.
+//   K2a map_reduce : image-level sum + threshold sum/count   (aggregate_uncertainties.py:34-37, 40-67)
+//   K2b patch_max  : fp64 sliding box-sum, max, first-isclose index      (:13-31)
+//   normalize_maps : map / clip(count, 1) in fp64                        (data_carrier_3D.py:326-329)
+// All HBM/L2-bound; algorithmic bytes = sizeof(T) per map voxel, outputs O(1).
+#include "common.cuh"
+
+namespace vb {
+
+// =============================================================================== K2a
+struct ThrTable { double v[16]; int n; };
+
+constexpr int kReduceEPT = 16;  // elements per thread per block
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) map_reduce_kernel(const T* __restrict__ maps, int64_t V,
+                                                              int64_t stride_m, int64_t bpm,
+                                                              ThrTable thr,
+                                                              double* __restrict__ partials) {
+    __shared__ double red[3 * 8];
+    const int64_t m = blockIdx.x / bpm;
+    const int64_t blk = blockIdx.x - m * bpm;
+    const T* src = maps + m * stride_m;
+    const double t = thr.n > 0 ? thr.v[m % thr.n] : __longlong_as_double(0x7ff0000000000000LL);
+    double acc[3] = {0.0, 0.0, 0.0};
+    const int64_t base = blk * (int64_t)(kThreads * kReduceEPT) + threadIdx.x;
+#pragma unroll 4
+    for (int i = 0; i < kReduceEPT; ++i) {
+        const int64_t v = base + (int64_t)i * kThreads;
+        if (v < V) {
+            const double x = (double)In<T>::load_one(src + v);
+            acc[0] += x;
+            if (x >= t) { acc[1] += x; acc[2] += 1.0; }
+        }
+    }
+    block_sum<3>(acc, red);
+    if (threadIdx.x == 0) {
+        double* dst = partials + (int64_t)blockIdx.x * 3;
+        dst[0] = acc[0]; dst[1] = acc[1]; dst[2] = acc[2];
+    }
+}
+
+// =============================================================================== normalize
+template <typename T>
+__global__ void __launch_bounds__(kThreads) normalize_kernel(const T* __restrict__ maps, int64_t V,
+                                                             int64_t stride_m, int64_t bpm,
+                                                             const double* __restrict__ count,
+                                                             double* __restrict__ out) {
+    const int64_t m = blockIdx.x / bpm;
+    const int64_t v = (blockIdx.x - m * bpm) * kThreads + threadIdx.x;
+    if (v >= V) return;
+    const double c = fmax(count[v], 1.0);  // np.clip(count, 1, None)
+    out[m * V + v] = (double)In<T>::load_one(maps + m * stride_m + v) / c;
+}
+
+// =============================================================================== K2b
+constexpr int kTX = 32;   // outputs per tile along the contiguous axis
+constexpr int kTY = 16;   // outputs per tile along axis 1
+constexpr int kSeg = 8;   // outputs per sliding x-segment
+constexpr int kOwn = kTX * kTY / kThreads;  // outputs owned per thread per plane (2)
+
+struct PatchParams {
+    const void* maps;
+    int64_t stride_m;
+    int64_t D0, D1, D2;   // map shape (unused leading axes = 1)
+    int64_t O0, O1, O2;   // number of windows per axis
+    int p0, p1, p2;
+    int tiles_x, tiles_y, chunks_z, zc;
+    int64_t ntiles;
+    double denom;         // prod(patch) when mean, else 1
+    int mean_flag;
+    double rtol, atol;
+    double* tile_max;               // [M, ntiles]
+    const double* gmax;             // [M]       (pass 2)
+    unsigned long long* best;       // [M]       (pass 2)
+};
+
+__device__ __forceinline__ bool np_isclose(double a, double b, double rtol, double atol) {
+    // numpy.isclose(a, b): |a-b| <= atol + rtol*|b|; equal infinities are close; NaN never is
+    if (a == b) return true;
+    if (isinf(a) || isinf(b)) return false;
+    return fabs(a - b) <= atol + rtol * fabs(b);
+}
+__device__ __forceinline__ double nanmax(double m, double v) {  // np.max: NaN propagates
+    return (v > m || v != v) ? v : m;
+}
+
+template <typename T, int PASS>
+__global__ void __launch_bounds__(kThreads) patch_kernel(const PatchParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = kTY + prm.p1 - 1;            // input rows per plane tile
+    const int W = kTX + prm.p2 - 1;            // input cols per plane tile
+    const int pitch = W | 1;                   // odd pitch: rows land in distinct 64-bit banks
+    double* in_tile = reinterpret_cast<double*>(smem_raw);          // [R][pitch]
+    double* rowsum = in_tile + (size_t)R * pitch;                   // [R][kTX]
+    double* ring = rowsum + (size_t)R * kTX;                        // [p0][kTX*kTY]
+    __shared__ double red[8];
+
+    const int64_t m = blockIdx.y;
+    int tile = blockIdx.x;
+    const int tx_i = tile % prm.tiles_x; tile /= prm.tiles_x;
+    const int ty_i = tile % prm.tiles_y; tile /= prm.tiles_y;
+    const int zc_i = tile;
+    if (PASS == 2) {
+        const double tm = prm.tile_max[m * prm.ntiles + blockIdx.x];
+        if (!np_isclose(tm, prm.gmax[m], prm.rtol, prm.atol)) return;  // exact cull (monotone)
+    }
+    const int64_t x0 = (int64_t)tx_i * kTX, y0 = (int64_t)ty_i * kTY;
+    const int64_t zo0 = (int64_t)zc_i * prm.zc;                       // first output plane
+    const int64_t zo1 = min(zo0 + prm.zc, prm.O0);                    // one past last output plane
+    const T* src = reinterpret_cast<const T*>(prm.maps) + m * prm.stride_m;
+    const int tid = threadIdx.x;
+    const int lx = tid % kTX, ly = tid / kTX;  // owns outputs (ly + 8k, lx)
+
+    double run[kOwn];
+#pragma unroll
+    for (int k = 0; k < kOwn; ++k) run[k] = 0.0;
+    double tmax = -__longlong_as_double(0x7ff0000000000000LL);
+    unsigned long long tbest = ~0ull;
+    const double gmax = PASS == 2 ? prm.gmax[m] : 0.0;
+
+    const int64_t nplanes = (zo1 - zo0) + prm.p0 - 1;
+    for (int64_t zi = 0; zi < nplanes; ++zi) {
+        const int64_t z = zo0 + zi;
+        // 1. stage the input plane tile (coalesced along x), widened to fp64
+        const T* plane = src + z * prm.D1 * prm.D2;
+        for (int idx = tid; idx < R * W; idx += kThreads) {
+            const int r = idx / W, cx = idx - r * W;
+            const int64_t y = y0 + r, x = x0 + cx;
+            double v = 0.0;
+            if (y < prm.D1 && x < prm.D2) v = (double)In<T>::load_one(plane + y * prm.D2 + x);
+            in_tile[r * pitch + cx] = v;
+        }
+        __syncthreads();
+        // 2. x-pass: sliding sums in registers, kSeg outputs per task
+        for (int task = tid; task < R * (kTX / kSeg); task += kThreads) {
+            const int r = task % R, seg = task / R;
+            const double* row = in_tile + r * pitch + seg * kSeg;
+            double s = 0.0;
+            for (int k = 0; k < prm.p2; ++k) s += row[k];
+            double* dst = rowsum + r * kTX + seg * kSeg;
+            dst[0] = s;
+#pragma unroll
+            for (int i = 1; i < kSeg; ++i) {
+                s += row[i + prm.p2 - 1] - row[i - 1];
+                dst[i] = s;
+            }
+        }
+        __syncthreads();
+        // 3. y-pass (direct) + z-pass (sliding over a private ring column)
+        const int slot = (int)(zi % prm.p0);
+#pragma unroll
+        for (int k = 0; k < kOwn; ++k) {
+            const int oy = ly + k * (kThreads / kTX);
+            double s2 = 0.0;
+            for (int j = 0; j < prm.p1; ++j) s2 += rowsum[(oy + j) * kTX + lx];
+            double* rs = ring + (size_t)slot * (kTX * kTY) + oy * kTX + lx;
+            const double old = zi >= prm.p0 ? *rs : 0.0;
+            *rs = s2;
+            run[k] += s2 - old;
+            if (zi >= prm.p0 - 1) {
+                const int64_t oz = z - (prm.p0 - 1);
+                const int64_t y = y0 + oy, x = x0 + lx;
+                if (y < prm.O1 && x < prm.O2) {
+                    const double v = prm.mean_flag ? run[k] / prm.denom : run[k];
+                    if (PASS == 1) {
+                        tmax = nanmax(tmax, v);
+                    } else if (np_isclose(v, gmax, prm.rtol, prm.atol)) {
+                        const unsigned long long lin =
+                            (unsigned long long)((oz * prm.O1 + y) * prm.O2 + x);
+                        tbest = lin < tbest ? lin : tbest;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (PASS == 1) {
+        // block max with NaN propagation
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmax = nanmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if (lane == 0) red[warp] = tmax;
+        __syncthreads();
+        if (tid == 0) {
+            double mm = red[0];
+            for (int w = 1; w < kThreads / 32; ++w) mm = nanmax(mm, red[w]);
+            prm.tile_max[m * prm.ntiles + blockIdx.x] = mm;
+        }
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, tbest, o);
+            tbest = other < tbest ? other : tbest;
+        }
+        if ((tid & 31) == 0 && tbest != ~0ull) atomicMin(prm.best + m, tbest);  // min is order-free
+    }
+}
+
+// one block per map: global max over tile maxima; reset the first-index slot
+__global__ void __launch_bounds__(kThreads) patch_select_kernel(const double* __restrict__ tile_max,
+                                                                int64_t ntiles,
+                                                                double* __restrict__ gmax,
+                                                                double* __restrict__ max_score,
+                                                                unsigned long long* __restrict__ best) {
+    __shared__ double red[8];
+    const int64_t m = blockIdx.x;
+    double mm = -__longlong_as_double(0x7ff0000000000000LL);
+    for (int64_t i = threadIdx.x; i < ntiles; i += kThreads) mm = nanmax(mm, tile_max[m * ntiles + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mm = nanmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double g = red[0];
+        for (int w = 1; w < kThreads / 32; ++w) g = nanmax(g, red[w]);
+        gmax[m] = g;
+        max_score[m] = g;
+        best[m] = ~0ull;
+    }
+}
+
+__global__ void patch_finish_kernel(const unsigned long long* __restrict__ best, int64_t M,
+                                    int64_t O1, int64_t O2, int64_t* __restrict__ bbox_lo) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const unsigned long long b = best[m];
+    if (b == ~0ull) {  // no window is close to the max (NaN map): the reference raises IndexError
+        bbox_lo[3 * m] = bbox_lo[3 * m + 1] = bbox_lo[3 * m + 2] = -1;
+        return;
+    }
+    const int64_t lin = (int64_t)b;
+    bbox_lo[3 * m + 2] = lin % O2;
+    bbox_lo[3 * m + 1] = (lin / O2) % O1;
+    bbox_lo[3 * m] = lin / (O2 * O1);
+}
+
+struct PatchPlan {
+    int64_t O0, O1, O2;
+    int tiles_x, tiles_y, chunks_z, zc;
+    int64_t ntiles;
+    size_t smem;
+};
+
+static int make_patch_plan(const int64_t* shape, const int64_t* patch, PatchPlan& pl) {
+    for (int d = 0; d < 3; ++d) {
+        if (shape[d] <= 0 || patch[d] <= 0)
+            return set_error(VALUES_ERR_INVALID_ARG, "patch_max: non-positive shape/patch");
+        if (patch[d] > shape[d])
+            return set_error(VALUES_ERR_INVALID_ARG,
+                             "For 'valid' mode, one must be at least as large as the other in "
+                             "every dimension (axis %d: image %lld < patch %lld)",
+                             d, (long long)shape[d], (long long)patch[d]);
+    }
+    pl.O0 = shape[0] - patch[0] + 1; pl.O1 = shape[1] - patch[1] + 1; pl.O2 = shape[2] - patch[2] + 1;
+    pl.tiles_x = (int)ceil_div(pl.O2, kTX);
+    pl.tiles_y = (int)ceil_div(pl.O1, kTY);
+    pl.zc = 32;
+    pl.chunks_z = (int)ceil_div(pl.O0, pl.zc);
+    pl.ntiles = (int64_t)pl.tiles_x * pl.tiles_y * pl.chunks_z;
+    const int64_t R = kTY + patch[1] - 1, W = kTX + patch[2] - 1;
+    pl.smem = (size_t)(R * (W | 1) + R * kTX + patch[0] * kTX * kTY) * sizeof(double);
+    if (pl.smem > 227 * 1024)
+        return set_error(VALUES_ERR_UNSUPPORTED,
+                         "patch_max: patch (%lld,%lld,%lld) needs %zu B of shared memory (> 227 KB)",
+                         (long long)patch[0], (long long)patch[1], (long long)patch[2], pl.smem);
+    if (pl.ntiles > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: too many tiles");
+    return VALUES_OK;
+}
+
+template <typename T>
+static int run_patch(PatchParams prm, const PatchPlan& pl, int64_t M, double* gmax,
+                     double* max_score, int64_t* bbox_lo, cudaStream_t st) {
+    auto k1 = patch_kernel<T, 1>;
+    auto k2 = patch_kernel<T, 2>;
+    if (pl.smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess)
+            return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute failed");
+    }
+    for (int64_t m0 = 0; m0 < M; m0 += 65535) {  // gridDim.y limit
+        const int64_t mc = std::min<int64_t>(65535, M - m0);
+        PatchParams q = prm;
+        q.maps = reinterpret_cast<const T*>(prm.maps) + m0 * prm.stride_m;
+        q.tile_max = prm.tile_max + m0 * pl.ntiles;
+        q.gmax = gmax + m0;
+        q.best = prm.best + m0;
+        const dim3 grid((unsigned)pl.ntiles, (unsigned)mc);
+        k1<<<grid, kThreads, pl.smem, st>>>(q);
+        int rc = check_launch("patch_kernel<1>");
+        if (rc) return rc;
+        patch_select_kernel<<<(unsigned)mc, kThreads, 0, st>>>(q.tile_max, pl.ntiles, gmax + m0,
+                                                                max_score + m0, q.best);
+        if ((rc = check_launch("patch_select_kernel"))) return rc;
+        k2<<<grid, kThreads, pl.smem, st>>>(q);
+        if ((rc = check_launch("patch_kernel<2>"))) return rc;
+    }
+    patch_finish_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(prm.best, M, pl.O1, pl.O2, bbox_lo);
+    return check_launch("patch_finish_kernel");
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" size_t values_map_reduce_workspace_bytes(int64_t M, int64_t V) {
+    if (M <= 0 || V <= 0) return 0;
+    return (size_t)(M * ceil_div(V, kThreads * kReduceEPT) * 3) * sizeof(double);
+}
+
+extern "C" int values_map_reduce(const void* maps, int dtype, int64_t M, int64_t V,
+                                 int64_t stride_m, const double* thresholds_host, int n_thresholds,
+                                 double* out, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    if (!maps || !out) return set_error(VALUES_ERR_INVALID_ARG, "map_reduce: NULL pointer");
+    if (M < 0 || V < 0 || n_thresholds < 0 || n_thresholds > 16)
+        return set_error(VALUES_ERR_INVALID_ARG, "map_reduce: bad sizes");
+    if (M == 0) return VALUES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (V == 0) {
+        if (cudaMemsetAsync(out, 0, (size_t)M * 3 * sizeof(double), st) != cudaSuccess)
+            return set_error(VALUES_ERR_CUDA, "map_reduce: memset failed");
+        return VALUES_OK;
+    }
+    const size_t need = values_map_reduce_workspace_bytes(M, V);
+    if (!workspace || workspace_bytes < need)
+        return set_error(VALUES_ERR_WORKSPACE, "map_reduce: workspace %zu < %zu", workspace_bytes, need);
+    ThrTable thr{};
+    thr.n = thresholds_host ? n_thresholds : 0;
+    for (int i = 0; i < thr.n; ++i) thr.v[i] = thresholds_host[i];
+    const int64_t bpm = ceil_div(V, kThreads * kReduceEPT);
+    if (bpm * M > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "map_reduce: grid too large");
+    const unsigned grid = (unsigned)(bpm * M);
+    double* partials = reinterpret_cast<double*>(workspace);
+    switch (dtype) {
+        case VALUES_F32:
+            map_reduce_kernel<float><<<grid, kThreads, 0, st>>>((const float*)maps, V, stride_m, bpm, thr, partials);
+            break;
+        case VALUES_F64:
+            map_reduce_kernel<double><<<grid, kThreads, 0, st>>>((const double*)maps, V, stride_m, bpm, thr, partials);
+            break;
+        default: return set_error(VALUES_ERR_INVALID_ARG, "map_reduce: dtype must be f32 or f64");
+    }
+    int rc = check_launch("map_reduce_kernel");
+    if (rc) return rc;
+    return launch_reduce_partials(partials, M, bpm, 3, out, st);
+}
+
+extern "C" int values_normalize_maps(const void* maps, int dtype, int64_t M, int64_t V,
+                                     int64_t stride_m, const double* count, double* out,
+                                     void* stream) {
+    if (!maps || !count || !out) return set_error(VALUES_ERR_INVALID_ARG, "normalize: NULL pointer");
+    if (M < 0 || V < 0) return set_error(VALUES_ERR_INVALID_ARG, "normalize: bad sizes");
+    if (M == 0 || V == 0) return VALUES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t bpm = ceil_div(V, kThreads);
+    if (bpm * M > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "normalize: grid too large");
+    const unsigned grid = (unsigned)(bpm * M);
+    switch (dtype) {
+        case VALUES_F32:
+            normalize_kernel<float><<<grid, kThreads, 0, st>>>((const float*)maps, V, stride_m, bpm, count, out);
+            break;
+        case VALUES_F64:
+            normalize_kernel<double><<<grid, kThreads, 0, st>>>((const double*)maps, V, stride_m, bpm, count, out);
+            break;
+        default: return set_error(VALUES_ERR_INVALID_ARG, "normalize: dtype must be f32 or f64");
+    }
+    return check_launch("normalize_kernel");
+}
+
+// workspace layout: tile_max [M, ntiles] | gmax [M] | best [M]
+extern "C" size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* shape3_host,
+                                                   const int64_t* patch3_host) {
+    PatchPlan pl;
+    if (M <= 0 || !shape3_host || !patch3_host) return 0;
+    if (make_patch_plan(shape3_host, patch3_host, pl) != VALUES_OK) return 0;
+    return (size_t)(M * pl.ntiles + 2 * M) * sizeof(double);
+}
+
+extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t stride_m,
+                                const int64_t* shape3_host, const int64_t* patch3_host,
+                                int mean_flag, double rtol, double atol, double* max_score,
+                                int64_t* bbox_lo, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    if (!maps || !shape3_host || !patch3_host || !max_score || !bbox_lo)
+        return set_error(VALUES_ERR_INVALID_ARG, "patch_max: NULL pointer");
+    if (M < 0) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: M < 0");
+    PatchPlan pl;
+    int rc = make_patch_plan(shape3_host, patch3_host, pl);
+    if (rc) return rc;
+    if (M == 0) return VALUES_OK;
+    const size_t need = (size_t)(M * pl.ntiles + 2 * M) * sizeof(double);
+    if (!workspace || workspace_bytes < need)
+        return set_error(VALUES_ERR_WORKSPACE, "patch_max: workspace %zu < %zu", workspace_bytes, need);
+    PatchParams prm{};
+    prm.maps = maps; prm.stride_m = stride_m;
+    prm.D0 = shape3_host[0]; prm.D1 = shape3_host[1]; prm.D2 = shape3_host[2];
+    prm.O0 = pl.O0; prm.O1 = pl.O1; prm.O2 = pl.O2;
+    prm.p0 = (int)patch3_host[0]; prm.p1 = (int)patch3_host[1]; prm.p2 = (int)patch3_host[2];
+    prm.tiles_x = pl.tiles_x; prm.tiles_y = pl.tiles_y; prm.chunks_z = pl.chunks_z; prm.zc = pl.zc;
+    prm.ntiles = pl.ntiles;
+    prm.mean_flag = mean_flag ? 1 : 0;
+    prm.denom = mean_flag ? (double)patch3_host[0] * (double)patch3_host[1] * (double)patch3_host[2] : 1.0;
+    prm.rtol = rtol; prm.atol = atol;
+    double* ws = reinterpret_cast<double*>(workspace);
+    prm.tile_max = ws;
+    double* gmax = ws + M * pl.ntiles;
+    prm.best = reinterpret_cast<unsigned long long*>(gmax + M);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case VALUES_F32: return run_patch<float>(prm, pl, M, gmax, max_score, bbox_lo, st);
+        case VALUES_F64: return run_patch<double>(prm, pl, M, gmax, max_score, bbox_lo, st);
+        default: return set_error(VALUES_ERR_INVALID_ARG, "patch_max: dtype must be f32 or f64");
+    }
+}

@@ -1,0 +1,138 @@
+"""DataCarrier3D on B200: the stitch accumulator + result container of
+uncertainty_modeling/data_carrier_3D.py, with the accumulators resident in HBM.
+
+Same entry point and `.data` layout as the reference (data_carrier_3D.py:99-135):
+
+    carrier.concat_data(batch, softmax_pred, n_pred=1, pred_idx=0, sigma=None)
+    carrier.data[image_path] = {label_paths, softmax_pred [n_pred, C, X,Y,Z] fp64 raw sums,
+                                num_predictions [C, X,Y,Z] fp64, data [X,Y,Z] fp64,
+                                seg [R, X,Y,Z] int32, (sigma), + the three uncertainty maps}
+
+The arrays are CUDA tensors instead of numpy arrays (no device->host copy per patch, which
+is what the reference does at :161); `numpy_data()` materialises the reference's numpy
+layout.  The reference hardcodes C=2 (:120); here C is taken from the softmax batch.
+File output (NIfTI via medpy, :181-371) is host I/O and out of scope; `normalized()`
+provides the arithmetic of the save path (:208-217, 253-259, 281-285, 323-363).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .aggregation import normalize_maps
+from .stitching import stitch_accumulate
+from .uncertainty import MAP_KEYS, uncertainty_fused
+
+
+class DataCarrier3D:
+    def __init__(self, device: Optional[torch.device] = None, accum_dtype: torch.dtype = torch.float64):
+        self.data: Dict[str, Dict] = {}
+        self.save_dir = None
+        self.device = device
+        self.accum_dtype = accum_dtype  # fp64 = reference parity (np.zeros default)
+
+    def _dev(self) -> torch.device:
+        if self.device is None:
+            self.device = _lib.require_cuda()
+        return self.device
+
+    def concat_data(self, batch: Dict, softmax_pred: torch.Tensor, n_pred: int = 1,
+                    pred_idx: int = 0, sigma: torch.Tensor = None) -> None:
+        """Drop-in for data_carrier_3D.py:99-179.  `softmax_pred` [B, C, p,p,p] (any device);
+        batch["crop_idx"][i] = ((x0,x1),(y0,y1),(z0,z1)).  Patches of one call that belong to
+        the same image may overlap: the kernel sums them output-stationary in list order."""
+        dev = self._dev()
+        sp = softmax_pred.detach()
+        if sp.device != dev:
+            sp = sp.to(dev, non_blocking=True)
+        if sp.dtype not in (torch.float32, torch.float64, torch.bfloat16):
+            sp = sp.float()
+        sg = None
+        if sigma is not None:
+            sg = sigma.detach().to(dev)
+            if sg.dtype not in (torch.float32, torch.float64, torch.bfloat16):
+                sg = sg.float()
+        n_cls = sp.shape[1]
+        groups: Dict[str, list] = {}
+        for index, image_path in enumerate(batch["image_paths"]):
+            if image_path not in self.data:
+                size = tuple(int(s) for s in batch["org_image_size"][index])
+                entry = {
+                    "label_paths": batch["label_paths"][index],
+                    "softmax_pred": torch.zeros((n_pred, n_cls) + size, dtype=self.accum_dtype, device=dev),
+                    "_count": torch.zeros(size, dtype=torch.float64, device=dev),
+                    "data": torch.zeros(size, dtype=torch.float64, device=dev),
+                }
+                if sg is not None:
+                    entry["sigma"] = torch.zeros((n_pred, n_cls) + size, dtype=self.accum_dtype, device=dev)
+                n_raters = len(batch["label_paths"][index]) if batch["label_paths"][index] is not None else 0
+                entry["seg"] = torch.zeros((n_raters,) + size, dtype=torch.int32, device=dev)
+                # reference layout: [C, X, Y, Z] count (all class planes identical, :127-129)
+                entry["num_predictions"] = entry["_count"].unsqueeze(0).expand((n_cls,) + size)
+                self.data[image_path] = entry
+            groups.setdefault(image_path, []).append(index)
+        for image_path, idxs in groups.items():
+            entry = self.data[image_path]
+            lo = np.asarray([[batch["crop_idx"][i][d][0] for d in range(3)] for i in idxs], dtype=np.int32)
+            crop_lo = torch.from_numpy(lo).to(dev)
+            pidx = torch.tensor(idxs, dtype=torch.int32, device=dev)
+            stitch_accumulate(sp.unsqueeze(0), crop_lo, entry["softmax_pred"][pred_idx:pred_idx + 1],
+                              entry["_count"] if pred_idx == 0 else None, patch_index=pidx, accumulate=True)
+            if sg is not None:
+                stitch_accumulate(sg.unsqueeze(0), crop_lo, entry["sigma"][pred_idx:pred_idx + 1],
+                                  None, patch_index=pidx, accumulate=True)
+            if pred_idx == 0:  # image / label slabs (:138-153): bookkeeping, plain torch slicing
+                for i in idxs:
+                    (x0, x1), (y0, y1), (z0, z1) = batch["crop_idx"][i]
+                    if "data" in batch and batch["data"] is not None:
+                        img = batch["data"][i].detach().to(dev).squeeze()
+                        entry["data"][x0:x1, y0:y1, z0:z1] += img.to(torch.float64)
+                    if "seg" in batch and batch["seg"] is not None and entry["seg"].shape[0] > 0:
+                        seg = batch["seg"][:, i].detach().to(dev).to(torch.int32)
+                        entry["seg"][:, x0:x1, y0:y1, z0:z1] += seg.reshape(
+                            (entry["seg"].shape[0], x1 - x0, y1 - y0, z1 - z0))
+
+    # ------------------------------------------------------------------ save-path arithmetic
+    def normalized(self, image_path: str) -> Dict[str, torch.Tensor]:
+        """What save_data writes (data_carrier_3D.py:208-217, 253-259, 281-285, 323-363), on device:
+        softmax / clip(count,1), its mean over samples, mean_seg / per-sample arg-max (uint8)
+        and every uncertainty map / clip(count,1) as fp64."""
+        v = self.data[image_path]
+        cnt = v["_count"]
+        n_pred, n_cls = v["softmax_pred"].shape[:2]
+        size = tuple(cnt.shape)
+        sm = normalize_maps(v["softmax_pred"].reshape((n_pred * n_cls,) + size), cnt)
+        sm = sm.reshape((n_pred, n_cls) + size)
+        res = uncertainty_fused(sm.unsqueeze(0), maps=False, mean_argmax=True, sample_argmax=True)
+        out = {
+            "softmax_pred": sm,
+            "mean_softmax_pred": sm.mean(dim=0) if n_pred > 1 else None,
+            "mean_seg": res.mean_argmax[0],
+            "pred_seg": res.sample_argmax[0],
+        }
+        present = [k for k in MAP_KEYS if k in v]
+        if present:
+            maps = torch.stack([v[k].to(cnt.device) for k in present])
+            norm = normalize_maps(maps, cnt)
+            for i, k in enumerate(present):
+                out[k] = norm[i]
+        return out
+
+    def numpy_data(self) -> Dict[str, Dict]:
+        """The reference's `.data` layout with numpy arrays (torch fp32 maps stay torch CPU
+        tensors, as test_3D.py:533 stores them)."""
+        out = {}
+        for key, v in self.data.items():
+            e = {}
+            for name, val in v.items():
+                if name == "_count":
+                    continue
+                if isinstance(val, torch.Tensor):
+                    e[name] = val.cpu() if name in MAP_KEYS else val.cpu().numpy()
+                else:
+                    e[name] = val
+            out[key] = e
+        return out

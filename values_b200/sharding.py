@@ -1,0 +1,47 @@
+"""Multi-GPU sharding of the hot path: volumes are independent, so the
+image list is split contiguously over ranks with no data-path collective; the only exchange
+is one all_gather of the per-image score table (NCCL over NVLink on GPUs, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of rank `rank`; the first n_items % world_size ranks get one extra."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_items: int, world_size: int) -> List[int]:
+    return [shard_range(n_items, r, world_size)[1] - shard_range(n_items, r, world_size)[0]
+            for r in range(world_size)]
+
+
+def gather_scores(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+    """local [n_local, ...] (this rank's shard, in shard_range order) -> [n_items, ...] on every
+    rank.  Shards are padded to the largest shard so a single all_gather_into_tensor suffices
+    (~170 B per image: latency-bound)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        if local.shape[0] != n_items:
+            raise ValueError("single process: local shard must hold every item")
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = shard_sizes(n_items, world)
+    if local.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank}: shard has {local.shape[0]} rows, expected {sizes[rank]}")
+    pad = max(sizes)
+    tail = local.shape[1:]
+    buf = torch.zeros((pad,) + tuple(tail), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    out = torch.empty((world * pad,) + tuple(tail), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
+    out = out.view((world, pad) + tuple(tail))
+    return torch.cat([out[r, : sizes[r]] for r in range(world)], dim=0)
