@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ValUES C2+C3 uncertainty hot path on B200.
+
+One "step" = one pass of the fused pipeline (K1 PE/EE/MI + arg-max + image/threshold sums,
+K2 patch max, score gather) over one pool of synthetic softmax stacks per rank.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5]
+
+Under torchrun (N > 1) every rank processes its own pool (volume-sharded, weak scaling); the
+only collective is the all_gather of the per-image score table.  Rank 0 prints ONE JSON line.
+`--impl reference` times the CPU oracle port of the reference (oracle/values_oracle.py --
+the reference itself is pure Python and cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # BASELINE.json configs[4] per-volume shape (the config BASELINE.md quotes the 70% target on)
+    "cfg5": dict(name="cfg5: 128^3 volumes, N=16 samples, C=4 classes, fp32; PE/EE/MI + arg-max + "
+                      "image-level + threshold + patch-level(10) aggregation",
+                 N=16, C=4, spatial=(128, 128, 128), dtype="f32", pool=32, e2e_pool=4, patch=10, cfg=5),
+    # BASELINE.json configs[1]
+    "cfg2": dict(name="cfg2: LIDC 64^3 patches, N=5, C=2, fp32; patch-level(10) + threshold aggregation",
+                 N=5, C=2, spatial=(64, 64, 64), dtype="f32", pool=1024, e2e_pool=256, patch=10, cfg=2),
+    # BASELINE.json configs[3] (19 classes + the zero channel test_2D appends)
+    "cfg4": dict(name="cfg4: 1024x2048 images, N=10, C=19+1, fp32; all C3 aggregations",
+                 N=10, C=20, spatial=(1024, 2048), dtype="f32", pool=6, e2e_pool=2, patch=10, cfg=4),
+    "cfg4bf16": dict(name="cfg4: 1024x2048 images, N=10, C=19+1, bf16; all C3 aggregations",
+                     N=10, C=20, spatial=(1024, 2048), dtype="bf16", pool=6, e2e_pool=2, patch=10, cfg=4),
+}
+DTYPES = {"f32": torch.float32, "bf16": torch.bfloat16, "f64": torch.float64}
+METRIC, UNIT = "uncertainty_voxels_per_sec", "voxels/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, flag in zip(names, r[3:7]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_stack(gen, n_vol, wl, device, dtype):
+    """Synthetic softmax stacks [n_vol, N, C, *S]: logits ~ N(0, 3^2), softmax over classes."""
+    shape = (wl["N"], wl["C"]) + tuple(wl["spatial"])
+    out = torch.empty((n_vol,) + shape, dtype=dtype, device=device)
+    for i in range(n_vol):
+        logits = torch.randn(shape, generator=gen, device=device, dtype=torch.float32) * 3.0
+        out[i] = torch.softmax(logits, dim=1).to(dtype)
+        del logits
+    return out
+
+
+def algorithmic_bytes_per_voxel(wl):
+    es = {"f32": 4, "bf16": 2, "f64": 8}[wl["dtype"]]
+    return wl["N"] * wl["C"] * es + 3 * 4 + 1
+
+
+# ------------------------------------------------------------------------------ CPU oracle arm
+def oracle_volume(vo, x_cpu, thr, patch):
+    """The reference's path for ONE volume on the host: C2 maps, then all three aggregations on
+    each map (FFT box-sum exactly as the reference calls scipy)."""
+    d = vo.calculate_uncertainty(x_cpu)
+    mean_seg = vo.mean_argmax(x_cpu)
+    out = {}
+    for k, key in enumerate(("pred_entropy", "aleatoric_uncertainty", "epistemic_uncertainty")):
+        m = d[key].numpy()
+        out[key] = (vo.patch_level_aggregation(m, patch, method="fft"),
+                    vo.image_level_aggregation(m), vo.threshold_aggregation(m, threshold=thr[k]))
+    return out, mean_seg
+
+
+def host_stack(wl, seed, n_vol):
+    g = torch.Generator().manual_seed(seed)
+    shape = (n_vol, wl["N"], wl["C"]) + tuple(wl["spatial"])
+    x = torch.softmax(torch.randn(shape, generator=g) * 3.0, dim=2)
+    # the reference feeds fp64 on the 3D path (test_3D.py:532) and fp32 on the 2D path
+    return x.double() if len(wl["spatial"]) == 3 else x
+
+
+def run_cpu_sample(wl, n_vol, repeats=1):
+    from oracle import values_oracle as vo
+
+    x = host_stack(wl, 4321, n_vol)
+    thr = (0.5, 0.4, 0.05)
+    V = int(np.prod(wl["spatial"]))
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        for i in range(n_vol):
+            oracle_volume(vo, x[i], thr, wl["patch"])
+    dt = time.perf_counter() - t0
+    return n_vol * repeats * V / dt, dt
+
+
+def reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    V = int(np.prod(wl["spatial"]))
+    from oracle import values_oracle as vo
+
+    x = host_stack(wl, 4321, 1)
+    thr = (0.5, 0.4, 0.05)
+    for _ in range(args.warmup):
+        oracle_volume(vo, x[0], thr, wl["patch"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_volume(vo, x[0], thr, wl["patch"])
+    dt = time.perf_counter() - t0
+    value = args.steps * V / dt
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if len(wl["spatial"]) == 3 else "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "volumes_per_step": 1,
+                   "note": "CPU oracle port of the reference (pure-Python reference cannot travel); "
+                           "rank 0 only, host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x 1 volume of the workload shape, "
+                                   f"os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--pool", type=int, default=0, help="override volumes per rank per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.pool:
+        wl["pool"] = args.pool
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        reference_arm(args, wl, rank)
+        return
+
+    import torch.distributed as dist
+
+    import values_b200 as vb
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = DTYPES[wl["dtype"]]
+    V = int(np.prod(wl["spatial"]))
+    pool = wl["pool"]
+    gen = torch.Generator(device=dev).manual_seed(1234 + 1000 * wl["cfg"] + rank)
+    stack = make_stack(gen, pool, wl, dev, dtype)  # resident in HBM before the timed region
+    pool_bytes = stack.numel() * stack.element_size()
+
+    # thresholds: 0.98-quantile of a pilot map per uncertainty type (stand-in for threshold_analysis.json)
+    pilot = vb.uncertainty_fused(stack[:1])
+    sub = slice(None, None, max(1, V // (1 << 20)))
+    thr = tuple(float(torch.quantile(m.reshape(-1)[sub].float(), 0.98).item())
+                for m in (pilot.pred_entropy, pilot.expected_entropy, pilot.mutual_information))
+    del pilot
+    cfg = vb.AggregationConfig(patch_size=wl["patch"], thresholds=thr)
+    pipe = vb.UncertaintyPipeline(cfg)
+    k1_events = []
+    pipe.k1_timer = k1_events  # (start, end, n_volumes) per K1 launch, recorded on the launch stream
+
+    def step():
+        res = pipe.run(stack, mean_argmax=True)
+        table = res.scores.reshape(pool, -1)
+        if world > 1:
+            table = vb.gather_scores(table, pool * world)
+        return table
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    k1_events.clear()
+    launches0 = vb._lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            table = step()
+        e1.record()
+        sync_all()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = vb._lib.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    total_vox = float(pool) * V * world * args.steps
+    value = total_vox / (elapsed_ms * 1e-3)
+
+    # roofline of the dominant kernel (K1), from events recorded inside the timed region
+    k1_ms = [s.elapsed_time(e) for s, e, _ in k1_events]
+    k1_vols = [n for _, _, n in k1_events]
+    bpv = algorithmic_bytes_per_voxel(wl)
+    peak, peak_src = measured_peak_gbs()
+    k1_avg_ms = sum(k1_ms) / len(k1_ms)
+    k1_bytes = bpv * V * (sum(k1_vols) / len(k1_vols))
+    achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "kernel": "k1 fused N x C reduction",
+                "algorithmic_bytes_per_voxel": bpv, "avg_launch_ms": k1_avg_ms,
+                "launches_timed": len(k1_ms), "k1_share_of_step": sum(k1_ms) / elapsed_ms,
+                "peak_source": peak_src}
+
+    # end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(vb, wl, cfg, dev, stack, world, args)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = 2 if V >= (1 << 21) else (4 if V >= (1 << 20) else 32)
+        cpu_value, cpu_s = run_cpu_sample(wl, n_cpu)
+        cpu = {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n_cpu} volume(s) of the workload shape through oracle/values_oracle.py "
+                         f"(fp64 3D / fp32 2D as the reference feeds it), {cpu_s:.1f} s, "
+                         f"os.cpu_count()={os.cpu_count()}"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+            "config": {"workload": wl["name"], "volumes_per_rank_per_step": pool,
+                       "pool_bytes_per_rank": pool_bytes,
+                       "l2": "inputs (pool >> 126 MB L2) stream from HBM every step",
+                       "aggregations": "image_level + threshold(0.98-quantile pilot) + patch_level(10)",
+                       "sharding": f"volumes sharded over {world} rank(s), score table all_gather"},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(), "e2e": e2e,
+            "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(vb, wl, cfg, dev, stack, world, args):
+    """Same metric through the public API from pinned HOST buffers: per step, H2D of that step's
+    stacks (double-buffered against compute on a copy stream) and D2H of the score table."""
+    import torch.distributed as dist
+
+    n = min(wl["e2e_pool"], stack.shape[0])
+    V = int(np.prod(wl["spatial"]))
+    host = torch.empty((n,) + tuple(stack.shape[1:]), dtype=stack.dtype, pin_memory=True)
+    host.copy_(stack[:n])
+    host_scores = torch.empty((n, 3 * 7), dtype=torch.float64, pin_memory=True)
+    pipe = vb.UncertaintyPipeline(cfg)
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [torch.empty_like(stack[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
+
+    def step():
+        for i in range(n):
+            s = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[s])
+                bufs[s].copy_(host[i], non_blocking=True)
+                ready[s].record(copy_stream)
+            main.wait_event(ready[s])
+            res = pipe.run(bufs[s].unsqueeze(0), mean_argmax=True)
+            host_scores[i].copy_(res.scores.reshape(-1), non_blocking=True)
+            freed[s].record(main)
+        main.synchronize()  # the caller reads the scores: the step ends when they are on the host
+
+    for s in range(2):
+        freed[s].record(main)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    steps = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": n * V * world * steps / (ms * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": int(host.numel() * host.element_size()),
+            "d2h_bytes_per_step": int(host_scores.numel() * 8), "volumes_per_step": n, "steps": steps,
+            "api": "UncertaintyPipeline.run on pinned host stacks (H2D double-buffered) -> host score table"}
+
+
+if __name__ == "__main__":
+    main()

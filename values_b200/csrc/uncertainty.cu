@@ -346,10 +346,11 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
                                         uint8_t* mean_argmax, uint8_t* sample_argmax,
                                         double* scores, const double* thresholds_host,
                                         void* workspace, size_t workspace_bytes, void* stream) {
-    if (!probs) return set_error(VALUES_ERR_INVALID_ARG, "probs is NULL");
     if (B < 0 || N <= 0 || C <= 0 || V < 0)
         return set_error(VALUES_ERR_INVALID_ARG, "bad sizes B=%lld N=%lld C=%lld V=%lld",
                          (long long)B, (long long)N, (long long)C, (long long)V);
+    if (B == 0 || V == 0) return VALUES_OK;  // empty stack: nothing to do (pointers may be NULL)
+    if (!probs) return set_error(VALUES_ERR_INVALID_ARG, "probs is NULL");
     if ((mean_argmax || sample_argmax) && C > 256)
         return set_error(VALUES_ERR_UNSUPPORTED, "uint8 arg-max needs C <= 256");
     if (stride_b < 0 || stride_n < 0 || stride_c < 0)
@@ -389,9 +390,9 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
 
 extern "C" int values_one_minus_msr(const void* probs, int dtype, int64_t B, int64_t C, int64_t V,
                                     int64_t stride_b, int64_t stride_c, void* out, void* stream) {
-    if (!probs || !out) return set_error(VALUES_ERR_INVALID_ARG, "NULL pointer");
     if (B < 0 || C <= 0 || V < 0) return set_error(VALUES_ERR_INVALID_ARG, "bad sizes");
     if (B == 0 || V == 0) return VALUES_OK;
+    if (!probs || !out) return set_error(VALUES_ERR_INVALID_ARG, "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t bpv = ceil_div(V, kThreads);
     if (bpv * B > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");

@@ -83,6 +83,9 @@ class UncertaintyPipeline:
     def __init__(self, cfg: Optional[AggregationConfig] = None):
         self.cfg = cfg or AggregationConfig()
         self._maps_buf: Optional[torch.Tensor] = None
+        # optional list; when set, (start_event, end_event, n_volumes) is appended per K1 launch
+        # (CUDA events on the launching stream -- bench.py's roofline measurement)
+        self.k1_timer: Optional[list] = None
 
     def _chunk(self, B: int, V: int) -> int:
         per_volume = 3 * V * 4
@@ -120,8 +123,14 @@ class UncertaintyPipeline:
                 buf = torch.empty((3, nb) + spatial, dtype=torch.float32, device=dev) if cb < B else all_maps
             else:
                 buf = self._maps_buf[:3 * nb * V].view((3, nb) + spatial)
+            if self.k1_timer is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             res = uncertainty_fused(probs[b0:b1], maps=True, mean_argmax=mean_argmax, scores=True,
                                     thresholds=thr, out_maps=buf)
+            if self.k1_timer is not None:
+                ev1.record()
+                self.k1_timer.append((ev0, ev1, nb))
             scores[b0:b1, :, :3] = res.scores
             if mean_argmax:
                 am[b0:b1] = res.mean_argmax
