@@ -223,6 +223,8 @@ def test_c3_golden(vb):
     ((64, 64, 64), 10, np.float64), ((70, 45, 33), 10, np.float32), ((128, 96), 10, np.float32),
     ((40, 50, 60), [3, 7, 12], np.float64), ((10, 10, 10), 10, np.float64), ((300,), 10, np.float32),
     ((35, 200, 37), [20, 1, 30], np.float32), ((256, 478), 10, np.float32),
+    ((20, 30, 100), [3, 4, 40], np.float64),   # patch wider than a warp -> tiled shared-memory fallback
+    ((9, 70, 33), [9, 33, 32], np.float32), ((1024, 2048), 10, np.float32),
 ])
 def test_c3_patch_vs_oracle(vb, vo, shape, patch, dtype):
     rng = np.random.default_rng(sum(shape) * 7 + len(shape))
@@ -354,7 +356,7 @@ def test_pipeline_vs_oracle(vb, vo):
     B, n, c, spatial = 5, 5, 2, (32, 36, 40)
     x = softmax_stack(99, B * n, c, spatial).reshape(B, n, c, *spatial)
     thr = (0.45, 0.4, 0.03)
-    cfg = vb.AggregationConfig(patch_size=10, thresholds=thr, l2_budget_bytes=3 * 32 * 36 * 40 * 4 * 2)
+    cfg = vb.AggregationConfig(patch_size=10, thresholds=thr, l2_budget_bytes=3 * 32 * 36 * 40 * 12 * 2)
     res = vb.UncertaintyPipeline(cfg).run(x.cuda(), keep_maps=True, mean_argmax=True)
     ids = [f"img{b}" for b in range(B)]
     dicts = res.to_dicts(ids)

@@ -235,6 +235,141 @@ __global__ void patch_finish_kernel(const unsigned long long* __restrict__ best,
     bbox_lo[3 * m] = lin / (O2 * O1);
 }
 
+// ------------------------------------------------------------------ K2b fast path (p2 <= 32)
+// Two sync-free streaming kernels with an L2-resident fp64 intermediate:
+//   A  box_zx_kernel: thread = (y, x) column marching over a z-chunk.  z-box by a sliding sum
+//      (one new + one leaving plane per step, restarted every chunk so rounding cannot drift),
+//      x-box by warp shuffles (binary decomposition of p2), result XZ[z', y, x'] (fp64).
+//   B  box_y_kernel: thread = (z', x') marching over a y-chunk with a sliding sum over XZ;
+//      pass 1 records the per-CTA max, pass 2 re-walks only CTAs whose max is np.isclose to the
+//      global max and takes the minimum C-order index (atomicMin: order-free, deterministic).
+constexpr int kZC = 16;   // outputs per z-chunk (kernel A)
+constexpr int kYC = 32;   // outputs per y-chunk (kernel B)
+constexpr int kRowsA = kThreads / 32;  // y rows per CTA in kernel A
+
+struct StreamParams {
+    const void* maps;
+    int64_t stride_m;
+    int64_t D0, D1, D2, O0, O1, O2;
+    int p0, p1, p2;
+    int xs;                 // valid outputs per warp window = 32 - p2 + 1
+    int nxw, nyg, nzc;      // kernel A grid decomposition
+    int64_t nlb;            // kernel B: CTAs over (z', x')
+    int nyc;                // kernel B: y-chunks
+    int64_t ntiles;         // kernel B CTAs per map = nlb * nyc
+    double* xz;             // [M, O0, D1, O2]
+    double denom;
+    int mean_flag;
+    double rtol, atol;
+    double* tile_max;
+    const double* gmax;
+    unsigned long long* best;
+};
+
+__device__ __forceinline__ double shfl_down_f64(double v, int delta) {
+    return __shfl_down_sync(0xffffffffu, v, delta);
+}
+// sum of lanes [lane, lane + p) for every lane (valid where lane + p <= 32)
+__device__ __forceinline__ double warp_window_sum(double v, int p) {
+    double s = v, acc = 0.0;
+    int off = 0;
+    for (int bit = 1; bit <= p; bit <<= 1) {
+        if (p & bit) { acc += shfl_down_f64(s, off); off += bit; }
+        if ((bit << 1) <= p) s += shfl_down_f64(s, bit);
+    }
+    return acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) box_zx_kernel(const StreamParams prm) {
+    int64_t idx = blockIdx.x;
+    const int xw = (int)(idx % prm.nxw); idx /= prm.nxw;
+    const int yg = (int)(idx % prm.nyg); idx /= prm.nyg;
+    const int zc = (int)(idx % prm.nzc); idx /= prm.nzc;
+    const int64_t m = idx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t x = (int64_t)xw * prm.xs + lane;
+    const int64_t y = (int64_t)yg * kRowsA + warp;
+    if (y >= prm.D1) return;  // warp-uniform
+    const bool in_x = x < prm.D2;
+    const bool out_x = lane < prm.xs && x < prm.O2;
+    const int64_t z0 = (int64_t)zc * kZC;
+    const int64_t z1 = min(z0 + kZC, prm.O0);
+    const int64_t plane = prm.D1 * prm.D2;
+    const T* src = reinterpret_cast<const T*>(prm.maps) + m * prm.stride_m + y * prm.D2 + (in_x ? x : 0);
+    double* dst = prm.xz + ((m * prm.O0) * prm.D1 + y) * prm.O2 + (out_x ? x : 0);
+    const int64_t oplane = prm.D1 * prm.O2;
+    double run = 0.0;
+    for (int k = 0; k < prm.p0; ++k) {
+        const double v = in_x ? (double)In<T>::load_one(src + (z0 + k) * plane) : 0.0;
+        run += v;
+    }
+    for (int64_t z = z0;; ++z) {
+        const double xz = warp_window_sum(run, prm.p2);
+        if (out_x) dst[z * oplane] = xz;
+        if (z + 1 >= z1) break;
+        const double add = in_x ? (double)In<T>::load_one(src + (z + prm.p0) * plane) : 0.0;
+        const double sub = in_x ? (double)In<T>::load_one(src + z * plane) : 0.0;
+        run += add - sub;
+    }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kThreads) box_y_kernel(const StreamParams prm) {
+    __shared__ double red[8];
+    const int64_t m = blockIdx.y;
+    const int64_t lb = blockIdx.x % prm.nlb;
+    const int yc = (int)(blockIdx.x / prm.nlb);
+    if (PASS == 2) {
+        const double tm = prm.tile_max[m * prm.ntiles + blockIdx.x];
+        if (!np_isclose(tm, prm.gmax[m], prm.rtol, prm.atol)) return;
+    }
+    const int64_t L = lb * kThreads + threadIdx.x;     // flattened (z', x')
+    const bool valid = L < prm.O0 * prm.O2;
+    const int64_t zq = valid ? L / prm.O2 : 0;
+    const int64_t xq = valid ? L - zq * prm.O2 : 0;
+    const int64_t y0 = (int64_t)yc * kYC;
+    const int64_t y1 = min(y0 + kYC, prm.O1);
+    const double* src = prm.xz + ((m * prm.O0 + zq) * prm.D1) * prm.O2 + xq;
+    double tmax = -__longlong_as_double(0x7ff0000000000000LL);
+    unsigned long long tbest = ~0ull;
+    const double gmax = PASS == 2 ? prm.gmax[m] : 0.0;
+    if (valid) {
+        double run = 0.0;
+        for (int k = 0; k < prm.p1; ++k) run += src[(y0 + k) * prm.O2];
+        for (int64_t y = y0;; ++y) {
+            const double v = prm.mean_flag ? run / prm.denom : run;
+            if (PASS == 1) {
+                tmax = nanmax(tmax, v);
+            } else if (np_isclose(v, gmax, prm.rtol, prm.atol)) {
+                const unsigned long long lin = (unsigned long long)((zq * prm.O1 + y) * prm.O2 + xq);
+                tbest = lin < tbest ? lin : tbest;
+            }
+            if (y + 1 >= y1) break;
+            run += src[(y + prm.p1) * prm.O2] - src[y * prm.O2];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (PASS == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmax = nanmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if (lane == 0) red[warp] = tmax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double mm = red[0];
+            for (int w = 1; w < kThreads / 32; ++w) mm = nanmax(mm, red[w]);
+            prm.tile_max[m * prm.ntiles + blockIdx.x] = mm;
+        }
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, tbest, o);
+            tbest = other < tbest ? other : tbest;
+        }
+        if (lane == 0 && tbest != ~0ull) atomicMin(prm.best + m, tbest);
+    }
+}
+
 struct PatchPlan {
     int64_t O0, O1, O2;
     int tiles_x, tiles_y, chunks_z, zc;
@@ -296,6 +431,67 @@ static int run_patch(PatchParams prm, const PatchPlan& pl, int64_t M, double* gm
         if ((rc = check_launch("patch_kernel<2>"))) return rc;
     }
     patch_finish_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(prm.best, M, pl.O1, pl.O2, bbox_lo);
+    return check_launch("patch_finish_kernel");
+}
+
+struct StreamPlan {
+    int64_t O0, O1, O2;
+    int xs, nxw, nyg, nzc, nyc;
+    int64_t nlb, ntiles, xz_per_map;
+};
+
+static bool stream_path_ok(const int64_t* patch) { return patch[2] <= 32; }
+
+static int make_stream_plan(const int64_t* shape, const int64_t* patch, StreamPlan& sp) {
+    PatchPlan pl;  // reuse the argument checks (ValueError when patch > image)
+    for (int d = 0; d < 3; ++d) {
+        if (shape[d] <= 0 || patch[d] <= 0)
+            return set_error(VALUES_ERR_INVALID_ARG, "patch_max: non-positive shape/patch");
+        if (patch[d] > shape[d])
+            return set_error(VALUES_ERR_INVALID_ARG,
+                             "For 'valid' mode, one must be at least as large as the other in "
+                             "every dimension (axis %d: image %lld < patch %lld)",
+                             d, (long long)shape[d], (long long)patch[d]);
+    }
+    (void)pl;
+    sp.O0 = shape[0] - patch[0] + 1; sp.O1 = shape[1] - patch[1] + 1; sp.O2 = shape[2] - patch[2] + 1;
+    sp.xs = 32 - (int)patch[2] + 1;
+    sp.nxw = (int)ceil_div(sp.O2, sp.xs);
+    sp.nyg = (int)ceil_div(shape[1], kRowsA);
+    sp.nzc = (int)ceil_div(sp.O0, kZC);
+    sp.nlb = ceil_div(sp.O0 * sp.O2, kThreads);
+    sp.nyc = (int)ceil_div(sp.O1, kYC);
+    sp.ntiles = sp.nlb * sp.nyc;
+    sp.xz_per_map = sp.O0 * shape[1] * sp.O2;
+    if (sp.ntiles > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: too many tiles");
+    return VALUES_OK;
+}
+
+template <typename T>
+static int run_patch_stream(StreamParams prm, const StreamPlan& sp, int64_t M, double* gmax,
+                            double* max_score, int64_t* bbox_lo, cudaStream_t st) {
+    const int64_t gridA = (int64_t)sp.nxw * sp.nyg * sp.nzc * M;
+    if (gridA > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: grid too large");
+    box_zx_kernel<T><<<(unsigned)gridA, kThreads, 0, st>>>(prm);
+    int rc = check_launch("box_zx_kernel");
+    if (rc) return rc;
+    for (int64_t m0 = 0; m0 < M; m0 += 65535) {  // gridDim.y limit
+        const int64_t mc = std::min<int64_t>(65535, M - m0);
+        StreamParams q = prm;
+        q.xz = prm.xz + m0 * sp.xz_per_map;
+        q.tile_max = prm.tile_max + m0 * sp.ntiles;
+        q.gmax = gmax + m0;
+        q.best = prm.best + m0;
+        const dim3 grid((unsigned)sp.ntiles, (unsigned)mc);
+        box_y_kernel<1><<<grid, kThreads, 0, st>>>(q);
+        if ((rc = check_launch("box_y_kernel<1>"))) return rc;
+        patch_select_kernel<<<(unsigned)mc, kThreads, 0, st>>>(q.tile_max, sp.ntiles, gmax + m0,
+                                                                max_score + m0, q.best);
+        if ((rc = check_launch("patch_select_kernel"))) return rc;
+        box_y_kernel<2><<<grid, kThreads, 0, st>>>(q);
+        if ((rc = check_launch("box_y_kernel<2>"))) return rc;
+    }
+    patch_finish_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(prm.best, M, sp.O1, sp.O2, bbox_lo);
     return check_launch("patch_finish_kernel");
 }
 
@@ -368,11 +564,17 @@ extern "C" int values_normalize_maps(const void* maps, int dtype, int64_t M, int
     return check_launch("normalize_kernel");
 }
 
-// workspace layout: tile_max [M, ntiles] | gmax [M] | best [M]
+// workspace layout (streaming path): xz [M, O0, D1, O2] | tile_max [M, ntiles] | gmax [M] | best [M]
+//                  (tiled fallback): tile_max [M, ntiles] | gmax [M] | best [M]
 extern "C" size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* shape3_host,
                                                    const int64_t* patch3_host) {
-    PatchPlan pl;
     if (M <= 0 || !shape3_host || !patch3_host) return 0;
+    if (stream_path_ok(patch3_host)) {
+        StreamPlan sp;
+        if (make_stream_plan(shape3_host, patch3_host, sp) != VALUES_OK) return 0;
+        return (size_t)(M * sp.xz_per_map + M * sp.ntiles + 2 * M) * sizeof(double);
+    }
+    PatchPlan pl;
     if (make_patch_plan(shape3_host, patch3_host, pl) != VALUES_OK) return 0;
     return (size_t)(M * pl.ntiles + 2 * M) * sizeof(double);
 }
@@ -382,13 +584,43 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
                                 int mean_flag, double rtol, double atol, double* max_score,
                                 int64_t* bbox_lo, void* workspace, size_t workspace_bytes,
                                 void* stream) {
-    if (!maps || !shape3_host || !patch3_host || !max_score || !bbox_lo)
-        return set_error(VALUES_ERR_INVALID_ARG, "patch_max: NULL pointer");
+    if (!shape3_host || !patch3_host) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: NULL shape");
     if (M < 0) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: M < 0");
+    if (dtype != VALUES_F32 && dtype != VALUES_F64)
+        return set_error(VALUES_ERR_INVALID_ARG, "patch_max: dtype must be f32 or f64");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* ws = reinterpret_cast<double*>(workspace);
+    const double denom =
+        mean_flag ? (double)patch3_host[0] * (double)patch3_host[1] * (double)patch3_host[2] : 1.0;
+    if (stream_path_ok(patch3_host)) {
+        StreamPlan sp;
+        int rc = make_stream_plan(shape3_host, patch3_host, sp);
+        if (rc) return rc;
+        if (M == 0) return VALUES_OK;
+        if (!maps || !max_score || !bbox_lo) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: NULL pointer");
+        const size_t need = (size_t)(M * sp.xz_per_map + M * sp.ntiles + 2 * M) * sizeof(double);
+        if (!workspace || workspace_bytes < need)
+            return set_error(VALUES_ERR_WORKSPACE, "patch_max: workspace %zu < %zu", workspace_bytes, need);
+        StreamParams prm{};
+        prm.maps = maps; prm.stride_m = stride_m;
+        prm.D0 = shape3_host[0]; prm.D1 = shape3_host[1]; prm.D2 = shape3_host[2];
+        prm.O0 = sp.O0; prm.O1 = sp.O1; prm.O2 = sp.O2;
+        prm.p0 = (int)patch3_host[0]; prm.p1 = (int)patch3_host[1]; prm.p2 = (int)patch3_host[2];
+        prm.xs = sp.xs; prm.nxw = sp.nxw; prm.nyg = sp.nyg; prm.nzc = sp.nzc;
+        prm.nlb = sp.nlb; prm.nyc = sp.nyc; prm.ntiles = sp.ntiles;
+        prm.denom = denom; prm.mean_flag = mean_flag ? 1 : 0; prm.rtol = rtol; prm.atol = atol;
+        prm.xz = ws;
+        prm.tile_max = ws + M * sp.xz_per_map;
+        double* gmax = prm.tile_max + M * sp.ntiles;
+        prm.best = reinterpret_cast<unsigned long long*>(gmax + M);
+        if (dtype == VALUES_F32) return run_patch_stream<float>(prm, sp, M, gmax, max_score, bbox_lo, st);
+        return run_patch_stream<double>(prm, sp, M, gmax, max_score, bbox_lo, st);
+    }
     PatchPlan pl;
     int rc = make_patch_plan(shape3_host, patch3_host, pl);
     if (rc) return rc;
     if (M == 0) return VALUES_OK;
+    if (!maps || !max_score || !bbox_lo) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: NULL pointer");
     const size_t need = (size_t)(M * pl.ntiles + 2 * M) * sizeof(double);
     if (!workspace || workspace_bytes < need)
         return set_error(VALUES_ERR_WORKSPACE, "patch_max: workspace %zu < %zu", workspace_bytes, need);
@@ -400,16 +632,11 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
     prm.tiles_x = pl.tiles_x; prm.tiles_y = pl.tiles_y; prm.chunks_z = pl.chunks_z; prm.zc = pl.zc;
     prm.ntiles = pl.ntiles;
     prm.mean_flag = mean_flag ? 1 : 0;
-    prm.denom = mean_flag ? (double)patch3_host[0] * (double)patch3_host[1] * (double)patch3_host[2] : 1.0;
+    prm.denom = denom;
     prm.rtol = rtol; prm.atol = atol;
-    double* ws = reinterpret_cast<double*>(workspace);
     prm.tile_max = ws;
     double* gmax = ws + M * pl.ntiles;
     prm.best = reinterpret_cast<unsigned long long*>(gmax + M);
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (dtype) {
-        case VALUES_F32: return run_patch<float>(prm, pl, M, gmax, max_score, bbox_lo, st);
-        case VALUES_F64: return run_patch<double>(prm, pl, M, gmax, max_score, bbox_lo, st);
-        default: return set_error(VALUES_ERR_INVALID_ARG, "patch_max: dtype must be f32 or f64");
-    }
+    if (dtype == VALUES_F32) return run_patch<float>(prm, pl, M, gmax, max_score, bbox_lo, st);
+    return run_patch<double>(prm, pl, M, gmax, max_score, bbox_lo, st);
 }

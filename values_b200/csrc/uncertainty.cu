@@ -45,10 +45,33 @@ __device__ __forceinline__ void load_elems(const T* p, typename In<T>::acc_t (&o
     }
 }
 
-// acc (+)= p*log(p), NaN terms skipped; fp32 accumulator (test_3D.py:490-494, 500-504)
+// log(p) for finite normal p > 0, <= 1.06 ulp over every mantissa (exhaustive check in
+// tools/fit_log_poly.py).  CUDA's logf spends ~35 issue slots per element on special cases
+// (zero, negative, denormal, inf); here the caller's `p > 0` predicate already covers what the
+// NaN-skip rule needs, which keeps K1 under the HBM roofline instead of issue-bound:
+//   p = m * 2^e, m in [2/3, 4/3), f = m - 1;  log(p) = e*ln2 + f + f^2*Q(f), Q degree 7.
+// Denormals give a finite wrong log; times p (< 1.2e-38) the term is below any tolerance.
+__device__ __forceinline__ float fast_logf(float p) {
+    const int i = __float_as_int(p);
+    const int e = (i - 0x3f2aaaab) & 0xff800000;      // exponent field, scaled by 2^23
+    const float f = __int_as_float(i - e) - 1.0f;
+    float q = 0.13979104161262512f;
+    q = fmaf(q, f, -0.15397904813289642f);
+    q = fmaf(q, f, 0.14004801213741302f);
+    q = fmaf(q, f, -0.1641434133052826f);
+    q = fmaf(q, f, 0.20010659098625183f);
+    q = fmaf(q, f, -0.2500789761543274f);
+    q = fmaf(q, f, 0.3333320617675781f);
+    q = fmaf(q, f, -0.49999934434890747f);
+    const float r = fmaf(q * f, f, f);
+    return fmaf((float)e, 8.262958317573066e-08f /* ln2 * 2^-23 */, r);
+}
+
+// acc += p*log(p), NaN terms skipped (test_3D.py:490-494, 500-504).  A term is NaN exactly when
+// p is 0 (0 * -inf), negative (log -> NaN) or NaN, i.e. when !(p > 0); +inf is NOT skipped.
 __device__ __forceinline__ void accum_term(float& acc, float p) {
-    const float t = p * logf(p);
-    acc = (t == t) ? acc + t : acc;
+    const float t = fmaf(p, fast_logf(p), acc);
+    acc = (p > 0.f) ? t : acc;  // select, not a branch
 }
 __device__ __forceinline__ void accum_term(float& acc, double p) {
     const double t = p * log(p);
@@ -110,7 +133,7 @@ __device__ __forceinline__ void k1_epilogue(const K1Params& prm, int64_t b, int6
         for (int j = 0; j < VEC; ++j) {
             const A m = getS(c, j) / invN_den;  // mean: true division (torch.mean / np.mean)
             if (c == 0) best[j] = m; else argmax_update(m, c, best[j], idx[j]);
-            if (prm.need_ent) accum_term(pe[j], m);
+            if (CT > 0 || prm.need_ent) accum_term(pe[j], m);
         }
     }
     const float nf = (float)prm.N;
@@ -148,9 +171,10 @@ __device__ __forceinline__ void k1_write_partials(const K1Params& prm, double (&
     }
 }
 
-// ---- class sums in registers (compile-time C)
-template <typename T, int CT, int VEC>
-__global__ void __launch_bounds__(kThreads) k1_reg_kernel(const K1Params prm) {
+// ---- class sums in registers (compile-time C): the fast path.  Always computes the three
+// maps; per-sample arg-max and the arg-max-only mode go through the shared-memory kernel.
+template <typename T, int CT, int VEC, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k1_reg_kernel(const K1Params prm) {
     using A = typename In<T>::acc_t;
     const int64_t b = blockIdx.x / prm.blocks_per_vol;
     const int64_t blk = blockIdx.x - b * prm.blocks_per_vol;
@@ -162,13 +186,27 @@ __global__ void __launch_bounds__(kThreads) k1_reg_kernel(const K1Params prm) {
         const T* base = reinterpret_cast<const T*>(prm.probs) + b * prm.sb + v0;
         A S[CT][VEC];
         float E[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) E[j] = 0.f;
-#pragma unroll 2
-        for (int64_t n = 0; n < prm.N; ++n) {
+        {   // sample 0 initialises the class sums (torch.mean / np.mean start from the first row)
             A p[CT][VEC];
 #pragma unroll
-            for (int c = 0; c < CT; ++c) load_elems<T, VEC>(base + n * prm.sn + c * prm.sc, p[c]);
+            for (int c = 0; c < CT; ++c) load_elems<T, VEC>(base + c * prm.sc, p[c]);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) E[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    S[c][j] = p[c][j];
+                    accum_term(E[j], p[c][j]);
+                }
+            }
+        }
+#pragma unroll 1
+        for (int64_t n = 1; n < prm.N; ++n) {
+            A p[CT][VEC];
+            const T* pn = base + n * prm.sn;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) load_elems<T, VEC>(pn + c * prm.sc, p[c]);
             float H[VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) H[j] = 0.f;
@@ -176,23 +214,12 @@ __global__ void __launch_bounds__(kThreads) k1_reg_kernel(const K1Params prm) {
             for (int c = 0; c < CT; ++c) {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    S[c][j] = (n == 0) ? p[c][j] : S[c][j] + p[c][j];
-                    if (prm.need_ent) accum_term(H[j], p[c][j]);
+                    S[c][j] += p[c][j];
+                    accum_term(H[j], p[c][j]);
                 }
             }
 #pragma unroll
             for (int j = 0; j < VEC; ++j) E[j] += H[j];
-            if (prm.samax) {
-                int idx[VEC];
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    A best = p[0][j];
-                    idx[j] = 0;
-#pragma unroll
-                    for (int c = 1; c < CT; ++c) argmax_update(p[c][j], c, best, idx[j]);
-                }
-                store_u8<VEC>(prm.samax + (b * prm.N + n) * prm.V + v0, idx);
-            }
         }
         k1_epilogue<A, VEC, CT>(prm, b, v0, CT, [&](int c, int j) -> A { return S[c][j]; }, E, part);
     }
@@ -297,14 +324,20 @@ template <typename T>
 static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, cudaStream_t st) {
     constexpr int NV = In<T>::VEC;
     const int64_t V = prm.V;
-    if (aligned && prm.C <= 8) {
+    // register path: class sums of one thread must fit comfortably in registers
+    constexpr int kMaxRegC = NV >= 8 ? 4 : 8;
+    if (aligned && prm.C <= kMaxRegC && prm.need_ent && !prm.samax) {
         prm.blocks_per_vol = ceil_div(ceil_div(V, NV), kThreads);
         const int64_t grid = prm.blocks_per_vol * B;
         if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
-#define VB_CASE(CT) \
-    case CT: k1_reg_kernel<T, CT, NV><<<(unsigned)grid, kThreads, 0, st>>>(prm); break;
+#define VB_CASE(CT, MINB) \
+    case CT: k1_reg_kernel<T, CT, NV, MINB><<<(unsigned)grid, kThreads, 0, st>>>(prm); break;
         switch (prm.C) {
-            VB_CASE(1) VB_CASE(2) VB_CASE(3) VB_CASE(4) VB_CASE(5) VB_CASE(6) VB_CASE(7) VB_CASE(8)
+            VB_CASE(1, 4) VB_CASE(2, 4) VB_CASE(3, 3) VB_CASE(4, 3)
+            default:
+                if constexpr (kMaxRegC >= 8) {
+                    switch (prm.C) { VB_CASE(5, 2) VB_CASE(6, 2) VB_CASE(7, 2) VB_CASE(8, 2) }
+                }
         }
 #undef VB_CASE
         return check_launch("k1_reg_kernel");

@@ -29,7 +29,7 @@ class AggregationConfig:
     patch_mean: bool = False
     thresholds: Optional[Sequence[float]] = None  # (pred_entropy, aleatoric, epistemic)
     threshold_mean: bool = True
-    l2_budget_bytes: int = 48 << 20            # maps of one chunk stay L2-resident (126 MB L2)
+    l2_budget_bytes: int = 80 << 20            # maps + K2b intermediate of one chunk stay L2-resident (126 MB L2)
 
 
 @dataclass
@@ -88,7 +88,7 @@ class UncertaintyPipeline:
         self.k1_timer: Optional[list] = None
 
     def _chunk(self, B: int, V: int) -> int:
-        per_volume = 3 * V * 4
+        per_volume = 3 * V * (4 + 8)  # three fp32 maps + their fp64 z/x box sums (K2b workspace)
         return max(1, min(B, self.cfg.l2_budget_bytes // max(per_volume, 1)))
 
     def run(self, probs: torch.Tensor, ssn: bool = False, keep_maps: bool = False,
