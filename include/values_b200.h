@@ -125,6 +125,11 @@ int values_stitch_accumulate(const void* patches, int patch_dtype, int64_t patch
 int values_normalize_maps(const void* maps, int dtype, int64_t M, int64_t V, int64_t stride_m,
                           const double* count, double* out, void* stream);
 
+/* Tuning hooks for benchmarks and tests (process-wide; 0 restores the automatic choice):
+ * voxel tiles per CTA of the K1 stream kernel, and its batch / occupancy variant. */
+void values_debug_set_k1_iter(int iter);
+void values_debug_set_k1_variant(int variant);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,8 @@ def _load() -> C.CDLL:
         "values_stitch_accumulate": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, i64, i64, i64,
                                                pi64, pi64, vp, C.c_int, vp, C.c_int, vp]),
         "values_normalize_maps": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, vp, vp]),
+        "values_debug_set_k1_iter": (None, [C.c_int]),
+        "values_debug_set_k1_variant": (None, [C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
@@ -63,7 +65,7 @@ EXPORTED = [
     "values_uncertainty_workspace_bytes", "values_uncertainty_fused", "values_one_minus_msr",
     "values_map_reduce_workspace_bytes", "values_map_reduce",
     "values_patch_max_workspace_bytes", "values_patch_max", "values_stitch_accumulate",
-    "values_normalize_maps",
+    "values_normalize_maps", "values_debug_set_k1_iter", "values_debug_set_k1_variant",
 ]
 
 

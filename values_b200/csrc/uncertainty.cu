@@ -13,6 +13,9 @@
 
 namespace vb {
 
+static int g_k1_iter_override = 0;
+static int g_k1_variant = 0;
+
 struct K1Params {
     const void* probs;
     int64_t N, C, V, sb, sn, sc;
@@ -23,8 +26,13 @@ struct K1Params {
     uint8_t* amax;
     uint8_t* samax;
     double* partials;  // [B, blocks_per_vol, 9] or nullptr
-    double thr[3];
+    double* scores;    // [B, 9]: written by the last CTA of each volume
+    unsigned int* counters;  // [B] arrival tickets (zeroed before the launch)
+    float thr_f[3];    // thresholds rounded to fp32: numpy compares an fp32 map in fp32
+    int has_thr;
     int need_ent;
+    int iter;          // voxel tiles per CTA (stream kernel)
+    float inv_n;       // RN(1/N)
 };
 
 // ---- raw vector loads of VEC elements (16 / 8 / smaller bytes)
@@ -155,75 +163,424 @@ __device__ __forceinline__ void k1_epilogue(const K1Params& prm, int64_t b, int6
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 part[3 * k] += m3[k];
-                if (m3[k] >= prm.thr[k]) { part[3 * k + 1] += m3[k]; part[3 * k + 2] += 1.0; }
+                const float mk = k == 0 ? pe[j] : k == 1 ? ee[j] : mi[j];
+                if (prm.has_thr && mk >= prm.thr_f[k]) { part[3 * k + 1] += m3[k]; part[3 * k + 2] += 1.0; }
             }
         }
     }
 }
 
+// Block partial -> workspace; the LAST CTA of a volume to arrive (ticket counter) sums all of
+// that volume's partials in a fixed order, so the scores do not depend on CTA scheduling and
+// no second kernel launch is needed.
 __device__ __forceinline__ void k1_write_partials(const K1Params& prm, double (&part)[9]) {
     __shared__ double red[9 * 8];
+    __shared__ int s_last;
     block_sum<9>(part, red);
+    const int64_t b = blockIdx.x / prm.blocks_per_vol;
     if (threadIdx.x == 0) {
         double* dst = prm.partials + (int64_t)blockIdx.x * 9;
 #pragma unroll
         for (int k = 0; k < 9; ++k) dst[k] = part[k];
+        __threadfence();
+        const unsigned int ticket = atomicAdd(prm.counters + b, 1u);
+        s_last = ticket == (unsigned int)(prm.blocks_per_vol - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double* src = prm.partials + b * prm.blocks_per_vol * 9;
+    double acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+    for (int64_t r = threadIdx.x; r < prm.blocks_per_vol; r += kThreads) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] += __ldcg(src + r * 9 + k);
+    }
+    __syncthreads();
+    block_sum<9>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) prm.scores[b * 9 + k] = acc[k];
     }
 }
 
-// ---- class sums in registers (compile-time C): the fast path.  Always computes the three
-// maps; per-sample arg-max and the arg-max-only mode go through the shared-memory kernel.
-template <typename T, int CT, int VEC, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k1_reg_kernel(const K1Params prm) {
+// =========================================================================== K1 stream kernel
+// One generic kernel for any N and C: the (class, sample) rows of a voxel vector are walked
+// class-outer / sample-inner, so the only state that lives across rows is the running class
+// sum S, the entropy sum and the arg-max -- a handful of registers regardless of C.  Rows
+// are fetched U at a time, one batch ahead of the arithmetic (register double buffer), with
+// 128-bit read-once loads.  fp32 / bf16 inputs use packed f32x2 arithmetic (FFMA2 / FADD2 /
+// FMUL2, sm_100): the kernel is bounded by HBM only if p*log(p) costs ~10 issue slots per
+// element, which the packed degree-7 polynomial does (11) and the scalar one (20) does not.
+//
+// NaN-skip rule without a per-element select: for finite p >= +0 the polynomial log is finite,
+// so p*log(p) is already the reference's contribution (0 for p == 0).  Elements the rule would
+// treat differently (negative, -0, NaN, inf) are detected from the OR of the sign bits and the
+// finiteness of the class sums; a thread that saw one recomputes its entropy sum with the
+// exact per-element select (k1_entropy_exact) -- a cold path softmax outputs never take.
+
+template <typename T, int VEC> struct Raw {
+    static constexpr int BYTES = VEC * (int)sizeof(T);
+    static constexpr int WORDS = BYTES >= 4 ? BYTES / 4 : 1;
+    uint32_t w[WORDS];
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_raw(const T* p, Raw<T, VEC>& r) {
+    constexpr int BYTES = Raw<T, VEC>::BYTES;
+    if constexpr (BYTES == 16) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p));
+    } else if constexpr (BYTES == 8) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]) : "l"(p));
+    } else if constexpr (BYTES == 4) {
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r.w[0]) : "l"(p));
+    } else {
+        static_assert(BYTES == 2, "unsupported vector width");
+        uint16_t h;
+        asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(h) : "l"(p));
+        r.w[0] = h;
+    }
+}
+
+template <int VEC> __device__ __forceinline__ void unpack(const Raw<float, VEC>& r, float (&o)[VEC]) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = __uint_as_float(r.w[j]);
+}
+template <int VEC> __device__ __forceinline__ void unpack(const Raw<double, VEC>& r, double (&o)[VEC]) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = __hiloint2double((int)r.w[2 * j + 1], (int)r.w[2 * j]);
+}
+template <int VEC>
+__device__ __forceinline__ void unpack(const Raw<__nv_bfloat16, VEC>& r, float (&o)[VEC]) {
+    if constexpr (VEC == 1) {
+        o[0] = __uint_as_float(r.w[0] << 16);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC / 2; ++j) {
+            o[2 * j] = __uint_as_float(r.w[j] << 16);
+            o[2 * j + 1] = __uint_as_float(r.w[j] & 0xffff0000u);
+        }
+    }
+}
+// OR of the sign bits of every element of a row (bit 31 set <=> some element has its sign set)
+template <int VEC> __device__ __forceinline__ uint32_t sign_or(const Raw<float, VEC>& r) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s |= r.w[j];
+    return s;
+}
+template <int VEC> __device__ __forceinline__ uint32_t sign_or(const Raw<__nv_bfloat16, VEC>& r) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < Raw<__nv_bfloat16, VEC>::WORDS; ++j) s |= r.w[j] | (r.w[j] << 16);
+    return s;
+}
+template <int VEC> __device__ __forceinline__ uint32_t sign_or(const Raw<double, VEC>&) { return 0; }
+
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+
+// acc += p*log(p) for two fp32 elements, packed; same polynomial as fast_logf, so every
+// finite p > 0 gets bit-identical terms on the packed and the scalar (exact) path.
+__device__ __forceinline__ void plogp_pair(float& acc0, float& acc1, float p0, float p1) {
+    const int i0 = __float_as_int(p0), i1 = __float_as_int(p1);
+    const int e0 = (i0 - 0x3f2aaaab) & 0xff800000;
+    const int e1 = (i1 - 0x3f2aaaab) & 0xff800000;
+    const float2 f = __fadd2_rn(make_float2(__int_as_float(i0 - e0), __int_as_float(i1 - e1)),
+                                splat2(-1.0f));
+    float2 q = __ffma2_rn(splat2(0.13979104161262512f), f, splat2(-0.15397904813289642f));
+    q = __ffma2_rn(q, f, splat2(0.14004801213741302f));
+    q = __ffma2_rn(q, f, splat2(-0.1641434133052826f));
+    q = __ffma2_rn(q, f, splat2(0.20010659098625183f));
+    q = __ffma2_rn(q, f, splat2(-0.2500789761543274f));
+    q = __ffma2_rn(q, f, splat2(0.3333320617675781f));
+    q = __ffma2_rn(q, f, splat2(-0.49999934434890747f));
+    const float2 r = __ffma2_rn(__fmul2_rn(q, f), f, f);
+    const float2 lg = __ffma2_rn(make_float2((float)e0, (float)e1), splat2(8.262958317573066e-08f), r);
+    const float2 a = __ffma2_rn(make_float2(p0, p1), lg, make_float2(acc0, acc1));
+    acc0 = a.x; acc1 = a.y;
+}
+
+// bf16 inputs (tolerance 1e-3): log2 on the SFU (MUFU.LG2, abs err 2^-22), entropy kept in
+// log2 units until the epilogue.  max(p, FLT_MIN) keeps 0*log(0) at 0 without a select.
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Branch-free first-max-wins arg-max update; NaN counts as maximal (np.argmax / torch.argmax).
+template <typename A>
+__device__ __forceinline__ void argmax_update_sel(A v, int c, A& best, int& idx) {
+    const bool take = (v > best) | ((v != v) & (best == best));
+    best = take ? v : best;
+    idx = take ? c : idx;
+}
+
+// m = S / N, correctly rounded.  fp32: q0 = S*y, r = fma(-q0, N, S), q = fma(r, y, q0) with
+// y = RN(1/N) -- the refinement CUDA's own IEEE division ends with -- packed two at a time.
+// outside the range where the residual fma is exact (tiny non-zero, huge, inf, NaN): true division
+__device__ __forceinline__ bool mean_needs_div(float s) {
+    const float a = fabsf(s);
+    return !(a < 1e30f) | ((a < 1e-30f) & (a != 0.f));
+}
+__device__ __noinline__ float mean_div_slow(float s, float n) { return s / n; }  // cold
+template <int VEC>
+__device__ __forceinline__ void class_mean(const float (&S)[VEC], float Nf, float inv_n, float (&m)[VEC]) {
+    if constexpr (VEC == 1) {
+        const float q0 = S[0] * inv_n;
+        m[0] = fmaf(fmaf(-q0, Nf, S[0]), inv_n, q0);
+        if (mean_needs_div(S[0])) m[0] = mean_div_slow(S[0], Nf);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) {
+            const float2 s2 = make_float2(S[j], S[j + 1]);
+            const float2 q0 = __fmul2_rn(s2, splat2(inv_n));
+            const float2 r = __ffma2_rn(q0, splat2(-Nf), s2);
+            const float2 q = __ffma2_rn(r, splat2(inv_n), q0);
+            m[j] = q.x; m[j + 1] = q.y;
+            if (mean_needs_div(S[j])) m[j] = mean_div_slow(S[j], Nf);
+            if (mean_needs_div(S[j + 1])) m[j + 1] = mean_div_slow(S[j + 1], Nf);
+        }
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void class_mean(const double (&S)[VEC], double Nf, float, double (&m)[VEC]) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) m[j] = S[j] / Nf;
+}
+
+// PE[j] += m*log(m) with the NaN-skip select (exact for every m, packed where possible)
+template <int VEC>
+__device__ __forceinline__ void pe_terms(float (&PE)[VEC], const float (&m)[VEC]) {
+    if constexpr (VEC == 1) {
+        accum_term(PE[0], m[0]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) {
+            float t0 = PE[j], t1 = PE[j + 1];
+            plogp_pair(t0, t1, m[j], m[j + 1]);
+            PE[j] = (m[j] > 0.f) ? t0 : PE[j];
+            PE[j + 1] = (m[j + 1] > 0.f) ? t1 : PE[j + 1];
+        }
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void pe_terms(float (&PE)[VEC], const double (&m)[VEC]) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) accum_term(PE[j], m[j]);
+}
+
+template <typename T> struct Math;
+template <> struct Math<float> {
+    static constexpr bool kFlagged = true;     // fast path + flag + exact recompute
+    static constexpr float kScale = 1.0f;      // entropy accumulators are in nats
+    template <int VEC>
+    static __device__ __forceinline__ void rows(float (&e)[VEC], const float (&p)[VEC]) {
+        if constexpr (VEC == 1) {
+            e[0] = fmaf(p[0], fast_logf(p[0]), e[0]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; j += 2) plogp_pair(e[j], e[j + 1], p[j], p[j + 1]);
+        }
+    }
+};
+template <> struct Math<__nv_bfloat16> {
+    static constexpr bool kFlagged = true;
+    static constexpr float kScale = 0.693147180559945309f;  // accumulators are in bits
+    template <int VEC>
+    static __device__ __forceinline__ void rows(float (&e)[VEC], const float (&p)[VEC]) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) e[j] = fmaf(p[j], lg2_ftz(fmaxf(p[j], 1.17549435e-38f)), e[j]);
+    }
+};
+template <> struct Math<double> {
+    static constexpr bool kFlagged = false;    // exact per-element select, always
+    static constexpr float kScale = 1.0f;
+    template <int VEC>
+    static __device__ __forceinline__ void rows(float (&e)[VEC], const double (&p)[VEC]) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) accum_term(e[j], p[j]);
+    }
+};
+
+// Cold path: entropy sum of one voxel vector with the exact NaN-skip select per element.
+template <typename T, int VEC>
+__device__ __noinline__ void k1_entropy_exact(const T* base, int N, int C, int64_t sn, int64_t sc,
+                                              float* E_out) {
     using A = typename In<T>::acc_t;
+    float E[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) E[j] = 0.f;
+    for (int c = 0; c < C; ++c) {
+        float e[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) e[j] = 0.f;
+        for (int n = 0; n < N; ++n) {
+            Raw<T, VEC> r;
+            load_raw<T, VEC>(base + c * sc + n * sn, r);
+            A p[VEC];
+            unpack(r, p);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) accum_term(e[j], p[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) E[j] += e[j];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) E_out[j] = E[j];
+}
+
+// S += p, packed two at a time for fp32
+template <int VEC> __device__ __forceinline__ void add_rows(float (&S)[VEC], const float (&p)[VEC]) {
+    if constexpr (VEC % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) {
+            const float2 r = __fadd2_rn(make_float2(S[j], S[j + 1]), make_float2(p[j], p[j + 1]));
+            S[j] = r.x; S[j + 1] = r.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) S[j] += p[j];
+    }
+}
+template <int VEC> __device__ __forceinline__ void add_rows(double (&S)[VEC], const double (&p)[VEC]) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) S[j] += p[j];
+}
+
+// FULL: N % U == 0, every batch holds exactly U rows (no per-row guards).
+template <typename T, int VEC, int U, int MINB, bool FULL>
+__global__ void __launch_bounds__(kThreads, MINB) k1_stream_kernel(const K1Params prm) {
+    using A = typename In<T>::acc_t;
+    using M = Math<T>;
     const int64_t b = blockIdx.x / prm.blocks_per_vol;
     const int64_t blk = blockIdx.x - b * prm.blocks_per_vol;
-    const int64_t v0 = (blk * kThreads + threadIdx.x) * VEC;
-    double part[9];
+    const int N = (int)prm.N, C = (int)prm.C;
+    const int64_t snb = prm.sn * (int64_t)sizeof(T), scb = prm.sc * (int64_t)sizeof(T);  // bytes
+    const A Nf = (A)prm.N;
+    double psum[6];
+    int pcnt[3];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) part[k] = 0.0;
-    if (v0 < prm.V) {
+    for (int k = 0; k < 6; ++k) psum[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pcnt[k] = 0;
+
+    for (int it = 0; it < prm.iter; ++it) {
+        const int64_t v0 = ((blk * prm.iter + it) * kThreads + threadIdx.x) * VEC;
+        if (v0 >= prm.V) break;
         const T* base = reinterpret_cast<const T*>(prm.probs) + b * prm.sb + v0;
-        A S[CT][VEC];
-        float E[VEC];
-        {   // sample 0 initialises the class sums (torch.mean / np.mean start from the first row)
-            A p[CT][VEC];
+        A S[VEC], best[VEC];
+        float e[VEC], E[VEC], PE[VEC];
+        int idx[VEC];
+        float Sacc[VEC];  // sum of the class sums: non-finite iff some input was +-inf / NaN
+        uint32_t bad = 0;
 #pragma unroll
-            for (int c = 0; c < CT; ++c) load_elems<T, VEC>(base + c * prm.sc, p[c]);
+        for (int j = 0; j < VEC; ++j) {
+            S[j] = (A)0; e[j] = 0.f; E[j] = 0.f; PE[j] = 0.f; idx[j] = 0; best[j] = (A)0; Sacc[j] = 0.f;
+        }
+
+        // Rows are fetched in batches of <= U samples of ONE class (a batch never straddles a
+        // class boundary, so the class epilogue sits at two code sites only); the load cursor
+        // runs one batch ahead of the arithmetic across class boundaries.
+        const char* lrow = reinterpret_cast<const char*>(base);  // load cursor: next batch
+        int ln = 0, lc = 0;
+        auto issue = [&](Raw<T, VEC> (&buf)[U]) {
+            if (lc < C) {
+                const char* r = lrow;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) E[j] = 0.f;
+                for (int u = 0; u < U; ++u) {
+                    if (FULL || ln + u < N) load_raw<T, VEC>(reinterpret_cast<const T*>(r), buf[u]);
+                    r += snb;
+                }
+                lrow = r;
+                ln += U;
+                if (ln >= N) { lrow += scb - (int64_t)ln * snb; ln = 0; ++lc; }
+            }
+        };
+        int n = 0, c = 0;       // consume cursor
+        auto consume = [&](const Raw<T, VEC> (&buf)[U]) {
 #pragma unroll
-            for (int c = 0; c < CT; ++c) {
+            for (int u = 0; u < U; ++u) {
+                if (FULL || n + u < N) {
+                    A p[VEC];
+                    unpack(buf[u], p);
+                    if (M::kFlagged) bad |= sign_or(buf[u]);
+                    add_rows<VEC>(S, p);
+                    M::rows(e, p);
+                }
+            }
+            n += U;
+            if (n >= N) {  // class c complete: mean, arg-max, PE term (uniform branch)
+                A m[VEC];
+                class_mean<VEC>(S, Nf, prm.inv_n, m);
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    S[c][j] = p[c][j];
-                    accum_term(E[j], p[c][j]);
+                    if (c == 0) best[j] = m[j]; else argmax_update_sel(m[j], c, best[j], idx[j]);
+                    if (M::kFlagged) Sacc[j] += (float)S[j];  // stays finite iff every class sum is
+                    S[j] = (A)0;
+                    E[j] += e[j];
+                    e[j] = 0.f;
+                }
+                pe_terms<VEC>(PE, m);
+                n = 0; ++c;
+            }
+        };
+        Raw<T, VEC> bufA[U], bufB[U];
+        issue(bufA);
+        while (true) {
+            issue(bufB);
+            consume(bufA);
+            if (c >= C) break;
+            issue(bufA);
+            consume(bufB);
+            if (c >= C) break;
+        }
+        if (M::kFlagged) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                bad |= ((__float_as_uint(Sacc[j]) & 0x7f800000u) == 0x7f800000u) ? 0x80000000u : 0u;
+        }
+        if (M::kFlagged && (bad & 0x80000000u)) {
+            k1_entropy_exact<T, VEC>(base, N, C, prm.sn, prm.sc, E);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) E[j] = E[j] / M::kScale;  // back to accumulator units
+        }
+        float pe[VEC], ee[VEC], mi[VEC];
+        const float nf = (float)prm.N;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            pe[j] = -PE[j];
+            ee[j] = -(M::kScale == 1.0f ? E[j] : E[j] * M::kScale) / nf;
+            mi[j] = pe[j] - ee[j];
+        }
+        const int64_t o = b * prm.V + v0;
+        if (prm.pe) store_f32<VEC>(prm.pe + o, pe);
+        if (prm.ee) store_f32<VEC>(prm.ee + o, ee);
+        if (prm.mi) store_f32<VEC>(prm.mi + o, mi);
+        if (prm.amax) store_u8<VEC>(prm.amax + o, idx);
+        if (prm.partials) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float m3[3] = {pe[j], ee[j], mi[j]};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    psum[2 * k] += (double)m3[k];
+                    if (prm.has_thr && m3[k] >= prm.thr_f[k]) { psum[2 * k + 1] += (double)m3[k]; ++pcnt[k]; }
                 }
             }
         }
-#pragma unroll 1
-        for (int64_t n = 1; n < prm.N; ++n) {
-            A p[CT][VEC];
-            const T* pn = base + n * prm.sn;
-#pragma unroll
-            for (int c = 0; c < CT; ++c) load_elems<T, VEC>(pn + c * prm.sc, p[c]);
-            float H[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) H[j] = 0.f;
-#pragma unroll
-            for (int c = 0; c < CT; ++c) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    S[c][j] += p[c][j];
-                    accum_term(H[j], p[c][j]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) E[j] += H[j];
-        }
-        k1_epilogue<A, VEC, CT>(prm, b, v0, CT, [&](int c, int j) -> A { return S[c][j]; }, E, part);
     }
-    if (prm.partials) k1_write_partials(prm, part);
+    if (prm.partials) {
+        double part[9];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            part[3 * k] = psum[2 * k]; part[3 * k + 1] = psum[2 * k + 1]; part[3 * k + 2] = (double)pcnt[k];
+        }
+        k1_write_partials(prm, part);
+    }
 }
 
 // ---- class sums in shared memory (any C); thread-private columns, conflict-free
@@ -320,28 +677,54 @@ static int launch_smem(const K1Params& prm, int64_t grid, cudaStream_t st) {
     return check_launch("k1_smem_kernel");
 }
 
+// tiles per CTA of the stream kernel: amortise the block reduction over several tiles once
+// the grid is many waves deep (148 SMs x MINB CTAs), keep one tile per CTA for small jobs.
+static int choose_iter(int64_t total_tiles, int minb) {
+    const int64_t resident = 148LL * minb;
+    if (total_tiles >= 32 * resident) return 4;
+    if (total_tiles >= 12 * resident) return 2;
+    return 1;
+}
+
+template <typename T, int VEC, int U, int MINB, bool FULL>
+static int launch_stream(K1Params& prm, int64_t B, cudaStream_t st) {
+    const int64_t tiles = ceil_div(ceil_div(prm.V, VEC), kThreads);
+    prm.iter = g_k1_iter_override > 0 ? g_k1_iter_override : choose_iter(tiles * B, MINB);
+    prm.blocks_per_vol = ceil_div(tiles, prm.iter);
+    const int64_t grid = prm.blocks_per_vol * B;
+    if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
+    k1_stream_kernel<T, VEC, U, MINB, FULL><<<(unsigned)grid, kThreads, 0, st>>>(prm);
+    return check_launch("k1_stream_kernel");
+}
+
 template <typename T>
 static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, cudaStream_t st) {
     constexpr int NV = In<T>::VEC;
     const int64_t V = prm.V;
-    // register path: class sums of one thread must fit comfortably in registers
-    constexpr int kMaxRegC = NV >= 8 ? 4 : 8;
-    if (aligned && prm.C <= kMaxRegC && prm.need_ent && !prm.samax) {
-        prm.blocks_per_vol = ceil_div(ceil_div(V, NV), kThreads);
-        const int64_t grid = prm.blocks_per_vol * B;
-        if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
-#define VB_CASE(CT, MINB) \
-    case CT: k1_reg_kernel<T, CT, NV, MINB><<<(unsigned)grid, kThreads, 0, st>>>(prm); break;
-        switch (prm.C) {
-            VB_CASE(1, 4) VB_CASE(2, 4) VB_CASE(3, 3) VB_CASE(4, 3)
-            default:
-                if constexpr (kMaxRegC >= 8) {
-                    switch (prm.C) { VB_CASE(5, 2) VB_CASE(6, 2) VB_CASE(7, 2) VB_CASE(8, 2) }
-                }
+    // fp64 stacks (the reference's 3D path, raw overlap sums with large magnitudes) keep the
+    // reference's exact accumulation order: sample-outer kernel below.
+    if (prm.need_ent && !prm.samax && sizeof(T) != 8) {  // fp32 / bf16: class-outer stream kernel
+        if (!aligned) return launch_stream<T, 1, 4, 4, false>(prm, B, st);
+        // batch = U samples of one class; unguarded when U divides N (N = 4k: MC-dropout/TTA
+        // 8, 16; N = 5k: the reference's 5-member ensembles and N = 10)
+        // Occupancy beats register comfort here (measured on B200, profiles/r01b_k1_variants.txt):
+        // 3 CTAs/SM with a few cold-path spills reaches 0.84 of the HBM peak, 2 CTAs/SM 0.66.
+        const int v = g_k1_variant;
+        if (prm.N % 4 == 0 && v != 9) {
+            if (v == 1) return launch_stream<T, NV, 4, 2, true>(prm, B, st);
+            if (v == 2) return launch_stream<T, NV, 2, 3, true>(prm, B, st);
+            if (v == 3) return launch_stream<T, NV, 4, 4, true>(prm, B, st);
+            if (v == 4) return launch_stream<T, NV, 2, 4, true>(prm, B, st);
+            return launch_stream<T, NV, 4, 3, true>(prm, B, st);
         }
-#undef VB_CASE
-        return check_launch("k1_reg_kernel");
+        if (prm.N % 5 == 0 && v != 9) {
+            if (v == 1) return launch_stream<T, NV, 5, 2, true>(prm, B, st);
+            return launch_stream<T, NV, 5, 3, true>(prm, B, st);
+        }
+        if (v == 1) return launch_stream<T, NV, 4, 2, false>(prm, B, st);
+        return launch_stream<T, NV, 4, 3, false>(prm, B, st);
     }
+    // per-sample arg-max / arg-max only: sample-outer kernel with class sums in shared memory
     int rc = 1;
     if (aligned) {
         // widest vector whose class sums fit in shared memory
@@ -370,7 +753,8 @@ using namespace vb;
 extern "C" size_t values_uncertainty_workspace_bytes(int64_t B, int64_t V, int dtype) {
     (void)dtype;
     if (B <= 0 || V <= 0) return 0;
-    return (size_t)(B * k1_blocks_per_vol_upper(V) * 9) * sizeof(double);
+    // [B, blocks, 9] fp64 block partials, then [B] arrival counters
+    return (size_t)(B * k1_blocks_per_vol_upper(V) * 9) * sizeof(double) + (size_t)B * sizeof(unsigned int);
 }
 
 extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B, int64_t N,
@@ -395,13 +779,19 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
     prm.N = N; prm.C = C; prm.V = V; prm.sb = stride_b; prm.sn = stride_n; prm.sc = stride_c;
     prm.pe = pe; prm.ee = ee; prm.mi = mi; prm.amax = mean_argmax; prm.samax = sample_argmax;
     prm.need_ent = (pe || ee || mi || scores) ? 1 : 0;
-    for (int k = 0; k < 3; ++k)
-        prm.thr[k] = thresholds_host ? thresholds_host[k] : __builtin_inf();
+    prm.inv_n = (float)(1.0 / (double)N);
+    prm.has_thr = thresholds_host ? 1 : 0;
+    for (int k = 0; k < 3; ++k) prm.thr_f[k] = thresholds_host ? (float)thresholds_host[k] : 0.f;
+    if (N * C > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "N*C too large");
     if (scores) {
         const size_t need = values_uncertainty_workspace_bytes(B, V, dtype);
         if (!workspace || workspace_bytes < need)
             return set_error(VALUES_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
         prm.partials = reinterpret_cast<double*>(workspace);
+        prm.counters = reinterpret_cast<unsigned int*>(prm.partials + B * k1_blocks_per_vol_upper(V) * 9);
+        prm.scores = scores;
+        if (cudaMemsetAsync(prm.counters, 0, (size_t)B * sizeof(unsigned int), st) != cudaSuccess)
+            return set_error(VALUES_ERR_CUDA, "cudaMemsetAsync(counters) failed");
     }
     const size_t es = dtype == VALUES_F64 ? 8 : dtype == VALUES_F32 ? 4 : 2;
     const int nv = 16 / (int)es;
@@ -416,10 +806,12 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
         case VALUES_BF16: rc = dispatch_k1<__nv_bfloat16>(prm, B, aligned, st); break;
         default: return set_error(VALUES_ERR_INVALID_ARG, "unknown dtype %d", dtype);
     }
-    if (rc != VALUES_OK) return rc;
-    if (scores) return launch_reduce_partials(prm.partials, B, prm.blocks_per_vol, 9, scores, st);
-    return VALUES_OK;
+    return rc;
 }
+
+// Test/benchmark hook: force the number of voxel tiles per CTA (0 = automatic).
+extern "C" void values_debug_set_k1_iter(int iter) { g_k1_iter_override = iter; }
+extern "C" void values_debug_set_k1_variant(int variant) { g_k1_variant = variant; }
 
 extern "C" int values_one_minus_msr(const void* probs, int dtype, int64_t B, int64_t C, int64_t V,
                                     int64_t stride_b, int64_t stride_c, void* out, void* stream) {
