@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VALUES_ABI_VERSION 1
+#define VALUES_ABI_VERSION 2
 
 typedef enum { VALUES_F32 = 0, VALUES_F64 = 1, VALUES_BF16 = 2 } values_dtype_t;
 
@@ -47,7 +47,10 @@ int64_t values_launch_count(void);
  *
  *   probs   [B, N, C, V] with element strides (stride_b, stride_n, stride_c, 1)
  *   pe/ee/mi      float [B, V]   predictive entropy / expected entropy / mutual information
- *                               (the `ssn` key swap is a host-side relabelling)
+ *                               (the `ssn` key swap is a host-side relabelling); volume b of each
+ *                               map starts map_stride_b elements after volume b-1 (0 = V), so
+ *                               pe, ee = pe + V, mi = pe + 2V with map_stride_b = 3V gives the
+ *                               volume-major layout [B, 3, V] that K2b consumes
  *   mean_argmax   uint8 [B, V]      or NULL
  *   sample_argmax uint8 [B, N, V]   or NULL
  *   scores  double [B, 3, 3] or NULL: per map (pe, ee, mi): {sum, sum over v>=thr, count v>=thr}
@@ -59,8 +62,8 @@ int64_t values_launch_count(void);
 size_t values_uncertainty_workspace_bytes(int64_t B, int64_t V, int dtype);
 int values_uncertainty_fused(const void* probs, int dtype, int64_t B, int64_t N, int64_t C,
                              int64_t V, int64_t stride_b, int64_t stride_n, int64_t stride_c,
-                             float* pe, float* ee, float* mi, uint8_t* mean_argmax,
-                             uint8_t* sample_argmax, double* scores,
+                             float* pe, float* ee, float* mi, int64_t map_stride_b,
+                             uint8_t* mean_argmax, uint8_t* sample_argmax, double* scores,
                              const double* thresholds_host, void* workspace,
                              size_t workspace_bytes, void* stream);
 
@@ -129,6 +132,8 @@ int values_normalize_maps(const void* maps, int dtype, int64_t M, int64_t V, int
  * voxel tiles per CTA of the K1 stream kernel, and its batch / occupancy variant. */
 void values_debug_set_k1_iter(int iter);
 void values_debug_set_k1_variant(int variant);
+/* K2b implementation: 0 automatic, 1 streaming two-kernel path, 2 generic tiled path. */
+void values_debug_set_patch_path(int path);
 
 #ifdef __cplusplus
 }

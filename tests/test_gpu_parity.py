@@ -34,6 +34,15 @@ def vo():
     return values_oracle
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["k2b-fused", "k2b-stream", "k2b-tiled"])
+def patch_path(request, vb):
+    """Every K2b implementation (fused tile kernel, streaming two-kernel path, generic tiled
+    path) must give the same scores and the same bounding boxes."""
+    vb._lib.lib.values_debug_set_patch_path(request.param)
+    yield request.param
+    vb._lib.lib.values_debug_set_patch_path(0)
+
+
 def softmax_stack(seed, n, c, spatial, dtype=torch.float32, shared=False, sharp=3.0):
     g = torch.Generator().manual_seed(seed)
     if shared:
@@ -66,7 +75,7 @@ def assert_argmax(got_u8, stack, exact_ref):
 def test_native_library_loaded(vb):
     with open("/proc/self/maps") as f:
         assert "libvalues_b200.so" in f.read()
-    assert vb._lib.lib.values_abi_version() == 1
+    assert vb._lib.lib.values_abi_version() == vb._lib.ABI_VERSION == 2
 
 
 @pytest.mark.parametrize("name", C2_CASES)
@@ -194,7 +203,7 @@ def test_fused_scores_vs_oracle(vb, vo):
 
 
 # ------------------------------------------------------------------------------------ C3
-def test_c3_golden(vb):
+def test_c3_golden(vb, patch_path):
     g = np.load(os.path.join(GOLDEN, "c3_aggregations.npz"))
     for i in range(int(g["n_patch_cases"])):
         for mean in (0, 1):
@@ -226,7 +235,7 @@ def test_c3_golden(vb):
     ((20, 30, 100), [3, 4, 40], np.float64),   # patch wider than a warp -> tiled shared-memory fallback
     ((9, 70, 33), [9, 33, 32], np.float32), ((1024, 2048), 10, np.float32),
 ])
-def test_c3_patch_vs_oracle(vb, vo, shape, patch, dtype):
+def test_c3_patch_vs_oracle(vb, vo, shape, patch, dtype, patch_path):
     rng = np.random.default_rng(sum(shape) * 7 + len(shape))
     m = rng.random(shape).astype(dtype)
     for mean in (False, True):
@@ -236,7 +245,7 @@ def test_c3_patch_vs_oracle(vb, vo, shape, patch, dtype):
         np.testing.assert_allclose(a["max_score"], b["max_score"], rtol=1e-12)
 
 
-def test_c3_batched_and_isclose_rule(vb, vo):
+def test_c3_batched_and_isclose_rule(vb, vo, patch_path):
     rng = np.random.default_rng(11)
     maps = rng.random((7, 30, 31, 32)).astype(np.float32)
     maps[3] = 0.0                                   # all-zero map -> score 0, box at origin
@@ -356,7 +365,7 @@ def test_pipeline_vs_oracle(vb, vo):
     B, n, c, spatial = 5, 5, 2, (32, 36, 40)
     x = softmax_stack(99, B * n, c, spatial).reshape(B, n, c, *spatial)
     thr = (0.45, 0.4, 0.03)
-    cfg = vb.AggregationConfig(patch_size=10, thresholds=thr, l2_budget_bytes=3 * 32 * 36 * 40 * 12 * 2)
+    cfg = vb.AggregationConfig(patch_size=10, thresholds=thr, chunk_bytes=3 * 32 * 36 * 40 * 4 * 2)  # two volumes per chunk
     res = vb.UncertaintyPipeline(cfg).run(x.cuda(), keep_maps=True, mean_argmax=True)
     ids = [f"img{b}" for b in range(B)]
     dicts = res.to_dicts(ids)

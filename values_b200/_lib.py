@@ -14,6 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libvalues_b200.so")
 
 F32, F64, BF16 = 0, 1, 2
+ABI_VERSION = 2  # include/values_b200.h VALUES_ABI_VERSION
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
@@ -38,7 +39,7 @@ def _load() -> C.CDLL:
         "values_launch_count": (i64, []),
         "values_uncertainty_workspace_bytes": (sz, [i64, i64, C.c_int]),
         "values_uncertainty_fused": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, i64, i64, i64,
-                                               vp, vp, vp, vp, vp, vp, pdbl, vp, sz, vp]),
+                                               vp, vp, vp, i64, vp, vp, vp, pdbl, vp, sz, vp]),
         "values_one_minus_msr": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, i64, vp, vp]),
         "values_map_reduce_workspace_bytes": (sz, [i64, i64]),
         "values_map_reduce": (C.c_int, [vp, C.c_int, i64, i64, i64, pdbl, C.c_int, vp, vp, sz, vp]),
@@ -50,11 +51,12 @@ def _load() -> C.CDLL:
         "values_normalize_maps": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, vp, vp]),
         "values_debug_set_k1_iter": (None, [C.c_int]),
         "values_debug_set_k1_variant": (None, [C.c_int]),
+        "values_debug_set_patch_path": (None, [C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
         fn.restype, fn.argtypes = res, args
-    if lib.values_abi_version() != 1:
+    if lib.values_abi_version() != ABI_VERSION:
         raise ValuesExtensionMissing("libvalues_b200.so ABI version mismatch; rebuild it")
     return lib
 
@@ -66,6 +68,7 @@ EXPORTED = [
     "values_map_reduce_workspace_bytes", "values_map_reduce",
     "values_patch_max_workspace_bytes", "values_patch_max", "values_stitch_accumulate",
     "values_normalize_maps", "values_debug_set_k1_iter", "values_debug_set_k1_variant",
+    "values_debug_set_patch_path",
 ]
 
 

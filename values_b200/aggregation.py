@@ -42,10 +42,20 @@ def _as_map(image, device: torch.device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ device-side batched ops
+def patch_max_workspace_bytes(M: int, spatial: Sequence[int], patch_size) -> int:
+    nd = len(spatial)
+    if isinstance(patch_size, (int, np.integer)):
+        patch_size = nd * [int(patch_size)]
+    return int(_lib.lib.values_patch_max_workspace_bytes(
+        M, _lib.i64x3([1] * (3 - nd) + list(spatial)), _lib.i64x3([1] * (3 - nd) + list(patch_size))))
+
+
 def patch_max(maps: torch.Tensor, patch_size, mean: bool = False,
-              rtol: float = ISCLOSE_RTOL, atol: float = ISCLOSE_ATOL
-              ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """maps [M, *S] (CUDA fp32/fp64, 1 <= len(S) <= 3) -> (max_score fp64 [M], bbox_lo int64 [M, len(S)])."""
+              rtol: float = ISCLOSE_RTOL, atol: float = ISCLOSE_ATOL,
+              out_score: Optional[torch.Tensor] = None, out_bbox: Optional[torch.Tensor] = None,
+              workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """maps [M, *S] (CUDA fp32/fp64, 1 <= len(S) <= 3) -> (max_score fp64 [M], bbox_lo int64 [M, len(S)]).
+    out_score fp64 [M] / out_bbox int64 [M, 3] / workspace (uint8) may be preallocated."""
     if maps.device.type != "cuda":
         raise RuntimeError("patch_max expects a CUDA tensor (no CPU fallback)")
     nd = maps.dim() - 1
@@ -60,11 +70,17 @@ def patch_max(maps: torch.Tensor, patch_size, mean: bool = False,
     shape3 = [1] * (3 - nd) + list(maps.shape[1:])
     patch3 = [1] * (3 - nd) + [int(p) for p in patch_size]
     dev = maps.device
-    score = torch.empty(M, dtype=torch.float64, device=dev)
-    bbox = torch.empty((M, 3), dtype=torch.int64, device=dev)
+    score = out_score if out_score is not None else torch.empty(M, dtype=torch.float64, device=dev)
+    bbox = out_bbox if out_bbox is not None else torch.empty((M, 3), dtype=torch.int64, device=dev)
+    if (tuple(score.shape) != (M,) or score.dtype != torch.float64 or not score.is_contiguous()
+            or tuple(bbox.shape) != (M, 3) or bbox.dtype != torch.int64 or not bbox.is_contiguous()):
+        raise ValueError("out_score must be contiguous fp64 [M] and out_bbox contiguous int64 [M, 3]")
     sh, pa = _lib.i64x3(shape3), _lib.i64x3(patch3)
     ws_bytes = _lib.lib.values_patch_max_workspace_bytes(M, sh, pa)
-    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+    if workspace is not None and workspace.numel() * workspace.element_size() >= ws_bytes:
+        ws = workspace
+    else:
+        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
     V = int(np.prod(shape3))
     with torch.cuda.device(dev):
         rc = _lib.lib.values_patch_max(maps.data_ptr(), _lib.dtype_code(maps.dtype), M, V, sh, pa,

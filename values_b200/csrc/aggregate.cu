@@ -7,6 +7,10 @@
 
 namespace vb {
 
+// 0 = automatic (fused tile kernel when the patch fits its shared memory), 1 = streaming
+// two-kernel path, 2 = generic tiled path (values_debug_set_patch_path; tests cover all three)
+static int g_patch_path = 0;
+
 // =============================================================================== K2a
 struct ThrTable { double v[16]; int n; };
 
@@ -233,6 +237,251 @@ __global__ void patch_finish_kernel(const unsigned long long* __restrict__ best,
     bbox_lo[3 * m + 2] = lin % O2;
     bbox_lo[3 * m + 1] = (lin / O2) % O1;
     bbox_lo[3 * m] = lin / (O2 * O1);
+}
+
+// ------------------------------------------------------------------ K2b fused tile kernel
+// One kernel per pass does all three box passes: a CTA owns TY x TX windows in-plane and a
+// chunk of ZC output planes, marching over z.  Per input plane: (1) the plane tile (+halo)
+// goes from L2 to shared memory through registers, one plane AHEAD of the arithmetic;
+// (2) x-pass: sliding fp64 sums in registers, 8 outputs per task, rows striped over lanes
+// (odd pitch -> conflict-free); (3) y-pass: a thread owns OWN consecutive rows of one column
+// (sliding), z-pass: sliding over a private shared-memory ring of the last p0 plane sums.
+// Two block barriers per plane.  Pass 1 keeps the tile maximum; pass 2 recomputes only the
+// tiles whose maximum is np.isclose to the global one and takes the minimum C-order index;
+// the last CTA of a map (ticket) converts it to the bounding box, so there is no select /
+// finish launch.  fp64 throughout: the result is independent of tiling and launch shape.
+template <int TY, int TX> struct FusedTile {
+    static constexpr int kSegF = 8;
+    static constexpr int kOwnF = TY * TX / kThreads;   // consecutive y outputs per thread
+    static constexpr int kStrips = kThreads / TX;      // strips of kOwnF rows
+    static constexpr int kStage = 8;                   // staged input elements per thread
+    static_assert(kOwnF * kStrips == TY, "tile shape");
+};
+
+struct FusedParams {
+    const void* maps;
+    int64_t stride_m;
+    int64_t D0, D1, D2, O0, O1, O2;
+    int p0, p1, p2;
+    int tiles_x, tiles_y, chunks_z, zc;
+    int zsub;                     // pass-2 sub-chunks per pass-1 z-chunk (zc % zsub == 0)
+    int64_t ntiles;
+    double denom;
+    int mean_flag;
+    double rtol, atol;
+    double* tile_max;             // [M, ntiles]
+    unsigned long long* best;     // [M]
+    unsigned int* tickets;        // [M]
+    double* max_score;            // [M]
+    int64_t* bbox_lo;             // [M, 3]
+};
+
+__device__ __noinline__ double box_mean_div(double s, double denom) { return s / denom; }  // mean=True only
+
+// PC > 0: in-plane patch extents p1 == p2 == PC known at compile time (the reference's configs
+// all use 10: evaluation/configs/tasks/aggregation_patch_*.yaml), so both box loops unroll.
+template <typename T, int TY, int TX, int PC, int PASS>
+__global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParams prm) {
+    using FT = FusedTile<TY, TX>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[8];
+    __shared__ int s_flag;
+    const int p1 = PC > 0 ? PC : prm.p1, p2 = PC > 0 ? PC : prm.p2, p0 = prm.p0;
+    const int R = TY + p1 - 1, W = TX + p2 - 1;
+    const int pitch_in = W | 1, pitch_rs = TX + 1;
+    double* rowsum = reinterpret_cast<double*>(smem_raw);     // [R][pitch_rs]
+    double* ring = rowsum + (size_t)R * pitch_rs;             // [p0][TY*TX]
+    double* in_tile = ring + (size_t)p0 * TY * TX;            // [R][pitch_in], widened to fp64
+
+    const int64_t m = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+    // pass 2 runs on a finer z split (prm.zsub sub-chunks per pass-1 chunk) so that the few
+    // surviving tiles finish quickly; tile_max is indexed by the pass-1 (coarse) tile
+    int tile = blockIdx.x;
+    const int tx_i = tile % prm.tiles_x; tile /= prm.tiles_x;
+    const int ty_i = tile % prm.tiles_y; tile /= prm.tiles_y;
+    const int zsub = PASS == 2 ? prm.zsub : 1;
+    const int zc_fine = prm.zc / zsub;
+    const int64_t coarse = ((int64_t)(tile / zsub) * prm.tiles_y + ty_i) * prm.tiles_x + tx_i;
+    double gmax = 0.0;
+    bool active = true;
+    if (PASS == 1) {
+        if (blockIdx.x == 0 && tid == 0) { prm.best[m] = ~0ull; prm.tickets[m] = 0u; }
+    } else {
+        // global maximum of this map from the pass-1 tile maxima (NaN propagates, as np.max)
+        double mm = ninf;
+        for (int64_t i = tid; i < prm.ntiles; i += kThreads) mm = nanmax(mm, prm.tile_max[m * prm.ntiles + i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mm = nanmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        if (lane == 0) red[warp] = mm;
+        __syncthreads();
+        gmax = red[0];
+#pragma unroll
+        for (int w = 1; w < kThreads / 32; ++w) gmax = nanmax(gmax, red[w]);
+        __syncthreads();
+        active = np_isclose(prm.tile_max[m * prm.ntiles + coarse], gmax, prm.rtol, prm.atol);
+    }
+    const int64_t zo0 = (int64_t)tile * zc_fine;
+    const int64_t zo1 = min(zo0 + zc_fine, min((int64_t)(tile / zsub + 1) * prm.zc, prm.O0));
+    if (zo0 >= zo1) active = false;
+    unsigned long long tbest = ~0ull;
+    double tmax = ninf;
+    if (active) {
+        const int64_t x0 = (int64_t)tx_i * TX, y0 = (int64_t)ty_i * TY;
+        const int nplanes = (int)(zo1 - zo0) + p0 - 1;
+        const T* src = reinterpret_cast<const T*>(prm.maps) + m * prm.stride_m;
+        const int64_t plane_elems = prm.D1 * prm.D2;
+
+        // staging map of this thread: global offset inside a plane (-1 = zero fill) and the
+        // shared-memory slot, fixed for the whole march
+        const int n_in = R * W;
+        int goff[FT::kStage], soff[FT::kStage];
+#pragma unroll
+        for (int i = 0; i < FT::kStage; ++i) {
+            const int idx = tid + i * kThreads;
+            goff[i] = -1; soff[i] = -1;
+            if (idx < n_in) {
+                const int r = idx / W, cx = idx - r * W;
+                const int64_t y = y0 + r, x = x0 + cx;
+                soff[i] = r * pitch_in + cx;
+                if (y < prm.D1 && x < prm.D2) goff[i] = (int)(y * prm.D2 + x);
+            }
+        }
+        const bool staged = n_in <= FT::kStage * kThreads && plane_elems < 0x7fffffffLL;
+        T st[FT::kStage];
+        auto fetch = [&](int64_t z) {
+            const T* pl = src + z * plane_elems;
+#pragma unroll
+            for (int i = 0; i < FT::kStage; ++i) st[i] = goff[i] >= 0 ? In<T>::load_one(pl + goff[i]) : (T)0;
+        };
+        auto commit = [&]() {
+#pragma unroll
+            for (int i = 0; i < FT::kStage; ++i) if (soff[i] >= 0) in_tile[soff[i]] = (double)st[i];
+        };
+        auto load_direct = [&](int64_t z) {   // halo too large for the register stage
+            const T* pl = src + z * plane_elems;
+            for (int idx = tid; idx < n_in; idx += kThreads) {
+                const int r = idx / W, cx = idx - r * W;
+                const int64_t y = y0 + r, x = x0 + cx;
+                in_tile[r * pitch_in + cx] =
+                    (y < prm.D1 && x < prm.D2) ? (double)In<T>::load_one(pl + y * prm.D2 + x) : 0.0;
+            }
+        };
+        // x-pass tasks: (row r, segment of 8 outputs), rows striped over lanes
+        const int ntask = R * (TX / FT::kSegF);
+        const int task_r = tid % R, task_seg = tid / R;
+        const int ox = tid % TX, oy0 = (tid / TX) * FT::kOwnF;   // y/z-pass ownership
+        double run[FT::kOwnF];
+        unsigned int valid = 0;   // bit k: output (oy0 + k, ox) of this thread lies inside the map
+#pragma unroll
+        for (int k = 0; k < FT::kOwnF; ++k) {
+            run[k] = 0.0;
+            if (y0 + oy0 + k < prm.O1 && x0 + ox < prm.O2) valid |= 1u << k;
+        }
+        auto x_task = [&](int r, int seg) {
+            const double* row = in_tile + r * pitch_in + seg * FT::kSegF;
+            double* dst = rowsum + r * pitch_rs + seg * FT::kSegF;
+            double s = 0.0;
+            if constexpr (PC > 0) {
+                double v[PC + FT::kSegF - 1];
+#pragma unroll
+                for (int k = 0; k < PC + FT::kSegF - 1; ++k) v[k] = row[k];
+#pragma unroll
+                for (int k = 0; k < PC; ++k) s += v[k];
+                dst[0] = s;
+#pragma unroll
+                for (int i = 1; i < FT::kSegF; ++i) { s += v[i + PC - 1] - v[i - 1]; dst[i] = s; }
+            } else {
+                for (int k = 0; k < p2; ++k) s += row[k];
+                dst[0] = s;
+#pragma unroll
+                for (int i = 1; i < FT::kSegF; ++i) { s += row[i + p2 - 1] - row[i - 1]; dst[i] = s; }
+            }
+        };
+
+        if (staged) fetch(zo0);
+        int slot = 0;
+        for (int zi = 0; zi < nplanes; ++zi) {
+            if (staged) commit(); else load_direct(zo0 + zi);
+            __syncthreads();
+            if (staged && zi + 1 < nplanes) fetch(zo0 + zi + 1);   // next plane, in flight during the math
+            // ---- x-pass
+            if (tid < ntask) x_task(task_r, task_seg);
+            for (int task = tid + kThreads; task < ntask; task += kThreads) x_task(task % R, task / R);
+            __syncthreads();
+            // ---- y-pass (sliding down the strip) + z-pass (sliding over the ring)
+            const double* col = rowsum + oy0 * pitch_rs + ox;
+            double s2 = 0.0;
+            if constexpr (PC > 0) {
+#pragma unroll
+                for (int j = 0; j < PC; ++j) s2 += col[j * pitch_rs];
+            } else {
+                for (int j = 0; j < p1; ++j) s2 += col[j * pitch_rs];
+            }
+            const bool warm = zi >= p0 - 1;     // the z-window is complete: an output plane
+            const int64_t oz = zo0 + zi - (p0 - 1);
+#pragma unroll
+            for (int k = 0; k < FT::kOwnF; ++k) {
+                if (k > 0) s2 += col[(k + p1 - 1) * pitch_rs] - col[(k - 1) * pitch_rs];
+                double* rs = ring + (size_t)slot * (TY * TX) + (oy0 + k) * TX + ox;
+                const double old = zi >= p0 ? *rs : 0.0;
+                *rs = s2;
+                run[k] += s2 - old;
+                if (warm && ((valid >> k) & 1u)) {
+                    double v = run[k];
+                    if (prm.mean_flag) v = box_mean_div(v, prm.denom);
+                    if (PASS == 1) {
+                        tmax = nanmax(tmax, v);
+                    } else if (np_isclose(v, gmax, prm.rtol, prm.atol)) {
+                        const unsigned long long lin =
+                            (unsigned long long)((oz * prm.O1 + (y0 + oy0 + k)) * prm.O2 + (x0 + ox));
+                        tbest = lin < tbest ? lin : tbest;
+                    }
+                }
+            }
+            slot = slot + 1 == p0 ? 0 : slot + 1;
+        }
+    }
+    if constexpr (PASS == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmax = nanmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if (lane == 0) red[warp] = tmax;
+        __syncthreads();
+        if (tid == 0) {
+            double mm = red[0];
+            for (int w = 1; w < kThreads / 32; ++w) mm = nanmax(mm, red[w]);
+            prm.tile_max[m * prm.ntiles + blockIdx.x] = mm;
+        }
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, tbest, o);
+            tbest = other < tbest ? other : tbest;
+        }
+        if (lane == 0 && tbest != ~0ull) atomicMin(prm.best + m, tbest);  // min is order-free
+        // last CTA of this map: publish max_score and the bounding-box corner
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_flag = atomicAdd(prm.tickets + m, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_flag && tid == 0) {
+            __threadfence();
+            const unsigned long long b = atomicMin(prm.best + m, ~0ull);  // atomic read
+            prm.max_score[m] = gmax;
+            int64_t* bb = prm.bbox_lo + 3 * m;
+            if (b == ~0ull) {  // no window is close to the max (NaN map): the reference raises IndexError
+                bb[0] = bb[1] = bb[2] = -1;
+            } else {
+                const int64_t lin = (int64_t)b;
+                bb[2] = lin % prm.O2;
+                bb[1] = (lin / prm.O2) % prm.O1;
+                bb[0] = lin / (prm.O2 * prm.O1);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ K2b fast path (p2 <= 32)
@@ -495,6 +744,96 @@ static int run_patch_stream(StreamParams prm, const StreamPlan& sp, int64_t M, d
     return check_launch("patch_finish_kernel");
 }
 
+// ------------------------------------------------------------------ fused path: host side
+struct FusedPlan {
+    int ty, tx;            // 16x64 or 8x32; 0 = fused path not applicable
+    int64_t O0, O1, O2;
+    int tiles_x, tiles_y, chunks_z, zc, zsub;
+    int64_t ntiles;
+};
+
+static size_t fused_smem_bytes(int ty, int tx, const int64_t* patch) {
+    const int64_t R = ty + patch[1] - 1, W = tx + patch[2] - 1;
+    return (size_t)(R * (tx + 1) + patch[0] * ty * tx + R * (W | 1)) * sizeof(double);
+}
+
+// 0 on success (pl.ty == 0 when the patch is too large for the fused kernel's shared memory)
+static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch, FusedPlan& pl) {
+    pl.ty = pl.tx = 0;
+    for (int d = 0; d < 3; ++d) {
+        if (shape[d] <= 0 || patch[d] <= 0)
+            return set_error(VALUES_ERR_INVALID_ARG, "patch_max: non-positive shape/patch");
+        if (patch[d] > shape[d])
+            return set_error(VALUES_ERR_INVALID_ARG,
+                             "For 'valid' mode, one must be at least as large as the other in "
+                             "every dimension (axis %d: image %lld < patch %lld)",
+                             d, (long long)shape[d], (long long)patch[d]);
+    }
+    pl.O0 = shape[0] - patch[0] + 1; pl.O1 = shape[1] - patch[1] + 1; pl.O2 = shape[2] - patch[2] + 1;
+    const size_t budget = 113 * 1024;  // two CTAs per SM
+    if (fused_smem_bytes(16, 64, patch) <= budget && pl.O2 > 32) { pl.ty = 16; pl.tx = 64; }
+    else if (fused_smem_bytes(8, 32, patch) <= budget) { pl.ty = 8; pl.tx = 32; }
+    else return VALUES_OK;
+    pl.tiles_x = (int)ceil_div(pl.O2, pl.tx);
+    pl.tiles_y = (int)ceil_div(pl.O1, pl.ty);
+    // output planes per z-chunk: the march is latency-bound per CTA, so prefer enough CTAs for
+    // ~3 waves of 2 CTAs/SM, but never chunks so short that the p0-1 warm-up planes dominate
+    const int64_t slots = 148 * 2, in_plane = (int64_t)pl.tiles_x * pl.tiles_y * std::max<int64_t>(M, 1);
+    int64_t best_cost = -1;
+    pl.zc = (int)pl.O0;
+    for (int64_t zc : {(int64_t)8, (int64_t)16, (int64_t)32, (int64_t)64, (int64_t)128, pl.O0}) {
+        if (zc > pl.O0) zc = pl.O0;
+        const int64_t ctas = in_plane * ceil_div(pl.O0, zc);
+        // time ~ planes marched per SM (2 CTAs interleave on one SM)
+        const int64_t per_sm = ceil_div(ctas, 148);
+        const int64_t cost = ceil_div(per_sm, 2) * (zc + patch[0] - 1 + 2);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; pl.zc = (int)zc; }
+    }
+    (void)slots;
+    pl.zsub = 1;
+    for (int sub : {8, 4, 2})
+        if (pl.zc % sub == 0 && pl.zc / sub >= 4) { pl.zsub = sub; break; }
+    pl.chunks_z = (int)ceil_div(pl.O0, pl.zc);
+    pl.ntiles = (int64_t)pl.tiles_x * pl.tiles_y * pl.chunks_z;
+    if (pl.ntiles * pl.zsub > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: too many tiles");
+    return VALUES_OK;
+}
+
+template <typename T, int TY, int TX, int PC>
+static int run_patch_fused_pc(FusedParams prm, const FusedPlan& pl, int64_t M, cudaStream_t st) {
+    auto k1 = box_fused_kernel<T, TY, TX, PC, 1>;
+    auto k2 = box_fused_kernel<T, TY, TX, PC, 2>;
+    const int64_t patch[3] = {prm.p0, prm.p1, prm.p2};
+    const size_t smem = fused_smem_bytes(TY, TX, patch);
+    if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute(%zu) failed", smem);
+    for (int64_t m0 = 0; m0 < M; m0 += 65535) {  // gridDim.y limit
+        const int64_t mc = std::min<int64_t>(65535, M - m0);
+        FusedParams q = prm;
+        q.maps = reinterpret_cast<const T*>(prm.maps) + m0 * prm.stride_m;
+        q.tile_max = prm.tile_max + m0 * pl.ntiles;
+        q.best = prm.best + m0; q.tickets = prm.tickets + m0;
+        q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
+        k1<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kThreads, smem, st>>>(q);
+        int rc = check_launch("box_fused_kernel<1>");
+        if (rc) return rc;
+        k2<<<dim3((unsigned)(pl.ntiles * pl.zsub), (unsigned)mc), kThreads, smem, st>>>(q);
+        if ((rc = check_launch("box_fused_kernel<2>"))) return rc;
+    }
+    return VALUES_OK;
+}
+
+template <typename T, int TY, int TX>
+static int run_patch_fused(FusedParams prm, const FusedPlan& pl, int64_t M, cudaStream_t st) {
+    if (prm.p1 == 10 && prm.p2 == 10) return run_patch_fused_pc<T, TY, TX, 10>(prm, pl, M, st);
+    return run_patch_fused_pc<T, TY, TX, 0>(prm, pl, M, st);
+}
+
+static size_t fused_workspace_bytes(int64_t M, const FusedPlan& pl) {
+    return (size_t)(M * pl.ntiles + 2 * M) * sizeof(double);  // tile_max | best | tickets (8-byte slots)
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -569,7 +908,12 @@ extern "C" int values_normalize_maps(const void* maps, int dtype, int64_t M, int
 extern "C" size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* shape3_host,
                                                    const int64_t* patch3_host) {
     if (M <= 0 || !shape3_host || !patch3_host) return 0;
-    if (stream_path_ok(patch3_host)) {
+    if (g_patch_path == 0) {
+        FusedPlan fp;
+        if (make_fused_plan(M, shape3_host, patch3_host, fp) != VALUES_OK) return 0;
+        if (fp.ty) return fused_workspace_bytes(M, fp);
+    }
+    if (stream_path_ok(patch3_host) && g_patch_path != 2) {
         StreamPlan sp;
         if (make_stream_plan(shape3_host, patch3_host, sp) != VALUES_OK) return 0;
         return (size_t)(M * sp.xz_per_map + M * sp.ntiles + 2 * M) * sizeof(double);
@@ -592,7 +936,37 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
     double* ws = reinterpret_cast<double*>(workspace);
     const double denom =
         mean_flag ? (double)patch3_host[0] * (double)patch3_host[1] * (double)patch3_host[2] : 1.0;
-    if (stream_path_ok(patch3_host)) {
+    if (g_patch_path == 0) {
+        FusedPlan fp;
+        int rc = make_fused_plan(M, shape3_host, patch3_host, fp);
+        if (rc) return rc;
+        if (fp.ty) {
+            if (M == 0) return VALUES_OK;
+            if (!maps || !max_score || !bbox_lo) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: NULL pointer");
+            const size_t need = fused_workspace_bytes(M, fp);
+            if (!workspace || workspace_bytes < need)
+                return set_error(VALUES_ERR_WORKSPACE, "patch_max: workspace %zu < %zu", workspace_bytes, need);
+            FusedParams prm{};
+            prm.maps = maps; prm.stride_m = stride_m;
+            prm.D0 = shape3_host[0]; prm.D1 = shape3_host[1]; prm.D2 = shape3_host[2];
+            prm.O0 = fp.O0; prm.O1 = fp.O1; prm.O2 = fp.O2;
+            prm.p0 = (int)patch3_host[0]; prm.p1 = (int)patch3_host[1]; prm.p2 = (int)patch3_host[2];
+            prm.tiles_x = fp.tiles_x; prm.tiles_y = fp.tiles_y; prm.chunks_z = fp.chunks_z; prm.zc = fp.zc;
+            prm.zsub = fp.zsub; prm.ntiles = fp.ntiles;
+            prm.denom = denom; prm.mean_flag = mean_flag ? 1 : 0; prm.rtol = rtol; prm.atol = atol;
+            prm.tile_max = ws;
+            prm.best = reinterpret_cast<unsigned long long*>(ws + M * fp.ntiles);
+            prm.tickets = reinterpret_cast<unsigned int*>(ws + M * fp.ntiles + M);
+            prm.max_score = max_score; prm.bbox_lo = bbox_lo;
+            if (fp.ty == 16) {
+                if (dtype == VALUES_F32) return run_patch_fused<float, 16, 64>(prm, fp, M, st);
+                return run_patch_fused<double, 16, 64>(prm, fp, M, st);
+            }
+            if (dtype == VALUES_F32) return run_patch_fused<float, 8, 32>(prm, fp, M, st);
+            return run_patch_fused<double, 8, 32>(prm, fp, M, st);
+        }
+    }
+    if (stream_path_ok(patch3_host) && g_patch_path != 2) {
         StreamPlan sp;
         int rc = make_stream_plan(shape3_host, patch3_host, sp);
         if (rc) return rc;
@@ -640,3 +1014,5 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
     if (dtype == VALUES_F32) return run_patch<float>(prm, pl, M, gmax, max_score, bbox_lo, st);
     return run_patch<double>(prm, pl, M, gmax, max_score, bbox_lo, st);
 }
+
+extern "C" void values_debug_set_patch_path(int path) { g_patch_path = path; }

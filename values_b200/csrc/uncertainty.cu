@@ -33,6 +33,7 @@ struct K1Params {
     int need_ent;
     int iter;          // voxel tiles per CTA (stream kernel)
     float inv_n;       // RN(1/N)
+    int64_t so;        // elements between consecutive volumes in pe / ee / mi (>= V)
 };
 
 // ---- raw vector loads of VEC elements (16 / 8 / smaller bytes)
@@ -151,11 +152,11 @@ __device__ __forceinline__ void k1_epilogue(const K1Params& prm, int64_t b, int6
         ee[j] = -E[j] / nf;
         mi[j] = pe[j] - ee[j];
     }
-    const int64_t o = b * prm.V + v0;
+    const int64_t o = b * prm.so + v0;
     if (prm.pe) store_f32<VEC>(prm.pe + o, pe);
     if (prm.ee) store_f32<VEC>(prm.ee + o, ee);
     if (prm.mi) store_f32<VEC>(prm.mi + o, mi);
-    if (prm.amax) store_u8<VEC>(prm.amax + o, idx);
+    if (prm.amax) store_u8<VEC>(prm.amax + b * prm.V + v0, idx);
     if (prm.partials) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -225,6 +226,20 @@ template <typename T, int VEC> struct Raw {
     static constexpr int WORDS = BYTES >= 4 ? BYTES / 4 : 1;
     uint32_t w[WORDS];
 };
+
+// 128-bit read-once load that also marks the line evict-first in L2: the softmax stack is
+// touched exactly once, while the maps K1 writes are re-read by K2b and should stay resident.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void load_raw_stream(const T* p, Raw<T, VEC>& r, uint64_t pol) {
+    static_assert(Raw<T, VEC>::BYTES == 16, "vector path only");
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p), "l"(pol));
+}
 
 template <typename T, int VEC>
 __device__ __forceinline__ void load_raw(const T* p, Raw<T, VEC>& r) {
@@ -461,6 +476,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k1_stream_kernel(const K1Param
     const int N = (int)prm.N, C = (int)prm.C;
     const int64_t snb = prm.sn * (int64_t)sizeof(T), scb = prm.sc * (int64_t)sizeof(T);  // bytes
     const A Nf = (A)prm.N;
+    const uint64_t policy = l2_evict_first_policy();
     double psum[6];
     int pcnt[3];
 #pragma unroll
@@ -492,7 +508,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k1_stream_kernel(const K1Param
                 const char* r = lrow;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (FULL || ln + u < N) load_raw<T, VEC>(reinterpret_cast<const T*>(r), buf[u]);
+                    if (FULL || ln + u < N) {
+                        if constexpr (Raw<T, VEC>::BYTES == 16)
+                            load_raw_stream<T, VEC>(reinterpret_cast<const T*>(r), buf[u], policy);
+                        else
+                            load_raw<T, VEC>(reinterpret_cast<const T*>(r), buf[u]);
+                    }
                     r += snb;
                 }
                 lrow = r;
@@ -556,11 +577,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k1_stream_kernel(const K1Param
             ee[j] = -(M::kScale == 1.0f ? E[j] : E[j] * M::kScale) / nf;
             mi[j] = pe[j] - ee[j];
         }
-        const int64_t o = b * prm.V + v0;
+        const int64_t o = b * prm.so + v0;
         if (prm.pe) store_f32<VEC>(prm.pe + o, pe);
         if (prm.ee) store_f32<VEC>(prm.ee + o, ee);
         if (prm.mi) store_f32<VEC>(prm.mi + o, mi);
-        if (prm.amax) store_u8<VEC>(prm.amax + o, idx);
+        if (prm.amax) store_u8<VEC>(prm.amax + b * prm.V + v0, idx);
         if (prm.partials) {
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
@@ -760,9 +781,10 @@ extern "C" size_t values_uncertainty_workspace_bytes(int64_t B, int64_t V, int d
 extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B, int64_t N,
                                         int64_t C, int64_t V, int64_t stride_b, int64_t stride_n,
                                         int64_t stride_c, float* pe, float* ee, float* mi,
-                                        uint8_t* mean_argmax, uint8_t* sample_argmax,
-                                        double* scores, const double* thresholds_host,
-                                        void* workspace, size_t workspace_bytes, void* stream) {
+                                        int64_t map_stride_b, uint8_t* mean_argmax,
+                                        uint8_t* sample_argmax, double* scores,
+                                        const double* thresholds_host, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
     if (B < 0 || N <= 0 || C <= 0 || V < 0)
         return set_error(VALUES_ERR_INVALID_ARG, "bad sizes B=%lld N=%lld C=%lld V=%lld",
                          (long long)B, (long long)N, (long long)C, (long long)V);
@@ -780,6 +802,8 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
     prm.pe = pe; prm.ee = ee; prm.mi = mi; prm.amax = mean_argmax; prm.samax = sample_argmax;
     prm.need_ent = (pe || ee || mi || scores) ? 1 : 0;
     prm.inv_n = (float)(1.0 / (double)N);
+    prm.so = map_stride_b > 0 ? map_stride_b : V;
+    if (prm.so < V) return set_error(VALUES_ERR_INVALID_ARG, "map_stride_b < V");
     prm.has_thr = thresholds_host ? 1 : 0;
     for (int k = 0; k < 3; ++k) prm.thr_f[k] = thresholds_host ? (float)thresholds_host[k] : 0.f;
     if (N * C > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "N*C too large");
@@ -797,7 +821,7 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
     const int nv = 16 / (int)es;
     auto al = [](const void* p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; };
     const bool aligned = V % nv == 0 && stride_b % nv == 0 && stride_n % nv == 0 &&
-                         stride_c % nv == 0 && al(probs, 16) && al(pe, 16) && al(ee, 16) &&
+                         stride_c % nv == 0 && prm.so % 4 == 0 && al(probs, 16) && al(pe, 16) && al(ee, 16) &&
                          al(mi, 16) && al(mean_argmax, nv) && al(sample_argmax, nv);
     int rc;
     switch (dtype) {

@@ -13,7 +13,8 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from .aggregation import ISCLOSE_ATOL, ISCLOSE_RTOL, patch_max
+from . import _lib
+from .aggregation import ISCLOSE_ATOL, ISCLOSE_RTOL, patch_max, patch_max_workspace_bytes
 from .uncertainty import MAP_KEYS, uncertainty_fused
 
 # column layout of the score table [B, 3 maps, N_COLS]
@@ -29,7 +30,9 @@ class AggregationConfig:
     patch_mean: bool = False
     thresholds: Optional[Sequence[float]] = None  # (pred_entropy, aleatoric, epistemic)
     threshold_mean: bool = True
-    l2_budget_bytes: int = 80 << 20            # maps + K2b intermediate of one chunk stay L2-resident (126 MB L2)
+    chunk_bytes: int = 256 << 20               # fp32 map scratch per chunk (8-10 128^3 volumes: enough
+                                               # K2b CTAs for several waves; K1 keeps the maps
+                                               # L2-friendly by reading its input evict-first)
 
 
 @dataclass
@@ -80,16 +83,30 @@ class PipelineResult:
 
 
 class UncertaintyPipeline:
+    """K1 -> K2b over chunks of volumes with every buffer preallocated and reused: per chunk
+    the host issues two C-ABI calls (one K1 launch + a 4-byte memset, two K2b launches) and
+    nothing else; the score table is assembled once per run.  Never synchronises."""
+
     def __init__(self, cfg: Optional[AggregationConfig] = None):
         self.cfg = cfg or AggregationConfig()
-        self._maps_buf: Optional[torch.Tensor] = None
+        self._bufs: Dict[tuple, torch.Tensor] = {}
         # optional list; when set, (start_event, end_event, n_volumes) is appended per K1 launch
         # (CUDA events on the launching stream -- bench.py's roofline measurement)
         self.k1_timer: Optional[list] = None
 
     def _chunk(self, B: int, V: int) -> int:
-        per_volume = 3 * V * (4 + 8)  # three fp32 maps + their fp64 z/x box sums (K2b workspace)
-        return max(1, min(B, self.cfg.l2_budget_bytes // max(per_volume, 1)))
+        per_volume = 3 * V * 4  # three fp32 maps
+        return max(1, min(B, self.cfg.chunk_bytes // max(per_volume, 1)))
+
+    def _buf(self, name: str, shape, dtype, dev) -> torch.Tensor:
+        """Grow-only scratch tensors keyed by (name, dtype, device)."""
+        key = (name, dtype, dev)
+        n = int(np.prod(shape)) if len(shape) else 1
+        t = self._bufs.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype, device=dev)
+            self._bufs[key] = t
+        return t[:n].view(shape)
 
     def run(self, probs: torch.Tensor, ssn: bool = False, keep_maps: bool = False,
             mean_argmax: bool = False) -> PipelineResult:
@@ -106,40 +123,43 @@ class UncertaintyPipeline:
         thr = cfg.thresholds  # given per reference key; K1 wants (pe, ee, mi) order
         if thr is not None and ssn:
             thr = (thr[0], thr[2], thr[1])
-        scores = torch.zeros((B, 3, N_COLS), dtype=torch.float64, device=dev)
+        cb = self._chunk(B, V)
+        if keep_maps:   # K1 writes straight into the kept [B, 3, *S] buffer, chunk by chunk
+            maps_all = torch.empty((B, 3) + spatial, dtype=torch.float32, device=dev)
+        else:
+            maps_buf = self._buf("maps", (cb, 3) + spatial, torch.float32, dev)
+        k1_scores = self._buf("k1_scores", (B, 3, 3), torch.float64, dev)
         am = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev) if mean_argmax else None
-        all_maps = torch.empty((3, B) + spatial, dtype=torch.float32, device=dev) if keep_maps else None
-        cb = B if keep_maps and patch is None else self._chunk(B, V)
-        if not keep_maps:
-            if (self._maps_buf is None or self._maps_buf.device != dev
-                    or self._maps_buf.numel() < 3 * cb * V):
-                self._maps_buf = torch.empty(3 * cb * V, dtype=torch.float32, device=dev)
+        k1_ws_bytes = _lib.lib.values_uncertainty_workspace_bytes(cb, V, _lib.dtype_code(probs.dtype))
+        k1_ws = self._buf("k1_ws", (max(k1_ws_bytes, 8),), torch.uint8, dev)
+        if patch is not None:
+            ps = self._buf("patch_score", (B * 3,), torch.float64, dev)
+            bb = self._buf("patch_bbox", (B * 3, 3), torch.int64, dev)
+            k2_ws = self._buf("k2_ws", (max(patch_max_workspace_bytes(cb * 3, spatial, patch), 8),),
+                              torch.uint8, dev)
         for b0 in range(0, B, cb):
             b1 = min(b0 + cb, B)
             nb = b1 - b0
-            if keep_maps:
-                # [3, nb, *S] slice of the kept buffer is not contiguous across maps: K1 writes
-                # through a contiguous scratch only when chunked; with keep_maps write per chunk
-                buf = torch.empty((3, nb) + spatial, dtype=torch.float32, device=dev) if cb < B else all_maps
-            else:
-                buf = self._maps_buf[:3 * nb * V].view((3, nb) + spatial)
+            buf = maps_all[b0:b1] if keep_maps else maps_buf[:nb]
             if self.k1_timer is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            res = uncertainty_fused(probs[b0:b1], maps=True, mean_argmax=mean_argmax, scores=True,
-                                    thresholds=thr, out_maps=buf)
+            uncertainty_fused(probs[b0:b1], maps=True, mean_argmax=mean_argmax, scores=True,
+                              thresholds=thr, out_maps=buf, volume_major=True,
+                              out_scores=k1_scores[b0:b1], out_argmax=am[b0:b1] if mean_argmax else None,
+                              workspace=k1_ws)
             if self.k1_timer is not None:
                 ev1.record()
                 self.k1_timer.append((ev0, ev1, nb))
-            scores[b0:b1, :, :3] = res.scores
-            if mean_argmax:
-                am[b0:b1] = res.mean_argmax
             if patch is not None:
-                ps, bbox = patch_max(buf.view((3 * nb,) + spatial), patch, mean=cfg.patch_mean,
-                                     rtol=ISCLOSE_RTOL, atol=ISCLOSE_ATOL)
-                scores[b0:b1, :, COL_PATCH_MAX] = ps.view(3, nb).t()
-                scores[b0:b1, :, COL_BBOX + 3 - nd:COL_BBOX + 3] = bbox.reshape(3, nb, nd).permute(1, 0, 2).to(torch.float64)
-            if keep_maps and cb < B:
-                all_maps[:, b0:b1] = buf
-        return PipelineResult(scores=scores, maps=all_maps, mean_argmax=am, ssn=ssn, patch_size=patch,
+                patch_max(buf.view((3 * nb,) + spatial), patch, mean=cfg.patch_mean,
+                          rtol=ISCLOSE_RTOL, atol=ISCLOSE_ATOL, out_score=ps[3 * b0:3 * b1],
+                          out_bbox=bb[3 * b0:3 * b1], workspace=k2_ws)
+        scores = torch.zeros((B, 3, N_COLS), dtype=torch.float64, device=dev)
+        scores[:, :, :3] = k1_scores
+        if patch is not None:
+            scores[:, :, COL_PATCH_MAX] = ps.view(B, 3)
+            scores[:, :, COL_BBOX + 3 - nd:COL_BBOX + 3] = bb.view(B, 3, 3)[:, :, 3 - nd:]
+        return PipelineResult(scores=scores, maps=maps_all.permute(1, 0, *range(2, 2 + nd)) if keep_maps else None,
+                              mean_argmax=am, ssn=ssn, patch_size=patch,
                               thresholds=cfg.thresholds, threshold_mean=cfg.threshold_mean)

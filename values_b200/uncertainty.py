@@ -77,12 +77,20 @@ def uncertainty_fused(
     scores: bool = False,
     thresholds: Optional[Sequence[float]] = None,
     out_maps: Optional[torch.Tensor] = None,
+    volume_major: bool = False,
+    out_scores: Optional[torch.Tensor] = None,
+    out_argmax: Optional[torch.Tensor] = None,
+    workspace: Optional[torch.Tensor] = None,
 ) -> FusedResult:
     """One HBM sweep over `probs` [B, N, C, *S] (CUDA; B/N/C axes may be strided views, e.g.
     a permuted [N, B, C, H, W] stack as test_2D.py:317 builds it).
 
     thresholds: (pe, ee, mi) scalars for the fused threshold sums (aggregate_uncertainties.py:61-62).
-    out_maps:   optional preallocated fp32 [3, B, *S] buffer (pe, ee, mi) to write into.
+    out_maps:   optional preallocated fp32 buffer to write the maps into: [3, B, *S] (pe, ee, mi
+                planes, map-major) or, with volume_major=True, [B, 3, *S] -- the layout K2b
+                consumes as 3B consecutive maps.
+    out_scores / out_argmax / workspace: optional preallocated outputs ([B, 3, 3] fp64,
+                [B, *S] uint8, uint8 scratch) so that a pipeline can run without allocating.
     """
     if probs.dim() < 3:
         raise ValueError("probs must be [B, N, C, *spatial]")
@@ -95,22 +103,42 @@ def uncertainty_fused(
     V = int(np.prod(spatial)) if spatial else 1
     sb, sn, sc = probs.stride()[:3]
     pe = ee = mi = None
+    map_stride_b = 0
     if maps:
+        want = ((B, 3) if volume_major else (3, B)) + spatial
         if out_maps is None:
-            out_maps = torch.empty((3, B) + spatial, dtype=torch.float32, device=dev)
-        elif (out_maps.shape != (3, B) + spatial or out_maps.dtype != torch.float32
+            out_maps = torch.empty(want, dtype=torch.float32, device=dev)
+        elif (tuple(out_maps.shape) != want or out_maps.dtype != torch.float32
               or not out_maps.is_contiguous() or out_maps.device != dev):
-            raise ValueError("out_maps must be a contiguous fp32 [3, B, *S] CUDA tensor")
-        pe, ee, mi = out_maps[0], out_maps[1], out_maps[2]
-    am = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev) if mean_argmax else None
+            raise ValueError(f"out_maps must be a contiguous fp32 {want} CUDA tensor")
+        if volume_major:
+            pe, ee, mi = out_maps[:, 0], out_maps[:, 1], out_maps[:, 2]
+            map_stride_b = 3 * V
+        else:
+            pe, ee, mi = out_maps[0], out_maps[1], out_maps[2]
+    if mean_argmax:
+        if out_argmax is None:
+            out_argmax = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev)
+        elif tuple(out_argmax.shape) != (B,) + spatial or out_argmax.dtype != torch.uint8 \
+                or not out_argmax.is_contiguous():
+            raise ValueError("out_argmax must be a contiguous uint8 [B, *S] tensor")
+    am = out_argmax if mean_argmax else None
     sam = torch.empty((B, N) + spatial, dtype=torch.uint8, device=dev) if sample_argmax else None
     sc_out = ws = None
     ws_bytes = 0
     thr = None
     if scores:
-        sc_out = torch.empty((B, 3, 3), dtype=torch.float64, device=dev)
+        if out_scores is None:
+            out_scores = torch.empty((B, 3, 3), dtype=torch.float64, device=dev)
+        elif tuple(out_scores.shape) != (B, 3, 3) or out_scores.dtype != torch.float64 \
+                or not out_scores.is_contiguous():
+            raise ValueError("out_scores must be a contiguous fp64 [B, 3, 3] tensor")
+        sc_out = out_scores
         ws_bytes = _lib.lib.values_uncertainty_workspace_bytes(B, V, _lib.dtype_code(probs.dtype))
-        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+        if workspace is not None and workspace.numel() * workspace.element_size() >= ws_bytes:
+            ws = workspace
+        else:
+            ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
         if thresholds is not None:
             if len(thresholds) != 3:
                 raise ValueError("thresholds must be (pe, ee, mi)")
@@ -118,7 +146,7 @@ def uncertainty_fused(
     with torch.cuda.device(dev):
         rc = _lib.lib.values_uncertainty_fused(
             probs.data_ptr(), _lib.dtype_code(probs.dtype), B, N, C, V, sb, sn, sc,
-            _lib.ptr(pe), _lib.ptr(ee), _lib.ptr(mi), _lib.ptr(am), _lib.ptr(sam),
+            _lib.ptr(pe), _lib.ptr(ee), _lib.ptr(mi), map_stride_b, _lib.ptr(am), _lib.ptr(sam),
             _lib.ptr(sc_out), thr, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
     _lib.check(rc)
     return FusedResult(pe, ee, mi, am, sam, sc_out)
