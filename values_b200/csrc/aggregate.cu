@@ -250,12 +250,15 @@ __global__ void patch_finish_kernel(const unsigned long long* __restrict__ best,
 // tiles whose maximum is np.isclose to the global one and takes the minimum C-order index;
 // the last CTA of a map (ticket) converts it to the bounding box, so there is no select /
 // finish launch.  fp64 throughout: the result is independent of tiling and launch shape.
+constexpr int kFusedThreads = 256;   // measured: the march is shared-memory-bandwidth bound, so fewer
+                                     // threads with more outputs each (register reuse) beat 512
+constexpr int kMaxActive = 64;       // pass-2 work list entries per map (more -> full re-walk)
+
 template <int TY, int TX> struct FusedTile {
-    static constexpr int kSegF = 8;
-    static constexpr int kOwnF = TY * TX / kThreads;   // consecutive y outputs per thread
-    static constexpr int kStrips = kThreads / TX;      // strips of kOwnF rows
-    static constexpr int kStage = 8;                   // staged input elements per thread
-    static_assert(kOwnF * kStrips == TY, "tile shape");
+    static constexpr int kSegF = 8;                          // outputs per x-pass task
+    static constexpr int kOwnF = TY * TX / kFusedThreads;    // consecutive y outputs per thread
+    static constexpr int kStage = 8;                         // staged input elements per thread
+    static_assert(kOwnF >= 1 && kOwnF * (kFusedThreads / TX) == TY, "tile shape");
 };
 
 struct FusedParams {
@@ -270,22 +273,42 @@ struct FusedParams {
     int mean_flag;
     double rtol, atol;
     double* tile_max;             // [M, ntiles]
+    double* gmax;                 // [M]   written by the last pass-1 CTA of a map
+    int* active;                  // [M, 1 + kMaxActive]: count (or -1 = walk every tile), tiles
     unsigned long long* best;     // [M]
-    unsigned int* tickets;        // [M]
+    unsigned int* tickets;        // [M, 2]  pass-1 / pass-2 arrival counters
     double* max_score;            // [M]
     int64_t* bbox_lo;             // [M, 3]
 };
 
 __device__ __noinline__ double box_mean_div(double s, double denom) { return s / denom; }  // mean=True only
 
+// sum of N consecutive doubles as a balanced tree (short dependency chains)
+template <int N> __device__ __forceinline__ double tree_sum(const double* v) {
+    if constexpr (N == 1) return v[0];
+    else return tree_sum<N / 2>(v) + tree_sum<N - N / 2>(v + N / 2);
+}
+
+// One kernel does all three box passes: a CTA owns TY x TX windows in-plane and a chunk of
+// output planes, marching over z.  Per input plane: (1) the plane tile (+halo) goes from L2
+// to shared memory through registers, one plane AHEAD of the arithmetic, widened to fp64;
+// (2) x-pass: tasks of 8 outputs, rows striped over lanes (odd pitch -> conflict-free);
+// (3) y-pass: a thread owns kOwnF consecutive rows of one column, z-pass: sliding over a
+// shared-memory ring of the last p0 plane sums.  Two block barriers per plane.
+// PASS 1 keeps the tile maximum; the last CTA of a map (ticket) reduces them to the map
+// maximum and lists the tiles whose maximum is np.isclose to it.  PASS 2 re-walks only the
+// listed tiles (split finer in z) for the minimum C-order index; its last CTA converts it to
+// the bounding-box corner.  fp64 throughout: results do not depend on tiling or launch shape.
 // PC > 0: in-plane patch extents p1 == p2 == PC known at compile time (the reference's configs
 // all use 10: evaluation/configs/tasks/aggregation_patch_*.yaml), so both box loops unroll.
 template <typename T, int TY, int TX, int PC, int PASS>
-__global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParams prm) {
+__global__ void __launch_bounds__(kFusedThreads, 2) box_fused_kernel(const FusedParams prm) {
     using FT = FusedTile<TY, TX>;
+    constexpr int NT = kFusedThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[8];
+    __shared__ double red[NT / 32];
     __shared__ int s_flag;
+    __shared__ int s_count;
     const int p1 = PC > 0 ? PC : prm.p1, p2 = PC > 0 ? PC : prm.p2, p0 = prm.p0;
     const int R = TY + p1 - 1, W = TX + p2 - 1;
     const int pitch_in = W | 1, pitch_rs = TX + 1;
@@ -296,38 +319,32 @@ __global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParam
     const int64_t m = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
-    // pass 2 runs on a finer z split (prm.zsub sub-chunks per pass-1 chunk) so that the few
-    // surviving tiles finish quickly; tile_max is indexed by the pass-1 (coarse) tile
-    int tile = blockIdx.x;
-    const int tx_i = tile % prm.tiles_x; tile /= prm.tiles_x;
-    const int ty_i = tile % prm.tiles_y; tile /= prm.tiles_y;
+    const int tiles_xy = prm.tiles_x * prm.tiles_y;
     const int zsub = PASS == 2 ? prm.zsub : 1;
     const int zc_fine = prm.zc / zsub;
-    const int64_t coarse = ((int64_t)(tile / zsub) * prm.tiles_y + ty_i) * prm.tiles_x + tx_i;
     double gmax = 0.0;
-    bool active = true;
-    if (PASS == 1) {
-        if (blockIdx.x == 0 && tid == 0) { prm.best[m] = ~0ull; prm.tickets[m] = 0u; }
-    } else {
-        // global maximum of this map from the pass-1 tile maxima (NaN propagates, as np.max)
-        double mm = ninf;
-        for (int64_t i = tid; i < prm.ntiles; i += kThreads) mm = nanmax(mm, prm.tile_max[m * prm.ntiles + i]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mm = nanmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-        if (lane == 0) red[warp] = mm;
-        __syncthreads();
-        gmax = red[0];
-#pragma unroll
-        for (int w = 1; w < kThreads / 32; ++w) gmax = nanmax(gmax, red[w]);
-        __syncthreads();
-        active = np_isclose(prm.tile_max[m * prm.ntiles + coarse], gmax, prm.rtol, prm.atol);
-    }
-    const int64_t zo0 = (int64_t)tile * zc_fine;
-    const int64_t zo1 = min(zo0 + zc_fine, min((int64_t)(tile / zsub + 1) * prm.zc, prm.O0));
-    if (zo0 >= zo1) active = false;
     unsigned long long tbest = ~0ull;
     double tmax = ninf;
-    if (active) {
+    // ---- work items of this CTA: pass 1 = its own tile; pass 2 = (listed tile, z sub-chunk)
+    int n_work = 1, work = 0, work_step = 1;
+    const int* list = nullptr;
+    if (PASS == 2) {
+        gmax = prm.gmax[m];
+        list = prm.active + m * (1 + kMaxActive);
+        const int n_act = list[0];
+        n_work = (n_act < 0 ? (int)prm.ntiles : n_act) * zsub;
+        work = blockIdx.x; work_step = gridDim.x;
+    }
+    for (; work < n_work; work += work_step) {
+        int tile, fine;
+        if (PASS == 1) { tile = blockIdx.x; fine = 0; }
+        else { const int a = work / zsub; fine = work - a * zsub; tile = list[0] < 0 ? a : list[1 + a]; }
+        const int tx_i = tile % prm.tiles_x;
+        const int ty_i = (tile / prm.tiles_x) % prm.tiles_y;
+        const int zc_i = tile / tiles_xy;
+        const int64_t zo0 = (int64_t)zc_i * prm.zc + (int64_t)fine * zc_fine;
+        const int64_t zo1 = min(zo0 + zc_fine, min((int64_t)(zc_i + 1) * prm.zc, prm.O0));
+        if (zo0 >= zo1) continue;
         const int64_t x0 = (int64_t)tx_i * TX, y0 = (int64_t)ty_i * TY;
         const int nplanes = (int)(zo1 - zo0) + p0 - 1;
         const T* src = reinterpret_cast<const T*>(prm.maps) + m * prm.stride_m;
@@ -339,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParam
         int goff[FT::kStage], soff[FT::kStage];
 #pragma unroll
         for (int i = 0; i < FT::kStage; ++i) {
-            const int idx = tid + i * kThreads;
+            const int idx = tid + i * NT;
             goff[i] = -1; soff[i] = -1;
             if (idx < n_in) {
                 const int r = idx / W, cx = idx - r * W;
@@ -348,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParam
                 if (y < prm.D1 && x < prm.D2) goff[i] = (int)(y * prm.D2 + x);
             }
         }
-        const bool staged = n_in <= FT::kStage * kThreads && plane_elems < 0x7fffffffLL;
+        const bool staged = n_in <= FT::kStage * NT && plane_elems < 0x7fffffffLL;
         T st[FT::kStage];
         auto fetch = [&](int64_t z) {
             const T* pl = src + z * plane_elems;
@@ -361,14 +378,14 @@ __global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParam
         };
         auto load_direct = [&](int64_t z) {   // halo too large for the register stage
             const T* pl = src + z * plane_elems;
-            for (int idx = tid; idx < n_in; idx += kThreads) {
+            for (int idx = tid; idx < n_in; idx += NT) {
                 const int r = idx / W, cx = idx - r * W;
                 const int64_t y = y0 + r, x = x0 + cx;
                 in_tile[r * pitch_in + cx] =
                     (y < prm.D1 && x < prm.D2) ? (double)In<T>::load_one(pl + y * prm.D2 + x) : 0.0;
             }
         };
-        // x-pass tasks: (row r, segment of 8 outputs), rows striped over lanes
+        // x-pass tasks: (row r, segment of kSegF outputs), rows striped over lanes
         const int ntask = R * (TX / FT::kSegF);
         const int task_r = tid % R, task_seg = tid / R;
         const int ox = tid % TX, oy0 = (tid / TX) * FT::kOwnF;   // y/z-pass ownership
@@ -382,17 +399,16 @@ __global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParam
         auto x_task = [&](int r, int seg) {
             const double* row = in_tile + r * pitch_in + seg * FT::kSegF;
             double* dst = rowsum + r * pitch_rs + seg * FT::kSegF;
-            double s = 0.0;
             if constexpr (PC > 0) {
                 double v[PC + FT::kSegF - 1];
 #pragma unroll
                 for (int k = 0; k < PC + FT::kSegF - 1; ++k) v[k] = row[k];
-#pragma unroll
-                for (int k = 0; k < PC; ++k) s += v[k];
+                double s = tree_sum<PC>(v);
                 dst[0] = s;
 #pragma unroll
                 for (int i = 1; i < FT::kSegF; ++i) { s += v[i + PC - 1] - v[i - 1]; dst[i] = s; }
             } else {
+                double s = 0.0;
                 for (int k = 0; k < p2; ++k) s += row[k];
                 dst[0] = s;
 #pragma unroll
@@ -400,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParam
             }
         };
 
+        __syncthreads();   // previous work item of this CTA is done with the shared tiles
         if (staged) fetch(zo0);
         int slot = 0;
         for (int zi = 0; zi < nplanes; ++zi) {
@@ -408,15 +425,18 @@ __global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParam
             if (staged && zi + 1 < nplanes) fetch(zo0 + zi + 1);   // next plane, in flight during the math
             // ---- x-pass
             if (tid < ntask) x_task(task_r, task_seg);
-            for (int task = tid + kThreads; task < ntask; task += kThreads) x_task(task % R, task / R);
+            for (int task = tid + NT; task < ntask; task += NT) x_task(task % R, task / R);
             __syncthreads();
             // ---- y-pass (sliding down the strip) + z-pass (sliding over the ring)
             const double* col = rowsum + oy0 * pitch_rs + ox;
-            double s2 = 0.0;
+            double s2;
             if constexpr (PC > 0) {
+                double c[PC];
 #pragma unroll
-                for (int j = 0; j < PC; ++j) s2 += col[j * pitch_rs];
+                for (int j = 0; j < PC; ++j) c[j] = col[j * pitch_rs];
+                s2 = tree_sum<PC>(c);
             } else {
+                s2 = 0.0;
                 for (int j = 0; j < p1; ++j) s2 += col[j * pitch_rs];
             }
             const bool warm = zi >= p0 - 1;     // the z-window is complete: an output plane
@@ -450,8 +470,38 @@ __global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParam
         __syncthreads();
         if (tid == 0) {
             double mm = red[0];
-            for (int w = 1; w < kThreads / 32; ++w) mm = nanmax(mm, red[w]);
+            for (int w = 1; w < NT / 32; ++w) mm = nanmax(mm, red[w]);
             prm.tile_max[m * prm.ntiles + blockIdx.x] = mm;
+            __threadfence();
+            s_flag = atomicAdd(prm.tickets + 2 * m, 1u) == gridDim.x - 1;
+            s_count = 0;
+        }
+        __syncthreads();
+        if (!s_flag) return;
+        // last CTA of this map: map maximum (NaN propagates, as np.max) and the pass-2 work list
+        __threadfence();
+        const double* tm = prm.tile_max + m * prm.ntiles;
+        double mm = ninf;
+        for (int64_t i = tid; i < prm.ntiles; i += NT) mm = nanmax(mm, __ldcg(tm + i));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mm = nanmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        if (lane == 0) red[warp] = mm;
+        __syncthreads();
+        double g = red[0];
+        for (int w = 1; w < NT / 32; ++w) g = nanmax(g, red[w]);
+        int* lst = prm.active + m * (1 + kMaxActive);
+        for (int64_t i = tid; i < prm.ntiles; i += NT) {   // list order is irrelevant (min index wins)
+            if (np_isclose(__ldcg(tm + i), g, prm.rtol, prm.atol)) {
+                const int n = atomicAdd(&s_count, 1);
+                if (n < kMaxActive) lst[1 + n] = (int)i;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            lst[0] = s_count > kMaxActive ? -1 : s_count;
+            prm.gmax[m] = g;
+            prm.max_score[m] = g;
+            prm.best[m] = ~0ull;
         }
     } else {
 #pragma unroll
@@ -460,17 +510,16 @@ __global__ void __launch_bounds__(kThreads, 2) box_fused_kernel(const FusedParam
             tbest = other < tbest ? other : tbest;
         }
         if (lane == 0 && tbest != ~0ull) atomicMin(prm.best + m, tbest);  // min is order-free
-        // last CTA of this map: publish max_score and the bounding-box corner
+        // last CTA of this map: publish the bounding-box corner
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            s_flag = atomicAdd(prm.tickets + m, 1u) == gridDim.x - 1;
+            s_flag = atomicAdd(prm.tickets + 2 * m + 1, 1u) == gridDim.x - 1;
         }
         __syncthreads();
         if (s_flag && tid == 0) {
             __threadfence();
             const unsigned long long b = atomicMin(prm.best + m, ~0ull);  // atomic read
-            prm.max_score[m] = gmax;
             int64_t* bb = prm.bbox_lo + 3 * m;
             if (b == ~0ull) {  // no window is close to the max (NaN map): the reference raises IndexError
                 bb[0] = bb[1] = bb[2] = -1;
@@ -813,12 +862,18 @@ static int run_patch_fused_pc(FusedParams prm, const FusedPlan& pl, int64_t M, c
         FusedParams q = prm;
         q.maps = reinterpret_cast<const T*>(prm.maps) + m0 * prm.stride_m;
         q.tile_max = prm.tile_max + m0 * pl.ntiles;
-        q.best = prm.best + m0; q.tickets = prm.tickets + m0;
+        q.best = prm.best + m0;
         q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
-        k1<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kThreads, smem, st>>>(q);
+        q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
+        q.tickets = prm.tickets + 2 * m0;
+        if (cudaMemsetAsync(q.tickets, 0, (size_t)mc * 2 * sizeof(unsigned int), st) != cudaSuccess)
+            return set_error(VALUES_ERR_CUDA, "patch_max: cudaMemsetAsync failed");
+        k1<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kFusedThreads, smem, st>>>(q);
         int rc = check_launch("box_fused_kernel<1>");
         if (rc) return rc;
-        k2<<<dim3((unsigned)(pl.ntiles * pl.zsub), (unsigned)mc), kThreads, smem, st>>>(q);
+        // pass 2: a few CTAs per map walk the (normally one-entry) work list
+        const unsigned g2 = (unsigned)std::min<int64_t>(pl.ntiles * pl.zsub, 4 * pl.zsub);
+        k2<<<dim3(g2, (unsigned)mc), kFusedThreads, smem, st>>>(q);
         if ((rc = check_launch("box_fused_kernel<2>"))) return rc;
     }
     return VALUES_OK;
@@ -830,8 +885,9 @@ static int run_patch_fused(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
     return run_patch_fused_pc<T, TY, TX, 0>(prm, pl, M, st);
 }
 
+// tile_max [M, ntiles] | gmax [M] | best [M] | tickets [M, 2] (one 8-byte slot) | active [M, 1 + kMaxActive] ints
 static size_t fused_workspace_bytes(int64_t M, const FusedPlan& pl) {
-    return (size_t)(M * pl.ntiles + 2 * M) * sizeof(double);  // tile_max | best | tickets (8-byte slots)
+    return (size_t)(M * pl.ntiles + 3 * M) * sizeof(double) + (size_t)M * (1 + kMaxActive) * sizeof(int);
 }
 
 }  // namespace vb
@@ -955,8 +1011,10 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
             prm.zsub = fp.zsub; prm.ntiles = fp.ntiles;
             prm.denom = denom; prm.mean_flag = mean_flag ? 1 : 0; prm.rtol = rtol; prm.atol = atol;
             prm.tile_max = ws;
-            prm.best = reinterpret_cast<unsigned long long*>(ws + M * fp.ntiles);
-            prm.tickets = reinterpret_cast<unsigned int*>(ws + M * fp.ntiles + M);
+            prm.gmax = ws + M * fp.ntiles;
+            prm.best = reinterpret_cast<unsigned long long*>(ws + M * fp.ntiles + M);
+            prm.tickets = reinterpret_cast<unsigned int*>(ws + M * fp.ntiles + 2 * M);
+            prm.active = reinterpret_cast<int*>(ws + M * fp.ntiles + 3 * M);
             prm.max_score = max_score; prm.bbox_lo = bbox_lo;
             if (fp.ty == 16) {
                 if (dtype == VALUES_F32) return run_patch_fused<float, 16, 64>(prm, fp, M, st);
