@@ -8,8 +8,9 @@ K2 patch max, score gather) over one pool of synthetic softmax stacks per rank.
 
 Under torchrun (N > 1) every rank processes its own pool (volume-sharded, weak scaling); the
 only collective is the all_gather of the per-image score table.  Rank 0 prints ONE JSON line.
-`--impl reference` times the CPU oracle port of the reference (oracle/values_oracle.py --
-the reference itself is pure Python and cannot travel to the GPU box) on the host cores.
+`--impl reference` times the reference's own CPU implementation of the path on the host cores:
+the UNMODIFIED reference functions imported from baseline/_ref (offline pip install, git-ignored,
+travels with the snapshot) or, if that is absent, the oracle port (oracle/values_oracle.py).
 """
 from __future__ import annotations
 
@@ -122,72 +123,124 @@ def algorithmic_bytes_per_voxel(wl):
     return wl["N"] * wl["C"] * es + 3 * 4 + 1
 
 
-# ------------------------------------------------------------------------------ CPU oracle arm
-def oracle_volume(vo, x_cpu, thr, patch):
-    """The reference's path for ONE volume on the host: C2 maps, then all three aggregations on
-    each map (FFT box-sum exactly as the reference calls scipy)."""
-    d = vo.calculate_uncertainty(x_cpu)
-    mean_seg = vo.mean_argmax(x_cpu)
-    out = {}
+# ------------------------------------------------------------------------------ CPU reference arm
+# The reference's own path for one unit of work on the host: C2 maps (fp64 stack on the 3D path,
+# fp32 on the 2D path, as the reference feeds it), the arg-max of the mean, then all three C3
+# aggregations on each of the three maps (scipy FFT box sum exactly as the reference calls it).
+# Implementation: the UNMODIFIED reference imported from baseline/_ref (offline pip install,
+# oracle/ref_loader.py) when present -- kind "reference" -- else the oracle port -- kind "port".
+_CPU = {}
+
+
+def _cpu_impl():
+    if "impl" not in _CPU:
+        from oracle import ref_loader
+
+        if ref_loader.available():
+            _CPU["impl"], _CPU["kind"] = ref_loader.load(), "reference"
+        else:
+            from oracle import values_oracle as vo
+
+            _CPU["impl"], _CPU["kind"] = vo, "port"
+    return _CPU["impl"], _CPU["kind"]
+
+
+def cpu_slab_shape(wl):
+    """Bounded sample: a quarter of the leading spatial axis of one volume / image (per-voxel
+    cost of the reference is flat in the volume size; the full volume takes ~6 s per core group)."""
+    sp = list(wl["spatial"])
+    sp[0] = max(sp[0] // 4, min(sp[0], 2 * wl["patch"]))
+    return tuple(sp)
+
+
+def _cpu_worker_init(wl, threads, seed):
+    torch.set_num_threads(threads)
+    impl, _ = _cpu_impl()
+    g = torch.Generator().manual_seed(seed + os.getpid() % 1000)
+    shape = (wl["N"], wl["C"]) + cpu_slab_shape(wl)
+    x = torch.softmax(torch.randn(shape, generator=g) * 3.0, dim=1)
+    _CPU["x"] = x.double() if len(wl["spatial"]) == 3 else x
+    _CPU["wl"] = wl
+
+
+def _cpu_worker_step(_):
+    impl, _k = _cpu_impl()
+    x, wl = _CPU["x"], _CPU["wl"]
+    thr = (0.5, 0.4, 0.05)
+    d = impl.calculate_uncertainty(x)
+    mean_seg = torch.argmax(torch.mean(x, dim=0), dim=0)  # data_carrier_3D.py:253-259 / test_2D.py:119-127
+    out = []
     for k, key in enumerate(("pred_entropy", "aleatoric_uncertainty", "epistemic_uncertainty")):
         m = d[key].numpy()
-        out[key] = (vo.patch_level_aggregation(m, patch, method="fft"),
-                    vo.image_level_aggregation(m), vo.threshold_aggregation(m, threshold=thr[k]))
-    return out, mean_seg
+        out.append((impl.patch_level_aggregation(m, wl["patch"])["max_score"],
+                    impl.image_level_aggregation(m)["max_score"],
+                    float(impl.threshold_aggregation(m, threshold=thr[k])["max_score"])))
+    return int(mean_seg.numel()), out
 
 
-def host_stack(wl, seed, n_vol):
-    g = torch.Generator().manual_seed(seed)
-    shape = (n_vol, wl["N"], wl["C"]) + tuple(wl["spatial"])
-    x = torch.softmax(torch.randn(shape, generator=g) * 3.0, dim=2)
-    # the reference feeds fp64 on the 3D path (test_3D.py:532) and fp32 on the 2D path
-    return x.double() if len(wl["spatial"]) == 3 else x
+class CpuReference:
+    """Pool of worker processes, each running the reference path on its own slab with its share
+    of the host threads; one step = one slab per worker."""
 
+    def __init__(self, wl):
+        import torch.multiprocessing as mp
 
-def run_cpu_sample(wl, n_vol, repeats=1):
-    from oracle import values_oracle as vo
+        cores = os.cpu_count() or 1
+        self.workers = max(1, min(8, cores // 4))
+        self.threads = max(1, cores // self.workers)
+        self.cores = self.workers * self.threads
+        self.wl = wl
+        self.slab_vox = int(np.prod(cpu_slab_shape(wl)))
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(self.workers, initializer=_cpu_worker_init, initargs=(wl, self.threads, 4321))
+        self.kind = _cpu_impl()[1]
 
-    x = host_stack(wl, 4321, n_vol)
-    thr = (0.5, 0.4, 0.05)
-    V = int(np.prod(wl["spatial"]))
-    t0 = time.perf_counter()
-    for _ in range(repeats):
-        for i in range(n_vol):
-            oracle_volume(vo, x[i], thr, wl["patch"])
-    dt = time.perf_counter() - t0
-    return n_vol * repeats * V / dt, dt
+    def step(self):
+        res = self.pool.map(_cpu_worker_step, range(self.workers))
+        return sum(r[0] for r in res)
+
+    def run(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        vox = 0
+        for _ in range(steps):
+            vox += self.step()
+        dt = time.perf_counter() - t0
+        return vox / dt, dt
+
+    def describe(self, steps, dt):
+        return (f"{steps} step(s) x {self.workers} slab(s) {cpu_slab_shape(self.wl)} of the workload "
+                f"(N={self.wl['N']}, C={self.wl['C']}, fp64 3D / fp32 2D as the reference feeds it), "
+                f"{self.workers} worker processes x {self.threads} torch threads, {dt:.1f} s, "
+                f"os.cpu_count()={os.cpu_count()}; implementation: "
+                + ("unmodified reference functions from baseline/_ref" if self.kind == "reference"
+                   else "oracle/values_oracle.py port"))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def reference_arm(args, wl, rank):
     if rank != 0:
         return
-    V = int(np.prod(wl["spatial"]))
-    from oracle import values_oracle as vo
-
-    x = host_stack(wl, 4321, 1)
-    thr = (0.5, 0.4, 0.05)
-    for _ in range(args.warmup):
-        oracle_volume(vo, x[0], thr, wl["patch"])
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_volume(vo, x[0], thr, wl["patch"])
-    dt = time.perf_counter() - t0
-    value = args.steps * V / dt
-    cores = torch.get_num_threads()
+    ref = CpuReference(wl)
+    value, dt = ref.run(args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64" if len(wl["spatial"]) == 3 else "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "volumes_per_step": 1,
-                   "note": "CPU oracle port of the reference (pure-Python reference cannot travel); "
-                           "rank 0 only, host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x 1 volume of the workload shape, "
-                                   f"os.cpu_count()={os.cpu_count()}"},
+        "config": {"workload": wl["name"], "slabs_per_step": ref.workers,
+                   "slab_shape": list(cpu_slab_shape(wl)),
+                   "note": "the reference's own CPU implementation of the path on the host cores; rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                         "sample": ref.describe(args.steps, dt)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    ref.close()
     print(json.dumps(line), flush=True)
 
 
@@ -296,12 +349,12 @@ def main():
         e2e = run_e2e(vb, wl, cfg, dev, stack, world, args)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_cpu = 2 if V >= (1 << 21) else (4 if V >= (1 << 20) else 32)
-        cpu_value, cpu_s = run_cpu_sample(wl, n_cpu)
-        cpu = {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{n_cpu} volume(s) of the workload shape through oracle/values_oracle.py "
-                         f"(fp64 3D / fp32 2D as the reference feeds it), {cpu_s:.1f} s, "
-                         f"os.cpu_count()={os.cpu_count()}"}
+        ref = CpuReference(wl)
+        cpu_steps = 4
+        cpu_value, cpu_s = ref.run(cpu_steps, 1)
+        cpu = {"value": cpu_value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+               "sample": ref.describe(cpu_steps, cpu_s)}
+        ref.close()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -19,7 +19,25 @@ import sys
 import types
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("VALUES_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    """VALUES_REFERENCE_ROOT, else the read-only mount of the build container, else the offline
+    pip install of the UNMODIFIED reference under baseline/_ref (git-ignored; it travels to the
+    GPU box with the snapshot, which is how `bench.py --impl reference` runs the real thing there):
+        python -m pip install --no-index --no-build-isolation --no-deps --ignore-requires-python \
+            --target baseline/_ref <copy of /root/reference>
+    (--ignore-requires-python because setup.py pins python ==3.10; --no-deps because its pinned
+    requirements are not in the wheelhouse -- the hot-path bodies need only torch/numpy/scipy.)"""
+    for cand in (os.environ.get("VALUES_REFERENCE_ROOT"), "/root/reference",
+                 os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "uncertainty_modeling")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _STUBBED = [
     "hydra", "hydra.utils", "omegaconf", "medpy", "medpy.io", "batchgenerators",
