@@ -267,7 +267,7 @@ struct FusedParams {
     int64_t D0, D1, D2, O0, O1, O2;
     int p0, p1, p2;
     int tiles_x, tiles_y, chunks_z, zc;
-    int zsub;                     // pass-2 sub-chunks per pass-1 z-chunk (zc % zsub == 0)
+    int zsub, zc_fine;            // pass 2 splits a pass-1 z-chunk into zsub pieces of zc_fine planes
     int64_t ntiles;
     double denom;
     int mean_flag;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_fused_kernel(const Fused
     const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
     const int tiles_xy = prm.tiles_x * prm.tiles_y;
     const int zsub = PASS == 2 ? prm.zsub : 1;
-    const int zc_fine = prm.zc / zsub;
+    const int zc_fine = PASS == 2 ? prm.zc_fine : prm.zc;
     double gmax = 0.0;
     unsigned long long tbest = ~0ull;
     double tmax = ninf;
@@ -797,7 +797,7 @@ static int run_patch_stream(StreamParams prm, const StreamPlan& sp, int64_t M, d
 struct FusedPlan {
     int ty, tx;            // 16x64 or 8x32; 0 = fused path not applicable
     int64_t O0, O1, O2;
-    int tiles_x, tiles_y, chunks_z, zc, zsub;
+    int tiles_x, tiles_y, chunks_z, zc, zsub, zc_fine;
     int64_t ntiles;
 };
 
@@ -825,23 +825,24 @@ static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch
     else return VALUES_OK;
     pl.tiles_x = (int)ceil_div(pl.O2, pl.tx);
     pl.tiles_y = (int)ceil_div(pl.O1, pl.ty);
-    // output planes per z-chunk: the march is latency-bound per CTA, so prefer enough CTAs for
-    // ~3 waves of 2 CTAs/SM, but never chunks so short that the p0-1 warm-up planes dominate
-    const int64_t slots = 148 * 2, in_plane = (int64_t)pl.tiles_x * pl.tiles_y * std::max<int64_t>(M, 1);
+    // output planes per z-chunk: minimise (planes marched per SM in pass 1, two CTAs interleaved
+    // per SM) + (planes of the serial pass-2 re-walk of one sub-chunk)
+    const int64_t in_plane = (int64_t)pl.tiles_x * pl.tiles_y * std::max<int64_t>(M, 1);
     int64_t best_cost = -1;
     pl.zc = (int)pl.O0;
     for (int64_t zc : {(int64_t)8, (int64_t)16, (int64_t)32, (int64_t)64, (int64_t)128, pl.O0}) {
         if (zc > pl.O0) zc = pl.O0;
         const int64_t ctas = in_plane * ceil_div(pl.O0, zc);
-        // time ~ planes marched per SM (2 CTAs interleave on one SM)
-        const int64_t per_sm = ceil_div(ctas, 148);
-        const int64_t cost = ceil_div(per_sm, 2) * (zc + patch[0] - 1 + 2);
+        const int64_t warm = patch[0] - 1 + 2;
+        // CTAs neither run in lock-step waves nor perfectly smoothly: average both models
+        const int64_t smooth = std::max(ceil_div(ctas * (zc + warm), 2 * 148), zc + warm);
+        const int64_t waves = ceil_div(ctas, 2 * 148) * (zc + warm);
+        const int64_t pass2 = ceil_div(zc, 8) + warm;
+        const int64_t cost = (smooth + waves) / 2 + pass2;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; pl.zc = (int)zc; }
     }
-    (void)slots;
-    pl.zsub = 1;
-    for (int sub : {8, 4, 2})
-        if (pl.zc % sub == 0 && pl.zc / sub >= 4) { pl.zsub = sub; break; }
+    pl.zsub = (int)std::min<int64_t>(8, pl.zc);
+    pl.zc_fine = (int)ceil_div(pl.zc, pl.zsub);
     pl.chunks_z = (int)ceil_div(pl.O0, pl.zc);
     pl.ntiles = (int64_t)pl.tiles_x * pl.tiles_y * pl.chunks_z;
     if (pl.ntiles * pl.zsub > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: too many tiles");
@@ -1008,7 +1009,7 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
             prm.O0 = fp.O0; prm.O1 = fp.O1; prm.O2 = fp.O2;
             prm.p0 = (int)patch3_host[0]; prm.p1 = (int)patch3_host[1]; prm.p2 = (int)patch3_host[2];
             prm.tiles_x = fp.tiles_x; prm.tiles_y = fp.tiles_y; prm.chunks_z = fp.chunks_z; prm.zc = fp.zc;
-            prm.zsub = fp.zsub; prm.ntiles = fp.ntiles;
+            prm.zsub = fp.zsub; prm.zc_fine = fp.zc_fine; prm.ntiles = fp.ntiles;
             prm.denom = denom; prm.mean_flag = mean_flag ? 1 : 0; prm.rtol = rtol; prm.atol = atol;
             prm.tile_max = ws;
             prm.gmax = ws + M * fp.ntiles;
