@@ -115,6 +115,33 @@ def test_c2_vs_oracle(vb, vo, n, c, spatial, dtype):
     np.testing.assert_array_equal(res.sample_argmax[0].cpu().numpy(), vo.sample_argmax(x).numpy())
 
 
+@pytest.mark.parametrize("n,c,spatial,dtype", [
+    (16, 4, (64, 64, 40), torch.float32),   # RS = 4 stages
+    (10, 20, (96, 132), torch.float32),     # RS = 5
+    (6, 3, (50, 64), torch.float32),        # RS = 2, ragged last tile
+    (7, 5, (40, 52), torch.float32),        # RS = 1
+    (8, 4, (33, 64), torch.bfloat16),
+])
+def test_k1_kernels_agree(vb, n, c, spatial, dtype):
+    """The bulk-copy (TMA ring) kernel and the register-stream kernel share their arithmetic and
+    its order: every output must be bit-identical, including the fused fp64 scores, for any
+    tiles-per-CTA setting."""
+    x = softmax_stack(n * 7 + c, 3 * n, c, spatial).reshape(3, n, c, *spatial).to(dtype).cuda()
+    outs = []
+    try:
+        for variant, it in [(0, 0), (0, 1), (0, 3), (8, 0), (8, 2)]:
+            vb._lib.lib.values_debug_set_k1_variant(variant)
+            vb._lib.lib.values_debug_set_k1_iter(it)
+            r = vb.uncertainty_fused(x, mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05))
+            outs.append((r.pred_entropy, r.expected_entropy, r.mutual_information, r.mean_argmax, r.scores))
+    finally:
+        vb._lib.lib.values_debug_set_k1_variant(0)
+        vb._lib.lib.values_debug_set_k1_iter(0)
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
+
+
 def test_c2_low_mi_regime(vb, vo):
     x = softmax_stack(5, 5, 2, (48, 48, 48), torch.float32, shared=True)
     ref = vo.calculate_uncertainty(x)

@@ -46,6 +46,10 @@ def main():
     batch = args.batch or pool
     out = torch.empty((3, batch) + spatial, dtype=torch.float32, device=dev)
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    _lib.lib.values_debug_set_k1_variant(0)
+    ref = vb.uncertainty_fused(x[:batch], mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05))
+    ref = (ref.pred_entropy.clone(), ref.expected_entropy.clone(), ref.mutual_information.clone(),
+           ref.mean_argmax.clone(), ref.scores.clone())
     for variant in [int(v) for v in args.variants.split(",")]:
         for it in [int(v) for v in args.iters.split(",")]:
             _lib.lib.values_debug_set_k1_variant(variant)
@@ -56,6 +60,9 @@ def main():
                     vb.uncertainty_fused(x[b0:b0 + batch], mean_argmax=True, scores=bool(args.scores),
                                          thresholds=(0.5, 0.4, 0.05), out_maps=out)
 
+            chk = vb.uncertainty_fused(x[:batch], mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05))
+            same = all(torch.equal(a, b) for a, b in zip(ref, (chk.pred_entropy, chk.expected_entropy,
+                                                               chk.mutual_information, chk.mean_argmax, chk.scores)))
             run()
             torch.cuda.synchronize()
             best = 1e9
@@ -69,7 +76,8 @@ def main():
             nvol = (pool // batch) * batch
             gbs = nvol * V * bpv / (best * 1e-3) / 1e9
             print(f"{args.shape} variant={variant} iter={it} batch={batch}: {best / nvol * 1e3:8.1f} us/vol "
-                  f"{nvol * V / best / 1e6:8.2f} Gvox/s {gbs:8.1f} GB/s = {gbs / peak:.3f} of measured peak", flush=True)
+                  f"{nvol * V / best / 1e6:8.2f} Gvox/s {gbs:8.1f} GB/s = {gbs / peak:.3f} of measured peak  "
+                  f"bit-identical to variant 0: {same}", flush=True)
     _lib.lib.values_debug_set_k1_variant(0)
     _lib.lib.values_debug_set_k1_iter(0)
 

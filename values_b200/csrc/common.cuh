@@ -81,20 +81,26 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// Block barrier: BAR == 0 is __syncthreads(); BAR > 0 is the named barrier BAR over the first
+// kThreads threads only (kernels with an extra producer warp that does not take part).
+template <int BAR> __device__ __forceinline__ void block_sync() {
+    if constexpr (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(kThreads) : "memory");
+}
 // Deterministic block sum of K doubles per thread -> valid in thread 0.
-template <int K>
+template <int K, int BAR = 0>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* smem /* [K * 8] */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
-    __syncthreads();
+    block_sync<BAR>();
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) smem[k * 8 + warp] = v[k];
     }
-    __syncthreads();
+    block_sync<BAR>();
     if (threadIdx.x == 0) {
-        const int nw = blockDim.x >> 5;
+        const int nw = BAR == 0 ? (int)(blockDim.x >> 5) : kThreads / 32;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             double s = 0.0;

@@ -174,10 +174,11 @@ __device__ __forceinline__ void k1_epilogue(const K1Params& prm, int64_t b, int6
 // Block partial -> workspace; the LAST CTA of a volume to arrive (ticket counter) sums all of
 // that volume's partials in a fixed order, so the scores do not depend on CTA scheduling and
 // no second kernel launch is needed.
+template <int BAR = 0>
 __device__ __forceinline__ void k1_write_partials(const K1Params& prm, double (&part)[9]) {
     __shared__ double red[9 * 8];
     __shared__ int s_last;
-    block_sum<9>(part, red);
+    block_sum<9, BAR>(part, red);
     const int64_t b = blockIdx.x / prm.blocks_per_vol;
     if (threadIdx.x == 0) {
         double* dst = prm.partials + (int64_t)blockIdx.x * 9;
@@ -187,7 +188,7 @@ __device__ __forceinline__ void k1_write_partials(const K1Params& prm, double (&
         const unsigned int ticket = atomicAdd(prm.counters + b, 1u);
         s_last = ticket == (unsigned int)(prm.blocks_per_vol - 1);
     }
-    __syncthreads();
+    block_sync<BAR>();
     if (!s_last) return;
     __threadfence();
     const double* src = prm.partials + b * prm.blocks_per_vol * 9;
@@ -198,8 +199,8 @@ __device__ __forceinline__ void k1_write_partials(const K1Params& prm, double (&
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc[k] += __ldcg(src + r * 9 + k);
     }
-    __syncthreads();
-    block_sum<9>(acc, red);
+    block_sync<BAR>();
+    block_sum<9, BAR>(acc, red);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) prm.scores[b * 9 + k] = acc[k];
@@ -604,6 +605,207 @@ __global__ void __launch_bounds__(kThreads, MINB) k1_stream_kernel(const K1Param
     }
 }
 
+// =========================================================================== K1 bulk-copy kernel
+// Same arithmetic as k1_stream_kernel, different data movement: one producer thread streams
+// the (tile, class, sample) rows of the CTA -- 4 KB each, the 16-byte vectors of its 256
+// consumer threads side by side -- into a shared-memory ring with cp.async.bulk (the TMA
+// engine, L2 evict-first), completion signalled on an mbarrier per stage; consumer warps wait on
+// "full", read their 16 bytes, hand the slot back on "empty" (one arrive per warp) and do the
+// arithmetic.  The loads in flight (kTmaStages x 4 KB per CTA) no longer depend on registers
+// or on how far the arithmetic has got, and run ahead across tiles of the CTA.
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     " selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+// RS rows (samples of one class) share a stage and one mbarrier round trip; N % RS == 0.
+template <typename T, int VEC, int MINB, int RS, int kTmaStages, bool EARLY>
+__global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Params prm) {
+    using A = typename In<T>::acc_t;
+    using M = Math<T>;
+    static_assert(VEC * sizeof(T) == 16, "vector path only");
+    constexpr int kRowBytes = kThreads * 16;
+    constexpr int kStageBytes = RS * kRowBytes;
+    extern __shared__ __align__(128) unsigned char ring[];            // [kTmaStages][RS][kRowBytes]
+    __shared__ __align__(8) uint64_t full_bar[kTmaStages], empty_bar[kTmaStages];
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.x / prm.blocks_per_vol;
+    const int64_t blk = blockIdx.x - b * prm.blocks_per_vol;
+    const int N = (int)prm.N, C = (int)prm.C;
+    const int64_t snb = prm.sn * (int64_t)sizeof(T), scb = prm.sc * (int64_t)sizeof(T);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, kThreads / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const char* vol = reinterpret_cast<const char*>(reinterpret_cast<const T*>(prm.probs) + b * prm.sb);
+    const int64_t tile_vox = (int64_t)kThreads * VEC;
+
+    if (tid >= kThreads) {   // ---------------- producer warp: one elected lane issues every copy
+        if (tid == kThreads) {
+            const uint64_t policy = l2_evict_first_policy();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < prm.iter; ++it) {
+                const int64_t t0 = (blk * prm.iter + it) * tile_vox;
+                if (t0 >= prm.V) break;
+                const uint32_t bytes = (uint32_t)(min(tile_vox, prm.V - t0) * (int64_t)sizeof(T));
+                const char* row_c = vol + t0 * (int64_t)sizeof(T);
+                for (int c = 0; c < C; ++c, row_c += scb) {
+                    const char* row = row_c;
+                    for (int n = 0; n < N; n += RS) {
+                        mbar_wait(empty_bar + stage, phase ^ 1u);
+                        mbar_expect_tx(full_bar + stage, bytes * RS);
+#pragma unroll
+                        for (int u = 0; u < RS; ++u, row += snb)
+                            bulk_g2s(ring + stage * kStageBytes + u * kRowBytes, row, bytes, full_bar + stage, policy);
+                        if (++stage == kTmaStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        return;   // consumers synchronise among themselves with named barrier 1
+    }
+
+    // ---------------- consumers
+    const A Nf = (A)prm.N;
+    const int lane = tid & 31;
+    double psum[6];
+    int pcnt[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) psum[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pcnt[k] = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < prm.iter; ++it) {
+        const int64_t t0 = (blk * prm.iter + it) * tile_vox;
+        if (t0 >= prm.V) break;                     // uniform: the producer stops at the same tile
+        const int64_t v0 = t0 + (int64_t)tid * VEC;
+        const bool active = v0 < prm.V;             // only the last tile of a volume is ragged
+        A S[VEC], best[VEC];
+        float e[VEC], E[VEC], PE[VEC], Sacc[VEC];
+        int idx[VEC];
+        uint32_t bad = 0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            S[j] = (A)0; e[j] = 0.f; E[j] = 0.f; PE[j] = 0.f; idx[j] = 0; best[j] = (A)0; Sacc[j] = 0.f;
+        }
+        for (int c = 0; c < C; ++c) {
+            for (int n = 0; n < N; n += RS) {
+                mbar_wait(full_bar + stage, phase);
+                Raw<T, VEC> raw[RS];
+#pragma unroll
+                for (int u = 0; u < RS; ++u) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(ring + stage * kStageBytes + u * kRowBytes + tid * 16);
+                    raw[u].w[0] = q.x; raw[u].w[1] = q.y; raw[u].w[2] = q.z; raw[u].w[3] = q.w;
+                }
+                if (EARLY) {   // hand the slot back as soon as the warp has read it
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_bar + stage);
+                }
+                if (active) {
+#pragma unroll
+                    for (int u = 0; u < RS; ++u) {
+                        A p[VEC];
+                        unpack(raw[u], p);
+                        if (M::kFlagged) bad |= sign_or(raw[u]);
+                        add_rows<VEC>(S, p);
+                        M::rows(e, p);
+                    }
+                }
+                if (!EARLY) {
+                    // The slot may only be handed back once the LDS above have RETURNED (an arrive
+                    // issued right after them races with the next bulk copy -- measured).  The
+                    // empty asm pins the arrive behind arithmetic that consumed every row of the
+                    // stage, and that arithmetic cannot issue before the loads complete.
+                    asm volatile("" ::"f"(e[0]), "r"(bad) : "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_bar + stage);
+                }
+                if (++stage == kTmaStages) { stage = 0; phase ^= 1u; }
+            }
+            if (active) {   // class c complete: mean, arg-max, PE term
+                A m[VEC];
+                class_mean<VEC>(S, Nf, prm.inv_n, m);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if (c == 0) best[j] = m[j]; else argmax_update_sel(m[j], c, best[j], idx[j]);
+                    if (M::kFlagged) Sacc[j] += (float)S[j];
+                    S[j] = (A)0;
+                    E[j] += e[j];
+                    e[j] = 0.f;
+                }
+                pe_terms<VEC>(PE, m);
+            }
+        }
+        if (!active) continue;
+        if (M::kFlagged) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                bad |= ((__float_as_uint(Sacc[j]) & 0x7f800000u) == 0x7f800000u) ? 0x80000000u : 0u;
+            if (bad & 0x80000000u) {
+                k1_entropy_exact<T, VEC>(reinterpret_cast<const T*>(vol) + v0, N, C, prm.sn, prm.sc, E);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) E[j] = E[j] / M::kScale;
+            }
+        }
+        float pe[VEC], ee[VEC], mi[VEC];
+        const float nf = (float)prm.N;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            pe[j] = -PE[j];
+            ee[j] = -(M::kScale == 1.0f ? E[j] : E[j] * M::kScale) / nf;
+            mi[j] = pe[j] - ee[j];
+        }
+        const int64_t o = b * prm.so + v0;
+        if (prm.pe) store_f32<VEC>(prm.pe + o, pe);
+        if (prm.ee) store_f32<VEC>(prm.ee + o, ee);
+        if (prm.mi) store_f32<VEC>(prm.mi + o, mi);
+        if (prm.amax) store_u8<VEC>(prm.amax + b * prm.V + v0, idx);
+        if (prm.partials) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float m3[3] = {pe[j], ee[j], mi[j]};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    psum[2 * k] += (double)m3[k];
+                    if (prm.has_thr && m3[k] >= prm.thr_f[k]) { psum[2 * k + 1] += (double)m3[k]; ++pcnt[k]; }
+                }
+            }
+        }
+    }
+    if (prm.partials) {
+        double part[9];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            part[3 * k] = psum[2 * k]; part[3 * k + 1] = psum[2 * k + 1]; part[3 * k + 2] = (double)pcnt[k];
+        }
+        k1_write_partials<1>(prm, part);
+    }
+}
+
 // ---- class sums in shared memory (any C); thread-private columns, conflict-free
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) k1_smem_kernel(const K1Params prm) {
@@ -718,6 +920,21 @@ static int launch_stream(K1Params& prm, int64_t B, cudaStream_t st) {
     return check_launch("k1_stream_kernel");
 }
 
+template <typename T, int VEC, int MINB, int RS, int STAGES, bool EARLY = false>
+static int launch_tma(K1Params& prm, int64_t B, cudaStream_t st) {
+    const int64_t tiles = ceil_div(ceil_div(prm.V, VEC), kThreads);
+    prm.iter = g_k1_iter_override > 0 ? g_k1_iter_override : choose_iter(tiles * B, MINB);
+    prm.blocks_per_vol = ceil_div(tiles, prm.iter);
+    const int64_t grid = prm.blocks_per_vol * B;
+    if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
+    auto kern = k1_tma_kernel<T, VEC, MINB, RS, STAGES, EARLY>;
+    const size_t smem = (size_t)STAGES * RS * kThreads * 16;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return set_error(VALUES_ERR_CUDA, "cudaFuncSetAttribute(k1_tma_kernel) failed");
+    kern<<<(unsigned)grid, kThreads + 32, smem, st>>>(prm);
+    return check_launch("k1_tma_kernel");
+}
+
 template <typename T>
 static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, cudaStream_t st) {
     constexpr int NV = In<T>::VEC;
@@ -731,6 +948,20 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, cudaStream_t st) 
         // Occupancy beats register comfort here (measured on B200, profiles/r01b_k1_variants.txt):
         // 3 CTAs/SM with a few cold-path spills reaches 0.84 of the HBM peak, 2 CTAs/SM 0.66.
         const int v = g_k1_variant;
+        if constexpr (sizeof(T) != 8) {
+            // default: bulk-copy ring, RS samples per stage (one mbarrier round trip per stage)
+            if (v == 0) {
+                if (prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4>(prm, B, st);
+                if (prm.N % 5 == 0) return launch_tma<T, NV, 3, 5, 3>(prm, B, st);
+                if (prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8>(prm, B, st);
+                return launch_tma<T, NV, 3, 1, 8>(prm, B, st);
+            }
+            if (v == 5) return launch_tma<T, NV, 3, 1, 8>(prm, B, st);
+            if (v == 7 && prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4, true>(prm, B, st);  // racy on purpose (test)
+            if (v == 10 && prm.N % 5 == 0) return launch_tma<T, NV, 2, 5, 4>(prm, B, st);
+            if (v == 11 && prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8>(prm, B, st);
+            if (v == 12 && prm.N % 5 == 0) return launch_tma<T, NV, 3, 5, 3>(prm, B, st);
+        }
         if (prm.N % 4 == 0 && v != 9) {
             if (v == 1) return launch_stream<T, NV, 4, 2, true>(prm, B, st);
             if (v == 2) return launch_stream<T, NV, 2, 3, true>(prm, B, st);
