@@ -337,8 +337,18 @@ def main():
     k1_avg_ms = sum(k1_ms) / len(k1_ms)
     k1_bytes = bpv * V * (sum(k1_vols) / len(k1_vols))
     achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tpath) and args.workload == "cfg5":
+        with open(tpath) as f:
+            tj = json.load(f)
+        # DRAM bytes per launch = per-voxel figure of the ncu --set full capture x voxels per launch
+        traffic = tj["dram_bytes_per_voxel"] * V * (sum(k1_vols) / len(k1_vols))
+        traffic_src = "profiles/k1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per voxel x voxels per launch)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel": "k1 fused N x C reduction",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": k1_bytes,
+                "kernel": "k1 fused N x C reduction (k1_tma_kernel)",
                 "algorithmic_bytes_per_voxel": bpv, "avg_launch_ms": k1_avg_ms,
                 "launches_timed": len(k1_ms), "k1_share_of_step": sum(k1_ms) / elapsed_ms,
                 "peak_source": peak_src}
