@@ -23,9 +23,13 @@
 extern "C" {
 #endif
 
-#define VALUES_ABI_VERSION 2
+#define VALUES_ABI_VERSION 3
 
-typedef enum { VALUES_F32 = 0, VALUES_F64 = 1, VALUES_BF16 = 2 } values_dtype_t;
+typedef enum {
+    VALUES_F32 = 0, VALUES_F64 = 1, VALUES_BF16 = 2,
+    /* label / segmentation maps (K4 statistics only) */
+    VALUES_U8 = 3, VALUES_I32 = 4, VALUES_I64 = 5
+} values_dtype_t;
 
 #define VALUES_OK 0
 #define VALUES_ERR_INVALID_ARG (-1) /* -> ValueError on the Python side            */
@@ -127,6 +131,68 @@ int values_stitch_accumulate(const void* patches, int patch_dtype, int64_t patch
  *   out[m, v] = (double) maps[m, v] / max(count[v], 1)   -> fp64 as written to NIfTI. */
 int values_normalize_maps(const void* maps, int dtype, int64_t M, int64_t V, int64_t stride_m,
                           const double* count, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4: whole-map statistics either side of the C2 -> C3 path.
+ *
+ * Replaces calculate_foreground_quantile_image(image)
+ * evaluation/uncertainty_aggregation/find_threshold.py:11-13 (np.count_nonzero):
+ *   *count += #{ i : data[i] != 0 }   (device counter, caller zeroes it; NaN counts, -0.0 does not)
+ *   dtype: U8 / I32 / I64 / F32 / F64. */
+int values_count_nonzero(const void* data, int dtype, int64_t n, unsigned long long* count,
+                         void* stream);
+
+/* Building blocks of the exact np.quantile(images, q) in calculate_threshold_image /
+ * find_threshold (find_threshold.py:63-68, 90-96) as a most-significant-digit radix select.
+ * Values map to order-preserving unsigned keys (32 bit for F32, 64 bit for F64; NaN -> all
+ * ones = last, as np.sort; -0.0 == +0.0).
+ *   hist[d] += #{ i : key_i >> (bits - prefix_bits) == prefix and
+ *                     (key_i >> (bits - prefix_bits - digit_bits)) & (2^digit_bits - 1) == d }
+ * hist is a device array of 2^digit_bits counters (digit_bits <= 11) that ACCUMULATES, so the
+ * maps of a validation set (and, after an all-reduce, of every rank) add into one histogram;
+ * the caller walks the digits from the top, keeping the prefix of the bucket that holds the
+ * wanted rank.  values_min_key_above: *out = min(*out, min key_i > key) -- the next order
+ * statistic when the interpolation partner is not a duplicate of the selected value. */
+int values_radix_histogram(const void* data, int dtype, int64_t n, uint64_t prefix,
+                           int prefix_bits, int digit_bits, unsigned long long* hist,
+                           void* stream);
+int values_min_key_above(const void* data, int dtype, int64_t n, uint64_t key,
+                         unsigned long long* out, void* stream);
+
+/* Replaces the reductions of compute_ncc(gt_unc_map, pred_unc_map) evaluation/metrics/ncc.py:9-25.
+ *   a [M, V] (stride_a, 1), b [M, V] (stride_b, 1), F32 or F64 each; shift: device double [M, 2]
+ *   (sa, sb per pair) or NULL (= 0).
+ *   out double [M, 5] = { sum(a-sa), sum(b-sb), sum (a-sa)^2, sum (b-sb)^2, sum (a-sa)(b-sb) }
+ * Two calls give the reference's two-pass result: shift = NULL -> means, shift = means ->
+ * centred moments.  Deterministic block-then-grid reduction in fp64. */
+size_t values_pair_moments_workspace_bytes(int64_t M, int64_t V);
+int values_pair_moments(const void* a, int dtype_a, int64_t stride_a, const void* b, int dtype_b,
+                        int64_t stride_b, int64_t M, int64_t V, const double* shift, double* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces the binning of calib_stats(correct, calib_confids) evaluation/metrics/ace.py:49-81:
+ * binids = np.digitize(prob, edges) - 1 with the caller's n_bins + 1 increasing edges
+ * (np.linspace(0, 1 + 1e-8, 21); n_bins must be 20 as the reference hard-codes).
+ *   prob F32/F64 [n]; correct U8/I32/I64 [n] (non-zero = true)
+ *   out double [3, n_bins + 1] = { bin_total, bin_sums (sum prob), bin_true } per slot;
+ *   counts are exact.  Elements below edges[0] are dropped (the reference raises ValueError
+ *   before binning; the Python mirror does too). */
+size_t values_calib_bins_workspace_bytes(int64_t n);
+int values_calib_bins(const void* prob, int dtype, const void* correct, int label_dtype, int64_t n,
+                      const double* edges_host, int n_bins, double* out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* The per-image body of calibration_error (ace.py:96-127) in one sweep: for every rater r and
+ * voxel v,  correct = (ref_segs[r, v] == pred_seg[v]),  conf = 1 / (1 + exp(-unc[v] * a + b))
+ * (platt_scale_confid, ace.py:42-46, evaluated in the map's dtype as numpy does), skipping
+ * ref_segs[r, v] == ignore_value when has_ignore; binned as values_calib_bins.
+ *   unc F32/F64 [V]; pred_seg [V], ref_segs [R, V] of label_dtype (U8/I32/I64)
+ *   workspace: values_calib_bins_workspace_bytes(V). */
+int values_calib_bins_fused(const void* unc, int dtype, const void* pred_seg, const void* ref_segs,
+                            int label_dtype, int64_t V, int64_t R, double a, double b,
+                            int has_ignore, int64_t ignore_value, const double* edges_host,
+                            int n_bins, double* out, void* workspace, size_t workspace_bytes,
+                            void* stream);
 
 /* Tuning hooks for benchmarks and tests (process-wide; 0 restores the automatic choice):
  * voxel tiles per CTA of the K1 stream kernel, and its batch / occupancy variant. */

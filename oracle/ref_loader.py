@@ -107,6 +107,8 @@ def load():
         "evaluation.uncertainty_aggregation.aggregate_uncertainties"
     )
     thr = importlib.import_module("evaluation.uncertainty_aggregation.find_threshold")
+    ncc = importlib.import_module("evaluation.metrics.ncc")
+    ace = importlib.import_module("evaluation.metrics.ace")
     _loaded.update(
         calculate_uncertainty=t3d.calculate_uncertainty,
         calculate_one_minus_msr=t3d.calculate_one_minus_msr,
@@ -116,7 +118,10 @@ def load():
         image_level_aggregation=agg.image_level_aggregation,
         threshold_aggregation=agg.threshold_aggregation,
         calculate_foreground_quantile_image=thr.calculate_foreground_quantile_image,
+        compute_ncc=ncc.compute_ncc, calib_stats=ace.calib_stats, calc_ace=ace.calc_ace,
+        platt_scale_confid=ace.platt_scale_confid, calibration_error=ace.calibration_error,
+        ncc_main=ncc.main, calculate_threshold_image=thr.calculate_threshold_image,
         modules=dict(test_3D=t3d, data_carrier_3D=dc, aggregate_uncertainties=agg,
-                     find_threshold=thr),
+                     find_threshold=thr, ncc=ncc, ace=ace),
     )
     return types.SimpleNamespace(**_loaded)

@@ -48,8 +48,126 @@ def c2_case(ref, name, x, ssn=False):
     print(name, {k: (v.shape, v.dtype) for k, v in out.items()})
 
 
+class FakeExpDataloader:
+    """Duck-typed stand-in for evaluation.experiment_dataloader.ExperimentDataloader: the
+    reference's metric loops only call these getters (ncc.py:28-47, ace.py:89-133)."""
+
+    def __init__(self, root, unc_maps, pred_segs, ref_segs, gt_unc):
+        import types
+        from pathlib import Path
+
+        self.dataset_path = Path(root)
+        self.exp_version = types.SimpleNamespace(exp_path=Path(root), unc_types=sorted(unc_maps),
+                                                 pred_model="Dropout", version_name="v0")
+        self.image_ids = sorted(pred_segs)
+        self._unc, self._pred, self._ref, self._gt = unc_maps, pred_segs, ref_segs, gt_unc
+
+    def get_unc_map(self, image_id, unc_type):
+        return self._unc[unc_type][image_id]
+
+    def get_mean_pred_seg(self, image_id):
+        return self._pred[image_id]
+
+    def get_pred_segs(self, image_id):
+        return [self._pred[image_id]]
+
+    def get_reference_segs(self, image_id):
+        return self._ref[image_id]
+
+    def get_gt_unc_map(self, image_id):
+        return self._gt[image_id]
+
+
+def k4_cases(ref):
+    """f1 / f3: threshold finding, NCC and ACE through the reference's own loops."""
+    import json
+    import tempfile
+
+    rng = np.random.default_rng(20261018)
+    out = {}
+    # ---- foreground quantile + np.quantile threshold (find_threshold.py:11-13, 63-68)
+    seg = (rng.random((9, 10, 11)) < 0.07).astype(np.uint8)
+    out["fg_seg"] = seg
+    out["fg_quantile"] = np.array(ref.calculate_foreground_quantile_image(seg))
+    maps64 = rng.random((3, 12, 11, 10)).astype(np.float32).astype(np.float64) / np.array([1.0, 2.0, 3.0]).reshape(3, 1, 1, 1)
+    maps64[1, :3] = 0.0          # duplicates (uncovered remainder)
+    maps32 = rng.random((4, 33, 20)).astype(np.float32)
+    out["thr_maps64"], out["thr_maps32"] = maps64, maps32
+    qs = [0.0, 0.25, 0.9312345, 0.98, 1.0, float(out["fg_quantile"])]
+    out["thr_q"] = np.array(qs)
+    with tempfile.TemporaryDirectory() as tmp:
+        for j, q in enumerate(qs):
+            qp = os.path.join(tmp, f"q{j}.json")
+            with open(qp, "w") as f:
+                json.dump({"Dropout": q}, f)
+            out[f"thr64_{j}"] = np.array(ref.calculate_threshold_image(qp, maps64, "Dropout"))
+            out[f"thr32_{j}"] = np.array(ref.calculate_threshold_image(qp, maps32, "Dropout"))
+    # ---- NCC + ACE through the reference loops with a duck-typed data loader
+    ids = ["img_a", "img_b", "img_c"]
+    shape3, shape2 = (10, 9, 8), (14, 21)
+    for tag, shape, dt, ignore in (("3d", shape3, np.float64, None), ("2d", shape2, np.float32, 255)):
+        unc = {u: {} for u in ("aleatoric_uncertainty", "epistemic_uncertainty", "pred_entropy")}
+        pred, refs, gt = {}, {}, {}
+        for i, image_id in enumerate(ids):
+            R = 1 + i
+            pred[image_id] = (rng.random(shape) < 0.3).astype(np.uint8)
+            r = np.stack([np.where(rng.random(shape) < 0.85, pred[image_id], 1 - pred[image_id])
+                          for _ in range(R)]).astype(np.uint8)
+            if ignore is not None:
+                r[rng.random(r.shape) < 0.1] = ignore
+            if i == 2 and tag == "3d":
+                r = np.repeat(pred[image_id][None], R, 0)   # all raters agree: single-label quirk
+            refs[image_id] = r
+            gt[image_id] = rng.random(shape).astype(dt)
+            for u in unc:
+                m = (rng.random(shape) ** 2 * 0.7).astype(dt)
+                # the 2D maps are loaded as (W, H) (ace.py:101-102)
+                unc[u][image_id] = np.ascontiguousarray(m.T) if tag == "2d" else m
+        params = {u: {"a": 3.0 + k, "b": -1.25 + 0.5 * k} for k, u in enumerate(sorted(unc))}
+        with tempfile.TemporaryDirectory() as tmp:
+            dl = FakeExpDataloader(tmp, unc, pred, refs, gt)
+            with open(os.path.join(tmp, "platt_scale_params.json"), "w") as f:
+                json.dump(params, f)
+            ref.calibration_error(dl, ignore_value=ignore)
+            with open(os.path.join(tmp, "calibration.json")) as f:
+                calib = json.load(f)
+            if tag == "3d":     # ncc.py needs equal shapes
+                ref.ncc_main(dl)
+                with open(os.path.join(tmp, "ambiguity_modeling.json")) as f:
+                    ncc = json.load(f)
+        for k, u in enumerate(sorted(unc)):
+            out[f"{tag}_platt_{k}"] = np.array([params[u]["a"], params[u]["b"]])
+            out[f"{tag}_ace_mean_{k}"] = np.array(calib["mean"][u]["metrics"]["ace"])
+            if tag == "3d":
+                out[f"{tag}_ncc_mean_{k}"] = np.array(ncc["mean"][u]["metrics"]["ncc"])
+            for i, image_id in enumerate(ids):
+                out[f"{tag}_unc_{k}_{i}"] = unc[u][image_id]
+                out[f"{tag}_ace_{k}_{i}"] = np.array(calib[image_id][u]["metrics"]["ace"])
+                if tag == "3d":
+                    out[f"{tag}_ncc_{k}_{i}"] = np.array(ncc[image_id][u]["metrics"]["ncc"])
+        for i, image_id in enumerate(ids):
+            out[f"{tag}_pred_{i}"], out[f"{tag}_refs_{i}"], out[f"{tag}_gt_{i}"] = pred[image_id], refs[image_id], gt[image_id]
+        out[f"{tag}_ignore"] = np.array(-1 if ignore is None else ignore)
+    out["unc_names"] = np.array(sorted(unc))
+    # ---- calib_stats directly (ace.py:49-81) incl. fp32 confidences
+    conf = rng.random(5000)
+    corr = (rng.random(5000) < conf).astype(int)
+    disc, tot, nz = ref.calib_stats(corr, conf)
+    out["cs_conf"], out["cs_correct"] = conf, corr
+    out["cs_disc"], out["cs_total"], out["cs_nonzero"] = disc, tot, np.array(nz)
+    out["cs_ace"] = np.array(ref.calc_ace(corr, conf))
+    # ncc on an fp32 pair
+    a32, b32 = rng.random((17, 19)).astype(np.float32), rng.random((17, 19)).astype(np.float32)
+    out["ncc32_a"], out["ncc32_b"], out["ncc32"] = a32, b32, np.array(ref.compute_ncc(a32, b32))
+    np.savez_compressed(os.path.join(HERE, "k4_stats.npz"), **out)
+    print("k4_stats", len(out), "arrays")
+
+
 def main():
     ref = ref_loader.load()
+    if "--only-k4" in sys.argv:
+        k4_cases(ref)
+        return
     gen = torch.Generator().manual_seed(20261017)
 
     # ---- C2: fp32 2D path incl. the appended all-zero channel (test_2D.py:208-218)
@@ -166,6 +284,7 @@ def main():
         mean_seg=np.argmax(np.mean(sm, axis=0), axis=0).astype(np.uint8),
     )
     print("stitch_3d", len(crops), "patches")
+    k4_cases(ref)
 
 
 if __name__ == "__main__":

@@ -130,3 +130,36 @@ def test_known_answers():
         st.concat_data({"image_paths": ["a"], "org_image_size": [(12, 8, 8)], "crop_idx": [c]},
                        torch.ones(1, 2, 8, 8, 8))
     assert st.data["a"]["num_predictions"][0, :, 0, 0].tolist() == [1] * 4 + [2] * 4 + [1] * 4
+
+
+# ------------------------------------------------------------------ f1 / f3 (k4_stats.npz)
+def test_k4_threshold_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "k4_stats.npz"))
+    assert vo.calculate_foreground_quantile_image(g["fg_seg"]) == float(g["fg_quantile"])
+    for j, q in enumerate(g["thr_q"].tolist()):
+        assert vo.quantile_threshold(g["thr_maps64"], q) == g[f"thr64_{j}"]
+        r32 = vo.quantile_threshold(g["thr_maps32"], q)
+        assert r32.dtype == np.float32 and r32 == g[f"thr32_{j}"]
+
+
+def test_k4_ncc_ace_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "k4_stats.npz"))
+    for tag in ("3d", "2d"):
+        ignore = int(g[f"{tag}_ignore"])
+        ignore = None if ignore < 0 else ignore
+        for k in range(3):
+            a, b = g[f"{tag}_platt_{k}"].tolist()
+            aces = []
+            for i in range(3):
+                unc, pred, refs = g[f"{tag}_unc_{k}_{i}"], g[f"{tag}_pred_{i}"], g[f"{tag}_refs_{i}"]
+                ace = vo.calibration_error_image(unc, pred, refs, a, b, ignore)
+                assert ace == float(g[f"{tag}_ace_{k}_{i}"])
+                aces.append(ace)
+                if tag == "3d":
+                    assert vo.compute_ncc(g[f"{tag}_gt_{i}"], unc) == float(g[f"{tag}_ncc_{k}_{i}"])
+            assert np.mean(np.array(aces)) == float(g[f"{tag}_ace_mean_{k}"])
+    disc, tot, nz = vo.calib_stats(g["cs_correct"], g["cs_conf"])
+    np.testing.assert_array_equal(disc, g["cs_disc"])
+    np.testing.assert_array_equal(tot, g["cs_total"])
+    assert nz == int(g["cs_nonzero"]) and vo.calc_ace(g["cs_correct"], g["cs_conf"]) == float(g["cs_ace"])
+    assert vo.compute_ncc(g["ncc32_a"], g["ncc32_b"]) == g["ncc32"]

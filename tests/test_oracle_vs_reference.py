@@ -44,3 +44,18 @@ def test_c3_random(ref):
         assert ref.image_level_aggregation(m) == vo.image_level_aggregation(m)
         ra, rb = ref.threshold_aggregation(m, threshold=0.7), vo.threshold_aggregation(m, threshold=0.7)
         assert float(ra["max_score"]) == float(rb["max_score"])
+
+
+def test_k4_stats_random(ref):
+    rng = np.random.default_rng(11)
+    for dt in (np.float64, np.float32):
+        a, b = rng.random((9, 8, 7)).astype(dt), rng.random((9, 8, 7)).astype(dt)
+        assert ref.compute_ncc(a, b) == vo.compute_ncc(a, b)
+        conf = rng.random(4000).astype(dt)
+        for corr in ((rng.random(4000) < conf).astype(int), np.ones(4000, dtype=int), np.zeros(4000, dtype=int)):
+            ra, rb = ref.calib_stats(corr, conf), vo.calib_stats(corr, conf)
+            np.testing.assert_array_equal(ra[0], rb[0])
+            np.testing.assert_array_equal(ra[1], rb[1])
+            assert ra[2] == rb[2] and ref.calc_ace(corr, conf) == vo.calc_ace(corr, conf)
+    seg = (rng.random((6, 7, 8)) < 0.2).astype(np.uint8)
+    assert ref.calculate_foreground_quantile_image(seg) == vo.calculate_foreground_quantile_image(seg)

@@ -9,10 +9,16 @@ from . import _lib  # noqa: F401  (raises ValuesExtensionMissing when the .so is
 from .aggregation import (aggregate_uncertainties, image_level_aggregation, map_reduce,
                           normalize_maps, patch_level_aggregation, patch_max,
                           threshold_aggregation)
+from . import metrics, threshold
 from .data_carrier import DataCarrier3D
+from .metrics import (calc_ace, calib_stats, calibration_error, calibration_error_image,
+                      compute_ncc, ncc_batched, ncc_main, platt_scale_confid)
 from .pipeline import AggregationConfig, PipelineResult, UncertaintyPipeline
 from .sharding import gather_scores, shard_range, shard_sizes
 from .stitching import patch_grid, stitch_accumulate, stitch_volume
+from .threshold import (calculate_foreground_quantile_image, calculate_threshold_image,
+                        count_nonzero, find_threshold, get_foreground_quantile, quantile,
+                        save_foreground_quantiles)
 from .uncertainty import (FusedResult, caculcate_uncertainty_multiple_pred,
                           calculate_one_minus_msr, calculate_uncertainty,
                           calculate_uncertainty_multiple_pred, uncertainty_fused)
@@ -25,4 +31,8 @@ __all__ = [
     "DataCarrier3D", "patch_grid", "stitch_accumulate", "stitch_volume",
     "UncertaintyPipeline", "AggregationConfig", "PipelineResult",
     "shard_range", "shard_sizes", "gather_scores",
+    "calculate_foreground_quantile_image", "get_foreground_quantile", "save_foreground_quantiles",
+    "calculate_threshold_image", "find_threshold", "quantile", "count_nonzero",
+    "compute_ncc", "ncc_batched", "ncc_main", "calib_stats", "calc_ace", "platt_scale_confid",
+    "calibration_error_image", "calibration_error",
 ]

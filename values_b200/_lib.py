@@ -13,9 +13,10 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libvalues_b200.so")
 
-F32, F64, BF16 = 0, 1, 2
-ABI_VERSION = 2  # include/values_b200.h VALUES_ABI_VERSION
+F32, F64, BF16, U8, I32, I64 = 0, 1, 2, 3, 4, 5
+ABI_VERSION = 3  # include/values_b200.h VALUES_ABI_VERSION
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
+_LABEL_DTYPES = {torch.uint8: U8, torch.int32: I32, torch.int64: I64}
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 
@@ -49,6 +50,15 @@ def _load() -> C.CDLL:
         "values_stitch_accumulate": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, i64, i64, i64,
                                                pi64, pi64, vp, C.c_int, vp, C.c_int, vp]),
         "values_normalize_maps": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, vp, vp]),
+        "values_count_nonzero": (C.c_int, [vp, C.c_int, i64, vp, vp]),
+        "values_radix_histogram": (C.c_int, [vp, C.c_int, i64, C.c_uint64, C.c_int, C.c_int, vp, vp]),
+        "values_min_key_above": (C.c_int, [vp, C.c_int, i64, C.c_uint64, vp, vp]),
+        "values_pair_moments_workspace_bytes": (sz, [i64, i64]),
+        "values_pair_moments": (C.c_int, [vp, C.c_int, i64, vp, C.c_int, i64, i64, i64, vp, vp, vp, sz, vp]),
+        "values_calib_bins_workspace_bytes": (sz, [i64]),
+        "values_calib_bins": (C.c_int, [vp, C.c_int, vp, C.c_int, i64, pdbl, C.c_int, vp, vp, sz, vp]),
+        "values_calib_bins_fused": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, i64, i64, dbl, dbl, C.c_int,
+                                              i64, pdbl, C.c_int, vp, vp, sz, vp]),
         "values_debug_set_k1_iter": (None, [C.c_int]),
         "values_debug_set_k1_variant": (None, [C.c_int]),
         "values_debug_set_patch_path": (None, [C.c_int]),
@@ -67,7 +77,10 @@ EXPORTED = [
     "values_uncertainty_workspace_bytes", "values_uncertainty_fused", "values_one_minus_msr",
     "values_map_reduce_workspace_bytes", "values_map_reduce",
     "values_patch_max_workspace_bytes", "values_patch_max", "values_stitch_accumulate",
-    "values_normalize_maps", "values_debug_set_k1_iter", "values_debug_set_k1_variant",
+    "values_normalize_maps", "values_count_nonzero", "values_radix_histogram",
+    "values_min_key_above", "values_pair_moments_workspace_bytes", "values_pair_moments",
+    "values_calib_bins_workspace_bytes", "values_calib_bins", "values_calib_bins_fused",
+    "values_debug_set_k1_iter", "values_debug_set_k1_variant",
     "values_debug_set_patch_path",
 ]
 
@@ -92,6 +105,13 @@ def dtype_code(dt: torch.dtype) -> int:
         return _DTYPES[dt]
     except KeyError:
         raise TypeError(f"values_b200: unsupported dtype {dt} (float32, float64, bfloat16)") from None
+
+
+def label_dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _LABEL_DTYPES[dt]
+    except KeyError:
+        raise TypeError(f"values_b200: unsupported label dtype {dt} (uint8, int32, int64)") from None
 
 
 def require_cuda() -> torch.device:

@@ -50,6 +50,8 @@ int launch_reduce_partials(const double* partials, int64_t n_items, int64_t n_bl
     if (n_items <= 0) return VALUES_OK;
     if (K == 9)
         reduce_partials_kernel<9><<<(unsigned)n_items, kThreads, 0, stream>>>(partials, n_blocks, out);
+    else if (K == 5)
+        reduce_partials_kernel<5><<<(unsigned)n_items, kThreads, 0, stream>>>(partials, n_blocks, out);
     else if (K == 3)
         reduce_partials_kernel<3><<<(unsigned)n_items, kThreads, 0, stream>>>(partials, n_blocks, out);
     else

@@ -8,7 +8,7 @@ from __future__ import annotations
 import importlib
 import sys
 
-from . import aggregation, data_carrier, uncertainty
+from . import aggregation, data_carrier, metrics, threshold, uncertainty
 
 _PATCHES = {
     "uncertainty_modeling.test_3D": {
@@ -27,6 +27,18 @@ _PATCHES = {
         "image_level_aggregation": aggregation.image_level_aggregation,
         "threshold_aggregation": aggregation.threshold_aggregation,
         "aggregate_uncertainties": aggregation.aggregate_uncertainties,
+    },
+    "evaluation.uncertainty_aggregation.find_threshold": {
+        "calculate_foreground_quantile_image": threshold.calculate_foreground_quantile_image,
+        "get_foreground_quantile": threshold.get_foreground_quantile,
+        "calculate_threshold_image": threshold.calculate_threshold_image,
+        "find_threshold": threshold.find_threshold,
+    },
+    "evaluation.metrics.ncc": {"compute_ncc": metrics.compute_ncc, "main": metrics.ncc_main},
+    "evaluation.metrics.ace": {
+        "calib_stats": metrics.calib_stats,
+        "calc_ace": metrics.calc_ace,
+        "calibration_error": metrics.calibration_error,
     },
 }
 

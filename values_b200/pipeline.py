@@ -33,6 +33,9 @@ class AggregationConfig:
     chunk_bytes: int = 256 << 20               # fp32 map scratch per chunk (8-10 128^3 volumes: enough
                                                # K2b CTAs for several waves; K1 keeps the maps
                                                # L2-friendly by reading its input evict-first)
+    overlap: bool = False                      # run K2b of chunk i on a second stream under K1 of chunk
+                                               # i+1 (K1 is HBM-bound, K2b shared-memory/issue-bound);
+                                               # costs a second map scratch buffer
 
 
 @dataclass
@@ -93,6 +96,7 @@ class UncertaintyPipeline:
         # optional list; when set, (start_event, end_event, n_volumes) is appended per K1 launch
         # (CUDA events on the launching stream -- bench.py's roofline measurement)
         self.k1_timer: Optional[list] = None
+        self._side: Dict[torch.device, torch.cuda.Stream] = {}
 
     def _chunk(self, B: int, V: int) -> int:
         per_volume = 3 * V * 4  # three fp32 maps
@@ -124,10 +128,19 @@ class UncertaintyPipeline:
         if thr is not None and ssn:
             thr = (thr[0], thr[2], thr[1])
         cb = self._chunk(B, V)
+        overlap = cfg.overlap and patch is not None and B > cb
+        if overlap:
+            main = torch.cuda.current_stream(dev)
+            side = self._side.get(dev)
+            if side is None:
+                side = self._side[dev] = torch.cuda.Stream(dev, priority=-1)
+            side.wait_stream(main)
+            k2_done = [None, None]
         if keep_maps:   # K1 writes straight into the kept [B, 3, *S] buffer, chunk by chunk
             maps_all = torch.empty((B, 3) + spatial, dtype=torch.float32, device=dev)
         else:
             maps_buf = self._buf("maps", (cb, 3) + spatial, torch.float32, dev)
+            maps_buf2 = self._buf("maps2", (cb, 3) + spatial, torch.float32, dev) if overlap else maps_buf
         k1_scores = self._buf("k1_scores", (B, 3, 3), torch.float64, dev)
         am = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev) if mean_argmax else None
         k1_ws_bytes = _lib.lib.values_uncertainty_workspace_bytes(cb, V, _lib.dtype_code(probs.dtype))
@@ -137,10 +150,12 @@ class UncertaintyPipeline:
             bb = self._buf("patch_bbox", (B * 3, 3), torch.int64, dev)
             k2_ws = self._buf("k2_ws", (max(patch_max_workspace_bytes(cb * 3, spatial, patch), 8),),
                               torch.uint8, dev)
-        for b0 in range(0, B, cb):
+        for ci, b0 in enumerate(range(0, B, cb)):
             b1 = min(b0 + cb, B)
             nb = b1 - b0
-            buf = maps_all[b0:b1] if keep_maps else maps_buf[:nb]
+            buf = maps_all[b0:b1] if keep_maps else (maps_buf2 if ci & 1 else maps_buf)[:nb]
+            if overlap and k2_done[ci & 1] is not None:
+                main.wait_event(k2_done[ci & 1])   # K2b of chunk ci-2 has released this scratch
             if self.k1_timer is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
@@ -151,10 +166,22 @@ class UncertaintyPipeline:
             if self.k1_timer is not None:
                 ev1.record()
                 self.k1_timer.append((ev0, ev1, nb))
-            if patch is not None:
+            if patch is not None and not overlap:
                 patch_max(buf.view((3 * nb,) + spatial), patch, mean=cfg.patch_mean,
                           rtol=ISCLOSE_RTOL, atol=ISCLOSE_ATOL, out_score=ps[3 * b0:3 * b1],
                           out_bbox=bb[3 * b0:3 * b1], workspace=k2_ws)
+            elif overlap:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    patch_max(buf.view((3 * nb,) + spatial), patch, mean=cfg.patch_mean,
+                              rtol=ISCLOSE_RTOL, atol=ISCLOSE_ATOL, out_score=ps[3 * b0:3 * b1],
+                              out_bbox=bb[3 * b0:3 * b1], workspace=k2_ws)
+                    k2_done[ci & 1] = torch.cuda.Event()
+                    k2_done[ci & 1].record(side)
+        if overlap:
+            main.wait_stream(side)
         scores = torch.zeros((B, 3, N_COLS), dtype=torch.float64, device=dev)
         scores[:, :, :3] = k1_scores
         if patch is not None:
