@@ -102,7 +102,7 @@ def test_quantile_matches_numpy_large(vb, dtype):
     for q in (0.0, 1e-7, 0.01, 0.5, 0.98, 0.999999, 1.0):
         got = vb.quantile([torch.from_numpy(m).cuda() for m in maps], q)
         want = np.quantile(stacked, q)
-            assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True), (q, got, want)  # q=1: inf-inf=NaN in numpy too
+        assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True), (q, got, want)  # q=1: inf-inf=NaN in numpy too
 
 
 def test_quantile_nan_and_errors(vb):
