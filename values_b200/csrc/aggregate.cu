@@ -7,8 +7,9 @@
 
 namespace vb {
 
-// 0 = automatic (fused tile kernel when the patch fits its shared memory), 1 = streaming
-// two-kernel path, 2 = generic tiled path (values_debug_set_patch_path; tests cover all three)
+// 0 = automatic (march kernel for 10x10 in-plane patches, else the fused tile kernel when the
+// patch fits its shared memory), 1 = streaming two-kernel path, 2 = generic tiled path, 4 = fused
+// tile kernel even where the march kernel applies (values_debug_set_patch_path; tests cover all)
 static int g_patch_path = 0;
 
 // =============================================================================== K2a
@@ -289,6 +290,85 @@ template <int N> __device__ __forceinline__ double tree_sum(const double* v) {
     else return tree_sum<N / 2>(v) + tree_sum<N - N / 2>(v + N / 2);
 }
 
+// Shared tail of the fused / march kernels.  PASS 1: tile maximum -> tile_max; the last CTA of a
+// map reduces them to the map maximum and lists the tiles np.isclose to it.  PASS 2: minimum
+// C-order index -> best (atomicMin, order-free); the last CTA publishes the bounding-box corner.
+template <int PASS, int NT = kFusedThreads>
+__device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t m, double tmax,
+                                                unsigned long long tbest, double* red, int& s_flag,
+                                                int& s_count) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+    if constexpr (PASS == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmax = nanmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if (lane == 0) red[warp] = tmax;
+        __syncthreads();
+        if (tid == 0) {
+            double mm = red[0];
+            for (int w = 1; w < NT / 32; ++w) mm = nanmax(mm, red[w]);
+            prm.tile_max[m * prm.ntiles + blockIdx.x] = mm;
+            __threadfence();
+            s_flag = atomicAdd(prm.tickets + 2 * m, 1u) == gridDim.x - 1;
+            s_count = 0;
+        }
+        __syncthreads();
+        if (!s_flag) return;
+        // last CTA of this map: map maximum (NaN propagates, as np.max) and the pass-2 work list
+        __threadfence();
+        const double* tm = prm.tile_max + m * prm.ntiles;
+        double mm = ninf;
+        for (int64_t i = tid; i < prm.ntiles; i += NT) mm = nanmax(mm, __ldcg(tm + i));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mm = nanmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        if (lane == 0) red[warp] = mm;
+        __syncthreads();
+        double g = red[0];
+        for (int w = 1; w < NT / 32; ++w) g = nanmax(g, red[w]);
+        int* lst = prm.active + m * (1 + kMaxActive);
+        for (int64_t i = tid; i < prm.ntiles; i += NT) {   // list order is irrelevant (min index wins)
+            if (np_isclose(__ldcg(tm + i), g, prm.rtol, prm.atol)) {
+                const int n = atomicAdd(&s_count, 1);
+                if (n < kMaxActive) lst[1 + n] = (int)i;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            lst[0] = s_count > kMaxActive ? -1 : s_count;
+            prm.gmax[m] = g;
+            prm.max_score[m] = g;
+            prm.best[m] = ~0ull;
+        }
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, tbest, o);
+            tbest = other < tbest ? other : tbest;
+        }
+        if (lane == 0 && tbest != ~0ull) atomicMin(prm.best + m, tbest);  // min is order-free
+        // last CTA of this map: publish the bounding-box corner
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_flag = atomicAdd(prm.tickets + 2 * m + 1, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_flag && tid == 0) {
+            __threadfence();
+            const unsigned long long b = atomicMin(prm.best + m, ~0ull);  // atomic read
+            int64_t* bb = prm.bbox_lo + 3 * m;
+            if (b == ~0ull) {  // no window is close to the max (NaN map): the reference raises IndexError
+                bb[0] = bb[1] = bb[2] = -1;
+            } else {
+                const int64_t lin = (int64_t)b;
+                bb[2] = lin % prm.O2;
+                bb[1] = (lin / prm.O2) % prm.O1;
+                bb[0] = lin / (prm.O2 * prm.O1);
+            }
+        }
+    }
+}
+
 // One kernel does all three box passes: a CTA owns TY x TX windows in-plane and a chunk of
 // output planes, marching over z.  Per input plane: (1) the plane tile (+halo) goes from L2
 // to shared memory through registers, one plane AHEAD of the arithmetic, widened to fp64;
@@ -463,74 +543,188 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_fused_kernel(const Fused
             slot = slot + 1 == p0 ? 0 : slot + 1;
         }
     }
-    if constexpr (PASS == 1) {
+    box_pass_finish<PASS>(prm, m, tmax, tbest, red, s_flag, s_count);
+}
+
+// ------------------------------------------------------------------ K2b march kernel (z first)
+// Same tiling, passes and finish protocol as box_fused_kernel, but the three box passes run
+// z -> x -> y: a thread keeps the z-window sums of its input positions (rows g, g+G, ... of one
+// tile column) in REGISTERS, sliding them with the entering plane and the leaving plane (both
+// re-read through L2, one plane ahead of the arithmetic), so there is no shared-memory ring of
+// plane sums.  That frees shared memory for 32 x 64 tiles (halo 1.28 x 1.14 instead of
+// 1.56 x 1.14), lets the x-pass produce 16 and the y-pass 8 outputs per task (25 resp. 17
+// shared loads), and makes the p0-1 warm-up planes of a z-chunk cost a register add instead of
+// a full plane of x/y passes.  Two block barriers per OUTPUT plane.
+// Input rows / columns past the map edge are CLAMPED, not zero-filled: they only ever feed
+// windows that are not fully inside the map, and those outputs are masked -- so every load is
+// unconditional (uniform plane pointer + 32-bit per-thread offset).  Requires the in-plane patch
+// extents to equal the compile-time PC (10 in all reference configs) and D1*D2 < 2^31.
+template <int TY, int TX, int PC> struct MarchTile {
+    static constexpr int NT = kFusedThreads;
+    static constexpr int R = TY + PC - 1, W = TX + PC - 1;
+    static constexpr int CW = (W + 15) / 16 * 16;              // threads per row group
+    static constexpr int G = NT / CW;                          // row groups marching in lock step
+    static constexpr int NSLOT = (R + G - 1) / G;              // input rows per thread
+    static constexpr int pitchA = W | 1, pitchB = TX + 1;      // odd pitches: rows striped over lanes
+    static constexpr int SEG = 16, NSEG = TX / SEG;            // x-pass task = 16 outputs of one row
+    static constexpr int RUN = TY * TX / NT;                   // y-pass: consecutive rows per thread
+    static constexpr size_t smem = (size_t)(R * pitchA + R * pitchB) * sizeof(double);
+    static_assert(G >= 1 && TX % SEG == 0 && RUN * (NT / TX) == TY && R * NSEG <= NT, "tile shape");
+    static_assert((NSLOT - 1) * G <= R, "only the last slot of a thread can fall outside the tile");
+};
+
+template <typename T, int TY, int TX, int PC, int PASS>
+__global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const FusedParams prm) {
+    using MT = MarchTile<TY, TX, PC>;
+    constexpr int NT = kFusedThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[NT / 32];
+    __shared__ int s_flag;
+    __shared__ int s_count;
+    double* A = reinterpret_cast<double*>(smem_raw);          // [R][pitchA] z-window sums
+    double* Bs = A + MT::R * MT::pitchA;                      // [R][pitchB] z-x sums
+    const int p0 = prm.p0;
+    const int64_t m = blockIdx.y;
+    const int tid = threadIdx.x;
+    const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+    const int tiles_xy = prm.tiles_x * prm.tiles_y;
+    const int zsub = PASS == 2 ? prm.zsub : 1;
+    const int zc_fine = PASS == 2 ? prm.zc_fine : prm.zc;
+    double gmax = 0.0;
+    unsigned long long tbest = ~0ull;
+    double tmax = ninf;
+    bool saw_nan = false;
+    int n_work = 1, work = 0, work_step = 1;
+    const int* list = nullptr;
+    if (PASS == 2) {
+        gmax = prm.gmax[m];
+        list = prm.active + m * (1 + kMaxActive);
+        const int n_act = list[0];
+        n_work = (n_act < 0 ? (int)prm.ntiles : n_act) * zsub;
+        work = blockIdx.x; work_step = gridDim.x;
+    }
+    // z-slide ownership: column cx of the input tile, rows g, g + G, ...
+    const int cx = min(tid % MT::CW, MT::W - 1), g = min(tid / MT::CW, MT::G - 1);
+    const bool zstore = tid % MT::CW < MT::W && tid / MT::CW < MT::G;
+    const bool last_in = g + (MT::NSLOT - 1) * MT::G < MT::R;   // last slot inside the tile?
+    // x-pass task and y-pass ownership
+    const int task_r = tid % MT::R, task_seg = tid / MT::R;
+    const int ox = tid % TX, oy0 = (tid / TX) * MT::RUN;
+    const unsigned int D1 = (unsigned int)prm.D1, D2 = (unsigned int)prm.D2;
+    for (; work < n_work; work += work_step) {
+        int tile, fine;
+        if (PASS == 1) { tile = blockIdx.x; fine = 0; }
+        else { const int a = work / zsub; fine = work - a * zsub; tile = list[0] < 0 ? a : list[1 + a]; }
+        const int tx_i = tile % prm.tiles_x;
+        const int ty_i = (tile / prm.tiles_x) % prm.tiles_y;
+        const int zc_i = tile / tiles_xy;
+        const int64_t zo0 = (int64_t)zc_i * prm.zc + (int64_t)fine * zc_fine;
+        const int64_t zo1 = min(zo0 + zc_fine, min((int64_t)(zc_i + 1) * prm.zc, prm.O0));
+        if (zo0 >= zo1) continue;
+        const unsigned int x0 = (unsigned int)tx_i * TX, y0 = (unsigned int)ty_i * TY;
+        const int nplanes = (int)(zo1 - zo0) + p0 - 1;
+        const unsigned int plane_elems = D1 * D2;
+        const T* src = reinterpret_cast<const T*>(prm.maps) + m * prm.stride_m + zo0 * (int64_t)plane_elems;
+        unsigned int off[MT::NSLOT];     // clamped in-plane offsets of this thread's input rows
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tmax = nanmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-        if (lane == 0) red[warp] = tmax;
-        __syncthreads();
-        if (tid == 0) {
-            double mm = red[0];
-            for (int w = 1; w < NT / 32; ++w) mm = nanmax(mm, red[w]);
-            prm.tile_max[m * prm.ntiles + blockIdx.x] = mm;
-            __threadfence();
-            s_flag = atomicAdd(prm.tickets + 2 * m, 1u) == gridDim.x - 1;
-            s_count = 0;
+        for (int i = 0; i < MT::NSLOT; ++i)
+            off[i] = min(y0 + g + i * MT::G, D1 - 1) * D2 + min(x0 + cx, D2 - 1);
+        double zs[MT::NSLOT];
+        T nw[MT::NSLOT], od[MT::NSLOT];
+#pragma unroll
+        for (int i = 0; i < MT::NSLOT; ++i) { zs[i] = 0.0; od[i] = (T)0; }
+        unsigned int valid = 0;   // bit k: output (oy0 + k, ox) lies inside the map
+#pragma unroll
+        for (int k = 0; k < MT::RUN; ++k)
+            if (y0 + oy0 + k < prm.O1 && x0 + ox < prm.O2) valid |= 1u << k;
+        const bool all_valid = valid == (1u << MT::RUN) - 1;
+
+        {   // plane 0 enters
+            const T* pn = src;
+#pragma unroll
+            for (int i = 0; i < MT::NSLOT; ++i) nw[i] = In<T>::load_one(pn + off[i]);
         }
-        __syncthreads();
-        if (!s_flag) return;
-        // last CTA of this map: map maximum (NaN propagates, as np.max) and the pass-2 work list
-        __threadfence();
-        const double* tm = prm.tile_max + m * prm.ntiles;
-        double mm = ninf;
-        for (int64_t i = tid; i < prm.ntiles; i += NT) mm = nanmax(mm, __ldcg(tm + i));
+        for (int zi = 0; zi < nplanes; ++zi) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mm = nanmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-        if (lane == 0) red[warp] = mm;
-        __syncthreads();
-        double g = red[0];
-        for (int w = 1; w < NT / 32; ++w) g = nanmax(g, red[w]);
-        int* lst = prm.active + m * (1 + kMaxActive);
-        for (int64_t i = tid; i < prm.ntiles; i += NT) {   // list order is irrelevant (min index wins)
-            if (np_isclose(__ldcg(tm + i), g, prm.rtol, prm.atol)) {
-                const int n = atomicAdd(&s_count, 1);
-                if (n < kMaxActive) lst[1 + n] = (int)i;
+            for (int i = 0; i < MT::NSLOT; ++i) zs[i] += (double)nw[i] - (double)od[i];
+            if (zi + 1 < nplanes) {    // entering plane zi+1 and leaving plane zi+1-p0: in flight
+                const T* pn = src + (int64_t)(zi + 1) * plane_elems;       // during the x / y passes
+#pragma unroll
+                for (int i = 0; i < MT::NSLOT; ++i) nw[i] = In<T>::load_one(pn + off[i]);
+                if (zi + 1 >= p0) {
+                    const T* po = pn - (int64_t)p0 * plane_elems;
+#pragma unroll
+                    for (int i = 0; i < MT::NSLOT; ++i) od[i] = In<T>::load_one(po + off[i]);
+                }
             }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            lst[0] = s_count > kMaxActive ? -1 : s_count;
-            prm.gmax[m] = g;
-            prm.max_score[m] = g;
-            prm.best[m] = ~0ull;
-        }
-    } else {
+            if (zi < p0 - 1) continue;                // z-window still filling: registers only
+            __syncthreads();                          // previous plane's y-pass is done with Bs (and A)
+            if (zstore) {
+                double* a = A + g * MT::pitchA + cx;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, tbest, o);
-            tbest = other < tbest ? other : tbest;
-        }
-        if (lane == 0 && tbest != ~0ull) atomicMin(prm.best + m, tbest);  // min is order-free
-        // last CTA of this map: publish the bounding-box corner
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            s_flag = atomicAdd(prm.tickets + 2 * m + 1, 1u) == gridDim.x - 1;
-        }
-        __syncthreads();
-        if (s_flag && tid == 0) {
-            __threadfence();
-            const unsigned long long b = atomicMin(prm.best + m, ~0ull);  // atomic read
-            int64_t* bb = prm.bbox_lo + 3 * m;
-            if (b == ~0ull) {  // no window is close to the max (NaN map): the reference raises IndexError
-                bb[0] = bb[1] = bb[2] = -1;
+                for (int i = 0; i < MT::NSLOT - 1; ++i) a[i * MT::G * MT::pitchA] = zs[i];
+                if (last_in) a[(MT::NSLOT - 1) * MT::G * MT::pitchA] = zs[MT::NSLOT - 1];
+            }
+            __syncthreads();
+            // ---- x-pass: 16 sliding outputs per task, window kept in registers
+            if (tid < MT::R * MT::NSEG) {
+                const double* row = A + task_r * MT::pitchA + task_seg * MT::SEG;
+                double* dst = Bs + task_r * MT::pitchB + task_seg * MT::SEG;
+                double v[PC];
+#pragma unroll
+                for (int k = 0; k < PC; ++k) v[k] = row[k];
+                double s = tree_sum<PC>(v);
+                dst[0] = s;
+#pragma unroll
+                for (int i = 1; i < MT::SEG; ++i) {
+                    const double in = row[i + PC - 1];
+                    s += in - v[(i - 1) % PC];
+                    v[(i - 1) % PC] = in;
+                    dst[i] = s;
+                }
+            }
+            __syncthreads();
+            // ---- y-pass: RUN sliding outputs down one column
+            const double* cb = Bs + oy0 * MT::pitchB + ox;
+            double c[PC];
+#pragma unroll
+            for (int j = 0; j < PC; ++j) c[j] = cb[j * MT::pitchB];
+            double o[MT::RUN];
+            o[0] = tree_sum<PC>(c);
+#pragma unroll
+            for (int k = 1; k < MT::RUN; ++k) {
+                const double in = cb[(k + PC - 1) * MT::pitchB];
+                o[k] = o[k - 1] + (in - c[(k - 1) % PC]);
+                c[(k - 1) % PC] = in;
+            }
+            if (prm.mean_flag) {
+#pragma unroll
+                for (int k = 0; k < MT::RUN; ++k) o[k] = box_mean_div(o[k], prm.denom);
+            }
+            if (PASS == 1) {
+                if (all_valid) {
+#pragma unroll
+                    for (int k = 0; k < MT::RUN; ++k) { tmax = fmax(tmax, o[k]); saw_nan |= o[k] != o[k]; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < MT::RUN; ++k)
+                        if ((valid >> k) & 1u) { tmax = fmax(tmax, o[k]); saw_nan |= o[k] != o[k]; }
+                }
             } else {
-                const int64_t lin = (int64_t)b;
-                bb[2] = lin % prm.O2;
-                bb[1] = (lin / prm.O2) % prm.O1;
-                bb[0] = lin / (prm.O2 * prm.O1);
+                const int64_t oz = zo0 + zi - (p0 - 1);
+#pragma unroll
+                for (int k = 0; k < MT::RUN; ++k) {
+                    if (((valid >> k) & 1u) && np_isclose(o[k], gmax, prm.rtol, prm.atol)) {
+                        const unsigned long long lin =
+                            (unsigned long long)((oz * prm.O1 + (y0 + oy0 + k)) * prm.O2 + (x0 + ox));
+                        tbest = lin < tbest ? lin : tbest;
+                    }
+                }
             }
         }
     }
+    if (saw_nan) tmax = __longlong_as_double(0x7ff8000000000000LL);   // np.max: NaN propagates
+    box_pass_finish<PASS>(prm, m, tmax, tbest, red, s_flag, s_count);
 }
 
 // ------------------------------------------------------------------ K2b fast path (p2 <= 32)
@@ -795,6 +989,7 @@ static int run_patch_stream(StreamParams prm, const StreamPlan& sp, int64_t M, d
 
 // ------------------------------------------------------------------ fused path: host side
 struct FusedPlan {
+    int march;             // 1 = box_march_kernel (32x64 tiles, z first), 0 = box_fused_kernel
     int ty, tx;            // 16x64 or 8x32; 0 = fused path not applicable
     int64_t O0, O1, O2;
     int tiles_x, tiles_y, chunks_z, zc, zsub, zc_fine;
@@ -809,6 +1004,7 @@ static size_t fused_smem_bytes(int ty, int tx, const int64_t* patch) {
 // 0 on success (pl.ty == 0 when the patch is too large for the fused kernel's shared memory)
 static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch, FusedPlan& pl) {
     pl.ty = pl.tx = 0;
+    pl.march = 0;
     for (int d = 0; d < 3; ++d) {
         if (shape[d] <= 0 || patch[d] <= 0)
             return set_error(VALUES_ERR_INVALID_ARG, "patch_max: non-positive shape/patch");
@@ -820,7 +1016,11 @@ static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch
     }
     pl.O0 = shape[0] - patch[0] + 1; pl.O1 = shape[1] - patch[1] + 1; pl.O2 = shape[2] - patch[2] + 1;
     const size_t budget = 113 * 1024;  // two CTAs per SM
-    if (fused_smem_bytes(16, 64, patch) <= budget && pl.O2 > 32) { pl.ty = 16; pl.tx = 64; }
+    if (g_patch_path != 4 && patch[1] == 10 && patch[2] == 10 && pl.O2 > 32 && pl.O1 > 16 &&
+        shape[1] * shape[2] < 0x7fffffffLL) {
+        pl.march = 1; pl.ty = 32; pl.tx = 64;
+    }
+    else if (fused_smem_bytes(16, 64, patch) <= budget && pl.O2 > 32) { pl.ty = 16; pl.tx = 64; }
     else if (fused_smem_bytes(8, 32, patch) <= budget) { pl.ty = 8; pl.tx = 32; }
     else return VALUES_OK;
     pl.tiles_x = (int)ceil_div(pl.O2, pl.tx);
@@ -833,7 +1033,8 @@ static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch
     for (int64_t zc : {(int64_t)8, (int64_t)16, (int64_t)32, (int64_t)64, (int64_t)128, pl.O0}) {
         if (zc > pl.O0) zc = pl.O0;
         const int64_t ctas = in_plane * ceil_div(pl.O0, zc);
-        const int64_t warm = patch[0] - 1 + 2;
+        // planes of pure warm-up per chunk, in units of a full plane (march: register adds only)
+        const int64_t warm = pl.march ? (patch[0] - 1) / 4 + 2 : patch[0] - 1 + 2;
         // CTAs neither run in lock-step waves nor perfectly smoothly: average both models
         const int64_t smooth = std::max(ceil_div(ctas * (zc + warm), 2 * 148), zc + warm);
         const int64_t waves = ceil_div(ctas, 2 * 148) * (zc + warm);
@@ -876,6 +1077,36 @@ static int run_patch_fused_pc(FusedParams prm, const FusedPlan& pl, int64_t M, c
         const unsigned g2 = (unsigned)std::min<int64_t>(pl.ntiles * pl.zsub, 4 * pl.zsub);
         k2<<<dim3(g2, (unsigned)mc), kFusedThreads, smem, st>>>(q);
         if ((rc = check_launch("box_fused_kernel<2>"))) return rc;
+    }
+    return VALUES_OK;
+}
+
+template <typename T>
+static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cudaStream_t st) {
+    using MT = MarchTile<32, 64, 10>;
+    auto k1 = box_march_kernel<T, 32, 64, 10, 1>;
+    auto k2 = box_march_kernel<T, 32, 64, 10, 2>;
+    const size_t smem = MT::smem;
+    if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute(%zu) failed", smem);
+    for (int64_t m0 = 0; m0 < M; m0 += 65535) {  // gridDim.y limit
+        const int64_t mc = std::min<int64_t>(65535, M - m0);
+        FusedParams q = prm;
+        q.maps = reinterpret_cast<const T*>(prm.maps) + m0 * prm.stride_m;
+        q.tile_max = prm.tile_max + m0 * pl.ntiles;
+        q.best = prm.best + m0;
+        q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
+        q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
+        q.tickets = prm.tickets + 2 * m0;
+        if (cudaMemsetAsync(q.tickets, 0, (size_t)mc * 2 * sizeof(unsigned int), st) != cudaSuccess)
+            return set_error(VALUES_ERR_CUDA, "patch_max: cudaMemsetAsync failed");
+        k1<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kFusedThreads, smem, st>>>(q);
+        int rc = check_launch("box_march_kernel<1>");
+        if (rc) return rc;
+        const unsigned g2 = (unsigned)std::min<int64_t>(pl.ntiles * pl.zsub, 4 * pl.zsub);
+        k2<<<dim3(g2, (unsigned)mc), kFusedThreads, smem, st>>>(q);
+        if ((rc = check_launch("box_march_kernel<2>"))) return rc;
     }
     return VALUES_OK;
 }
@@ -965,7 +1196,7 @@ extern "C" int values_normalize_maps(const void* maps, int dtype, int64_t M, int
 extern "C" size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* shape3_host,
                                                    const int64_t* patch3_host) {
     if (M <= 0 || !shape3_host || !patch3_host) return 0;
-    if (g_patch_path == 0) {
+    if (g_patch_path == 0 || g_patch_path == 4) {
         FusedPlan fp;
         if (make_fused_plan(M, shape3_host, patch3_host, fp) != VALUES_OK) return 0;
         if (fp.ty) return fused_workspace_bytes(M, fp);
@@ -993,7 +1224,7 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
     double* ws = reinterpret_cast<double*>(workspace);
     const double denom =
         mean_flag ? (double)patch3_host[0] * (double)patch3_host[1] * (double)patch3_host[2] : 1.0;
-    if (g_patch_path == 0) {
+    if (g_patch_path == 0 || g_patch_path == 4) {
         FusedPlan fp;
         int rc = make_fused_plan(M, shape3_host, patch3_host, fp);
         if (rc) return rc;
@@ -1017,6 +1248,10 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
             prm.tickets = reinterpret_cast<unsigned int*>(ws + M * fp.ntiles + 2 * M);
             prm.active = reinterpret_cast<int*>(ws + M * fp.ntiles + 3 * M);
             prm.max_score = max_score; prm.bbox_lo = bbox_lo;
+            if (fp.march) {
+                if (dtype == VALUES_F32) return run_patch_march<float>(prm, fp, M, st);
+                return run_patch_march<double>(prm, fp, M, st);
+            }
             if (fp.ty == 16) {
                 if (dtype == VALUES_F32) return run_patch_fused<float, 16, 64>(prm, fp, M, st);
                 return run_patch_fused<double, 16, 64>(prm, fp, M, st);
