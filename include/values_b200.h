@@ -127,10 +127,24 @@ int values_stitch_accumulate(const void* patches, int patch_dtype, int64_t patch
                              void* out_sum, int out_dtype, double* out_count, int accumulate,
                              void* stream);
 
+/* The same accumulator with a per-patch importance map (BASELINE.json north_star: "Gaussian-
+ * weighted sliding-window patch stitching"; the reference itself accumulates with uniform weights,
+ * SURVEY.md D1, so this is an opt-in extension and weight == NULL is exactly
+ * values_stitch_accumulate):  out_sum += weight * patch,  out_count += weight.
+ *   weight double [p0, p1, p2] (device) or NULL. */
+int values_stitch_accumulate_weighted(const void* patches, int patch_dtype, int64_t patch_stride_n,
+                                      int64_t patch_stride_p, const int32_t* patch_index,
+                                      const int32_t* crop_lo, const double* weight, int64_t n_sel,
+                                      int64_t N, int64_t C, const int64_t* patch3_host,
+                                      const int64_t* vol3_host, void* out_sum, int out_dtype,
+                                      double* out_count, int accumulate, void* stream);
+
 /* Save-time normalisation (data_carrier_3D.py:215-217, 326-329):
- *   out[m, v] = (double) maps[m, v] / max(count[v], 1)   -> fp64 as written to NIfTI. */
+ *   out[m, v] = (double) maps[m, v] / max(count[v], clip_min)   -> fp64 as written to NIfTI;
+ *   clip_min = 1 is the reference's np.clip(count, 1, None); clip_min = 0 divides by the weight
+ *   sum of a weighted stitch and leaves uncovered voxels (count == 0) unscaled. */
 int values_normalize_maps(const void* maps, int dtype, int64_t M, int64_t V, int64_t stride_m,
-                          const double* count, double* out, void* stream);
+                          const double* count, double clip_min, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4: whole-map statistics either side of the C2 -> C3 path.
@@ -198,8 +212,11 @@ int values_calib_bins_fused(const void* unc, int dtype, const void* pred_seg, co
  * voxel tiles per CTA of the K1 stream kernel, and its batch / occupancy variant. */
 void values_debug_set_k1_iter(int iter);
 void values_debug_set_k1_variant(int variant);
-/* K2b implementation: 0 automatic, 1 streaming two-kernel path, 2 generic tiled path. */
+/* K2b implementation: 0 automatic (march kernel for 10x10 in-plane patches, else fused tile kernel),
+ * 1 streaming two-kernel path, 2 generic tiled path, 4 fused tile kernel. */
 void values_debug_set_patch_path(int path);
+/* K3 implementation: 0 automatic (vector kernel when rows are 16-byte aligned), 1 scalar kernel. */
+void values_debug_set_stitch_path(int path);
 
 #ifdef __cplusplus
 }

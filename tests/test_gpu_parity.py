@@ -315,7 +315,16 @@ def test_c3_map_reduce_vs_oracle(vb, vo):
 
 
 # --------------------------------------------------------------------------------- stitch
-def test_stitch_golden(vb, vo):
+@pytest.fixture(params=[0, 1], ids=["k3-auto", "k3-scalar"])
+def stitch_path(request, vb):
+    """The vector kernel (4 z voxels per thread, used when rows are 16-byte aligned) and the scalar
+    kernel must both be bit-exact."""
+    vb._lib.lib.values_debug_set_stitch_path(request.param)
+    yield request.param
+    vb._lib.lib.values_debug_set_stitch_path(0)
+
+
+def test_stitch_golden(vb, vo, stitch_path):
     g = np.load(os.path.join(GOLDEN, "stitch_3d.npz"))
     shape, p = tuple(g["shape"].tolist()), int(g["patch"])
     crops = vb.patch_grid(shape, p, float(g["overlap"]))
@@ -355,8 +364,10 @@ def test_stitch_golden(vb, vo):
     ((96, 80, 72), 32, 0.5, torch.float32),
     ((50, 50, 40), 16, 0.75, torch.float32),     # non-multiple size -> uncovered remainder
     ((40, 24, 200), 8, 1.0, torch.bfloat16),
+    ((24, 40, 256), 16, 0.5, torch.float32),     # full-width vector tiles (64 threads x 4 voxels)
+    ((20, 24, 136), 12, 0.5, torch.float64),     # stride 6: z origins not multiples of 4
 ])
-def test_stitch_vs_oracle(vb, vo, shape, p, overlap, dtype):
+def test_stitch_vs_oracle(vb, vo, shape, p, overlap, dtype, stitch_path):
     crops = vo.patch_grid(shape, p, overlap)
     assert crops == vb.patch_grid(shape, p, overlap)
     n_pred, c = 2, 3
@@ -374,7 +385,7 @@ def test_stitch_vs_oracle(vb, vo, shape, p, overlap, dtype):
         np.testing.assert_allclose(t32.cpu().numpy(), st.data["v"]["softmax_pred"], rtol=1e-6)
 
 
-def test_stitch_many_patches_chunked_list(vb, vo):
+def test_stitch_many_patches_chunked_list(vb, vo, stitch_path):
     shape, p = (44, 44, 44), 8
     crops = vo.patch_grid(shape, p, 0.25)  # stride 2 -> 19^3 = 6859 patches > list chunk
     g = torch.Generator().manual_seed(1)
@@ -385,6 +396,35 @@ def test_stitch_many_patches_chunked_list(vb, vo):
     total, cnt = vb.stitch_volume(patches.cuda(), crops, shape)
     np.testing.assert_allclose(total.cpu().numpy(), st.data["v"]["softmax_pred"], rtol=1e-14)
     np.testing.assert_array_equal(cnt.cpu().numpy(), st.data["v"]["num_predictions"][0])
+
+
+def test_stitch_gaussian_weighted(vb, vo, stitch_path):
+    """Opt-in Gaussian-weighted stitching (north_star; the reference is uniform): bit-exact against
+    the numpy restatement `sum += w * patch`, `count += w`, and normalisation by the weight sum."""
+    shape, p = (40, 36, 72), 16
+    crops = vb.patch_grid(shape, p, 0.5)
+    g = torch.Generator().manual_seed(4)
+    patches = torch.rand(2, len(crops), 2, p, p, p, generator=g, dtype=torch.float32)
+    w = vb.gaussian_importance_map((p, p, p))
+    np.testing.assert_array_equal(w.numpy(), vo.gaussian_importance_map((p, p, p)))
+    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape, weight=w.cuda())
+    ref_total, ref_cnt = vo.stitch_weighted(patches.numpy(), crops, shape, w.numpy())
+    np.testing.assert_array_equal(total.cpu().numpy(), ref_total)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), ref_cnt)
+    # uniform weight of ones == the reference's unweighted accumulator, bit for bit
+    t1, c1 = vb.stitch_volume(patches.cuda(), crops, shape, weight=torch.ones(p, p, p, dtype=torch.float64).cuda())
+    t0, c0 = vb.stitch_volume(patches.cuda(), crops, shape)
+    assert torch.equal(t1, t0) and torch.equal(c1, c0)
+    # carrier with a weight: normalised softmax = weighted mean, uncovered remainder stays 0
+    carrier = vb.DataCarrier3D(patch_weight=w)
+    for pred_idx in range(2):
+        batch = {"image_paths": ["v"] * len(crops), "label_paths": [None] * len(crops),
+                 "org_image_size": [shape] * len(crops), "crop_idx": crops, "data": None, "seg": None}
+        carrier.concat_data(batch, patches[pred_idx], n_pred=2, pred_idx=pred_idx)
+    norm = carrier.normalized("v")["softmax_pred"].cpu().numpy()
+    want = ref_total / np.where(ref_cnt > 0, ref_cnt, 1.0)
+    np.testing.assert_allclose(norm, want, rtol=1e-15)
+    assert np.all(norm[:, :, :, 32:, :] == 0) and np.all(ref_cnt[:, 32:, :] == 0)
 
 
 # ------------------------------------------------------------------------------- pipeline
@@ -414,6 +454,25 @@ def test_pipeline_vs_oracle(vb, vo):
             np.testing.assert_allclose(e["patch_level"]["max_score"],
                                        vo.patch_level_aggregation(ref[key].numpy().astype(np.float64), 10)["max_score"], rtol=1e-5)
         assert_argmax(res.mean_argmax[b], x[b], np.argmax(np.mean(x[b].numpy(), axis=0), axis=0))
+
+
+def test_pipeline_chunking_and_overlap_do_not_change_results(vb):
+    """One chunk, many chunks, and K2b on a second stream under the next chunk's K1 must give
+    bit-identical score tables and maps (the two-stream schedule only reorders launches)."""
+    B, n, c, spatial = 7, 4, 3, (40, 44, 64)
+    x = softmax_stack(123, B * n, c, spatial).reshape(B, n, c, *spatial).cuda()
+    thr = (0.5, 0.4, 0.03)
+    per_vol = 3 * int(np.prod(spatial)) * 4
+    outs = []
+    for chunk, overlap in ((1 << 30, False), (2 * per_vol, False), (2 * per_vol, True), (per_vol, True)):
+        cfg = vb.AggregationConfig(patch_size=10, thresholds=thr, chunk_bytes=chunk, overlap=overlap)
+        pipe = vb.UncertaintyPipeline(cfg)
+        for _ in range(2):   # second run reuses the scratch buffers
+            r = pipe.run(x, keep_maps=False, mean_argmax=True)
+        torch.cuda.synchronize()
+        outs.append((r.scores.clone(), r.mean_argmax.clone()))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
 
 
 def test_full_size_properties(vb):

@@ -15,7 +15,7 @@ from .metrics import (calc_ace, calib_stats, calibration_error, calibration_erro
                       compute_ncc, ncc_batched, ncc_main, platt_scale_confid)
 from .pipeline import AggregationConfig, PipelineResult, UncertaintyPipeline
 from .sharding import gather_scores, shard_range, shard_sizes
-from .stitching import patch_grid, stitch_accumulate, stitch_volume
+from .stitching import gaussian_importance_map, patch_grid, stitch_accumulate, stitch_volume
 from .threshold import (calculate_foreground_quantile_image, calculate_threshold_image,
                         count_nonzero, find_threshold, get_foreground_quantile, quantile,
                         save_foreground_quantiles)
@@ -28,7 +28,7 @@ __all__ = [
     "calculate_uncertainty_multiple_pred", "uncertainty_fused", "FusedResult",
     "patch_level_aggregation", "image_level_aggregation", "threshold_aggregation",
     "aggregate_uncertainties", "patch_max", "map_reduce", "normalize_maps",
-    "DataCarrier3D", "patch_grid", "stitch_accumulate", "stitch_volume",
+    "DataCarrier3D", "patch_grid", "stitch_accumulate", "stitch_volume", "gaussian_importance_map",
     "UncertaintyPipeline", "AggregationConfig", "PipelineResult",
     "shard_range", "shard_sizes", "gather_scores",
     "calculate_foreground_quantile_image", "get_foreground_quantile", "save_foreground_quantiles",

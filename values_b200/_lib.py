@@ -49,7 +49,9 @@ def _load() -> C.CDLL:
                                        vp, vp, vp, sz, vp]),
         "values_stitch_accumulate": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, i64, i64, i64,
                                                pi64, pi64, vp, C.c_int, vp, C.c_int, vp]),
-        "values_normalize_maps": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, vp, vp]),
+        "values_stitch_accumulate_weighted": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, vp, i64, i64, i64,
+                                                        pi64, pi64, vp, C.c_int, vp, C.c_int, vp]),
+        "values_normalize_maps": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, dbl, vp, vp]),
         "values_count_nonzero": (C.c_int, [vp, C.c_int, i64, vp, vp]),
         "values_radix_histogram": (C.c_int, [vp, C.c_int, i64, C.c_uint64, C.c_int, C.c_int, vp, vp]),
         "values_min_key_above": (C.c_int, [vp, C.c_int, i64, C.c_uint64, vp, vp]),
@@ -62,6 +64,7 @@ def _load() -> C.CDLL:
         "values_debug_set_k1_iter": (None, [C.c_int]),
         "values_debug_set_k1_variant": (None, [C.c_int]),
         "values_debug_set_patch_path": (None, [C.c_int]),
+        "values_debug_set_stitch_path": (None, [C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
@@ -77,11 +80,12 @@ EXPORTED = [
     "values_uncertainty_workspace_bytes", "values_uncertainty_fused", "values_one_minus_msr",
     "values_map_reduce_workspace_bytes", "values_map_reduce",
     "values_patch_max_workspace_bytes", "values_patch_max", "values_stitch_accumulate",
+    "values_stitch_accumulate_weighted",
     "values_normalize_maps", "values_count_nonzero", "values_radix_histogram",
     "values_min_key_above", "values_pair_moments_workspace_bytes", "values_pair_moments",
     "values_calib_bins_workspace_bytes", "values_calib_bins", "values_calib_bins_fused",
     "values_debug_set_k1_iter", "values_debug_set_k1_variant",
-    "values_debug_set_patch_path",
+    "values_debug_set_patch_path", "values_debug_set_stitch_path",
 ]
 
 

@@ -114,8 +114,9 @@ def map_reduce(maps: torch.Tensor, thresholds: Optional[Sequence[float]] = None)
     return out
 
 
-def normalize_maps(maps: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
-    """maps [M, *S] / clip(count [*S], 1) -> fp64 [M, *S] (data_carrier_3D.py:215-217, 326-329)."""
+def normalize_maps(maps: torch.Tensor, count: torch.Tensor, clip_min: float = 1.0) -> torch.Tensor:
+    """maps [M, *S] / clip(count [*S], 1) -> fp64 [M, *S] (data_carrier_3D.py:215-217, 326-329).
+    clip_min=0: divide by a weighted stitch's weight sum, uncovered voxels unscaled."""
     maps = maps.contiguous()
     count = count.to(torch.float64).contiguous()
     M = maps.shape[0]
@@ -125,7 +126,7 @@ def normalize_maps(maps: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
     out = torch.empty(maps.shape, dtype=torch.float64, device=maps.device)
     with torch.cuda.device(maps.device):
         rc = _lib.lib.values_normalize_maps(maps.data_ptr(), _lib.dtype_code(maps.dtype), M, V, V,
-                                            count.data_ptr(), out.data_ptr(),
+                                            count.data_ptr(), float(clip_min), out.data_ptr(),
                                             _lib.stream_ptr(maps.device))
     _lib.check(rc)
     return out

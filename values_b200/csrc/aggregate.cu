@@ -50,11 +50,13 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) normalize_kernel(const T* __restrict__ maps, int64_t V,
                                                              int64_t stride_m, int64_t bpm,
                                                              const double* __restrict__ count,
+                                                             double clip_min,
                                                              double* __restrict__ out) {
     const int64_t m = blockIdx.x / bpm;
     const int64_t v = (blockIdx.x - m * bpm) * kThreads + threadIdx.x;
     if (v >= V) return;
-    const double c = fmax(count[v], 1.0);  // np.clip(count, 1, None)
+    // np.clip(count, 1, None) for clip_min = 1; clip_min = 0 (weighted stitching): uncovered -> 1
+    const double c = clip_min > 0.0 ? fmax(count[v], clip_min) : (count[v] > 0.0 ? count[v] : 1.0);
     out[m * V + v] = (double)In<T>::load_one(maps + m * stride_m + v) / c;
 }
 
@@ -1170,8 +1172,8 @@ extern "C" int values_map_reduce(const void* maps, int dtype, int64_t M, int64_t
 }
 
 extern "C" int values_normalize_maps(const void* maps, int dtype, int64_t M, int64_t V,
-                                     int64_t stride_m, const double* count, double* out,
-                                     void* stream) {
+                                     int64_t stride_m, const double* count, double clip_min,
+                                     double* out, void* stream) {
     if (!maps || !count || !out) return set_error(VALUES_ERR_INVALID_ARG, "normalize: NULL pointer");
     if (M < 0 || V < 0) return set_error(VALUES_ERR_INVALID_ARG, "normalize: bad sizes");
     if (M == 0 || V == 0) return VALUES_OK;
@@ -1181,10 +1183,10 @@ extern "C" int values_normalize_maps(const void* maps, int dtype, int64_t M, int
     const unsigned grid = (unsigned)(bpm * M);
     switch (dtype) {
         case VALUES_F32:
-            normalize_kernel<float><<<grid, kThreads, 0, st>>>((const float*)maps, V, stride_m, bpm, count, out);
+            normalize_kernel<float><<<grid, kThreads, 0, st>>>((const float*)maps, V, stride_m, bpm, count, clip_min, out);
             break;
         case VALUES_F64:
-            normalize_kernel<double><<<grid, kThreads, 0, st>>>((const double*)maps, V, stride_m, bpm, count, out);
+            normalize_kernel<double><<<grid, kThreads, 0, st>>>((const double*)maps, V, stride_m, bpm, count, clip_min, out);
             break;
         default: return set_error(VALUES_ERR_INVALID_ARG, "normalize: dtype must be f32 or f64");
     }

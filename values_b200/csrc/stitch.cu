@@ -13,12 +13,14 @@ namespace vb {
 constexpr int kSZ = 64;  // tile extent along the contiguous axis (z)
 constexpr int kSY = 4;   // tile extent along axis 1 (y); kSZ*kSY == kThreads
 constexpr int kMaxList = 1024;  // overlapping patches kept per tile chunk
+static int g_stitch_path = 0;    // 0 = automatic, 1 = scalar kernel only (values_debug_set_stitch_path)
 
 struct StitchParams {
     const void* patches;
     int64_t stride_n, stride_p;
     const int32_t* patch_index;
     const int32_t* crop_lo;
+    const double* weight;   // [p0, p1, p2] importance map or NULL (uniform, the reference)
     int64_t n_sel, N, C;
     int p0, p1, p2;
     int64_t X, Y, Z;
@@ -91,8 +93,15 @@ __global__ void __launch_bounds__(kThreads) stitch_kernel(const StitchParams prm
                     if (y >= cy && y < cy + prm.p1 && z >= cz && z < cz + prm.p2) {
                         const int64_t pi = prm.patch_index ? prm.patch_index[i] : i;
                         const int64_t local = ((x - cx) * prm.p1 + (y - cy)) * prm.p2 + (z - cz);
-                        acc += (double)In<TP>::load_one(pin + pi * prm.stride_p + c * pvol + local);
-                        if (c == 0) cnt += 1.0;
+                        const double v = (double)In<TP>::load_one(pin + pi * prm.stride_p + c * pvol + local);
+                        if (prm.weight) {
+                            const double w = __ldg(prm.weight + local);
+                            acc = __dadd_rn(acc, __dmul_rn(w, v));   // two roundings, as `sum += w * patch`
+                            if (c == 0) cnt += w;
+                        } else {
+                            acc += v;
+                            if (c == 0) cnt += 1.0;
+                        }
                     }
                 }
                 *dst = (TO)acc;
@@ -106,17 +115,258 @@ __global__ void __launch_bounds__(kThreads) stitch_kernel(const StitchParams prm
     }
 }
 
+
+// ------------------------------------------------------------------ K3 vector kernel
+// Same output-stationary scheme, but a thread owns FOUR consecutive z voxels of one (x, y) row
+// and kCB classes at once: per overlapping patch it issues kCB independent 16-byte loads (fp32
+// patches), so a CTA keeps ~8 KB in flight instead of 1 KB -- the scalar kernel is latency
+// bound at ~0.13 of HBM peak.  Patches whose z origin is not a multiple of 4 are handled element
+// by element inside the same kernel (uniform per patch, no divergence).  Requires Z % 4 == 0,
+// p2 % 4 == 0 and 16-byte aligned patch rows / outputs (checked on the host).
+constexpr int kCB = 2;   // classes per sweep of the overlap list (the reference has C == 2)
+
+// four consecutive elements: raw load (kept in flight as bits) and widening to fp64
+template <typename T> struct Raw4;
+template <> struct Raw4<float> {
+    using type = uint4;
+    __device__ static __forceinline__ type load(const float* p) { return ldg_stream_128(p); }
+    __device__ static __forceinline__ void widen(const type& r, double (&o)[4]) {
+        o[0] = (double)__uint_as_float(r.x); o[1] = (double)__uint_as_float(r.y);
+        o[2] = (double)__uint_as_float(r.z); o[3] = (double)__uint_as_float(r.w);
+    }
+};
+template <> struct Raw4<double> {
+    struct type { uint4 a, b; };
+    __device__ static __forceinline__ type load(const double* p) { return {ldg_stream_128(p), ldg_stream_128(p + 2)}; }
+    __device__ static __forceinline__ void widen(const type& r, double (&o)[4]) {
+        o[0] = __hiloint2double((int)r.a.y, (int)r.a.x); o[1] = __hiloint2double((int)r.a.w, (int)r.a.z);
+        o[2] = __hiloint2double((int)r.b.y, (int)r.b.x); o[3] = __hiloint2double((int)r.b.w, (int)r.b.z);
+    }
+};
+template <> struct Raw4<__nv_bfloat16> {
+    using type = uint2;
+    __device__ static __forceinline__ type load(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+    __device__ static __forceinline__ void widen(const type& r, double (&o)[4]) {
+        o[0] = (double)__uint_as_float(r.x << 16); o[1] = (double)__uint_as_float(r.x & 0xffff0000u);
+        o[2] = (double)__uint_as_float(r.y << 16); o[3] = (double)__uint_as_float(r.y & 0xffff0000u);
+    }
+};
+template <typename TO> __device__ __forceinline__ void store4(TO* p, const double (&v)[4]);
+template <> __device__ __forceinline__ void store4<double>(double* p, const double (&v)[4]) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<float>(float* p, const double (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+}
+template <typename TO> __device__ __forceinline__ void read4(const TO* p, double (&v)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (double)p[e];
+}
+
+constexpr int kXB = 8;   // x planes per CTA of the vector kernel (one overlap list serves them all)
+
+template <typename TP, typename TO, int TZ, bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads, 3) stitch_vec_kernel(const StitchParams prm) {
+    constexpr int TYV = kThreads / TZ;          // rows per tile
+    __shared__ int4 s_list[kMaxList];           // {cx, cy, cz, patch index} of the overlapping patches
+    __shared__ long long s_base[64];            // element offset of patch voxel (0,0,0) minus its crop origin
+    __shared__ int s_warp_cnt[kThreads / 32];
+    __shared__ int s_total;
+
+    int tile = blockIdx.x;
+    const int tz = tile % prm.tiles_z; tile /= prm.tiles_z;
+    const int ty = tile % prm.tiles_y; tile /= prm.tiles_y;
+    const int64_t x_lo = (int64_t)tile * kXB;
+    const int64_t x_hi = min(x_lo + kXB, prm.X);
+    const int64_t n = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t y_lo = (int64_t)ty * TYV, z_lo = (int64_t)tz * (TZ * 4);
+    const int64_t y = y_lo + tid / TZ, z = z_lo + (int64_t)(tid % TZ) * 4;
+    const bool inside = y < prm.Y && z < prm.Z;     // Z % 4 == 0: a vector is inside or outside
+    const int64_t vol = prm.X * prm.Y * prm.Z;
+    const int64_t pvol = (int64_t)prm.p0 * prm.p1 * prm.p2;
+    TO* out = reinterpret_cast<TO*>(prm.out_sum) + n * prm.C * vol;
+    const TP* pin = reinterpret_cast<const TP*>(prm.patches) + n * prm.stride_n;
+
+    for (int64_t base = 0; base < prm.n_sel; base += kMaxList) {
+        // ---- ordered compaction of the patches overlapping this CTA's box (chunk of kMaxList)
+        const int64_t chunk = min((int64_t)kMaxList, prm.n_sel - base);
+        if (tid == 0) s_total = 0;
+        __syncthreads();
+        for (int64_t off = 0; off < chunk; off += kThreads) {
+            const int64_t i = base + off + tid;
+            bool hit = false;
+            int4 e = make_int4(0, 0, 0, 0);
+            if (off + tid < chunk) {
+                e.x = prm.crop_lo[3 * i]; e.y = prm.crop_lo[3 * i + 1]; e.z = prm.crop_lo[3 * i + 2];
+                e.w = prm.patch_index ? prm.patch_index[i] : (int)i;
+                hit = x_lo < e.x + prm.p0 && x_hi > e.x && y_lo < e.y + prm.p1 && y_lo + TYV > e.y &&
+                      z_lo < e.z + prm.p2 && z_lo + TZ * 4 > e.z;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int before = s_total;
+            for (int w = 0; w < warp; ++w) before += s_warp_cnt[w];
+            if (hit) s_list[before + __popc(bal & ((1u << lane) - 1u))] = e;
+            __syncthreads();
+            if (tid == 0) {
+                int t = s_total;
+                for (int w = 0; w < kThreads / 32; ++w) t += s_warp_cnt[w];
+                s_total = t;
+            }
+            __syncthreads();
+        }
+        const int total = s_total;
+        const bool readback = base > 0 || prm.accumulate;
+        // one patch: add its four voxels (all classes of the chunk) to the accumulators
+        auto add_patch = [&](const int4& e, int64_t local, const TP* src, int64_t c0, double (&acc)[kCB][4],
+                             double (&cnt)[4]) {
+            if ((e.z & 3) == 0) {         // aligned z origin: the vector is fully inside the patch
+                typename Raw4<TP>::type raw[kCB];
+#pragma unroll
+                for (int cc = 0; cc < kCB; ++cc)
+                    if (c0 + cc < prm.C) raw[cc] = Raw4<TP>::load(src + cc * pvol);
+                double w[4] = {1.0, 1.0, 1.0, 1.0};
+                if (WEIGHTED) Raw4<double>::widen(Raw4<double>::load(prm.weight + local), w);
+#pragma unroll
+                for (int cc = 0; cc < kCB; ++cc) {
+                    if (c0 + cc < prm.C) {
+                        double v[4];
+                        Raw4<TP>::widen(raw[cc], v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            acc[cc][q] = WEIGHTED ? __dadd_rn(acc[cc][q], __dmul_rn(w[q], v[q])) : acc[cc][q] + v[q];
+                    }
+                }
+                if (c0 == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cnt[q] += w[q];
+                }
+            } else {                      // unaligned z origin: element by element
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (z + q < e.z || z + q >= e.z + prm.p2) continue;
+                    const double w = WEIGHTED ? __ldg(prm.weight + local + q) : 1.0;
+#pragma unroll
+                    for (int cc = 0; cc < kCB; ++cc) {
+                        if (c0 + cc < prm.C) {
+                            const double v = (double)In<TP>::load_one(src + cc * pvol + q);
+                            acc[cc][q] = WEIGHTED ? __dadd_rn(acc[cc][q], __dmul_rn(w, v)) : acc[cc][q] + v;
+                        }
+                    }
+                    if (c0 == 0) cnt[q] += w;
+                }
+            }
+        };
+        if (total <= 64) {
+            // Fast path: the (y, z) test of this thread against every listed patch is folded into one
+            // 64-bit mask, and each patch's address arithmetic into one shared 64-bit base, so the
+            // x / class loops only walk set bits.
+            if (tid < total) {
+                const int4 e = s_list[tid];
+                s_base[tid] = (long long)e.w * prm.stride_p - (((long long)e.x * prm.p1 + e.y) * prm.p2 + e.z);
+            }
+            __syncthreads();
+            unsigned long long mask = 0;
+            if (inside) {
+                for (int k = 0; k < total; ++k) {
+                    const int4 e = s_list[k];
+                    if (y >= e.y && y < e.y + prm.p1 && z + 3 >= e.z && z < e.z + prm.p2) mask |= 1ull << k;
+                }
+            }
+            for (int64_t x = x_lo; x < x_hi && mask; ++x) {
+                const int64_t vox = (x * prm.Y + y) * prm.Z + z;
+                const int64_t toff = (x * prm.p1 + y) * prm.p2 + z;
+                double cnt[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int64_t c0 = 0; c0 < prm.C; c0 += kCB) {
+                    double acc[kCB][4];
+#pragma unroll
+                    for (int cc = 0; cc < kCB; ++cc) {
+                        if (readback && c0 + cc < prm.C) read4(out + (c0 + cc) * vol + vox, acc[cc]);
+                        else { acc[cc][0] = acc[cc][1] = acc[cc][2] = acc[cc][3] = 0.0; }
+                    }
+                    unsigned long long m = mask;
+                    while (m) {
+                        const int k = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const int4 e = s_list[k];
+                        if (x < e.x || x >= e.x + prm.p0) continue;
+                        const int64_t sb = s_base[k] + toff;
+                        add_patch(e, sb - (int64_t)e.w * prm.stride_p, pin + sb + c0 * pvol, c0, acc, cnt);
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < kCB; ++cc)
+                        if (c0 + cc < prm.C) store4<TO>(out + (c0 + cc) * vol + vox, acc[cc]);
+                }
+                if (n == 0 && prm.out_count) {
+                    double* d = prm.out_count + vox;
+                    if (readback) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cnt[q] += d[q];
+                    }
+                    store4<double>(d, cnt);
+                }
+            }
+            if (inside && !mask && !readback) {   // no patch covers this thread's voxels: zeros
+                const double zero[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int64_t x = x_lo; x < x_hi; ++x) {
+                    const int64_t vox = (x * prm.Y + y) * prm.Z + z;
+                    for (int64_t c = 0; c < prm.C; ++c) store4<TO>(out + c * vol + vox, zero);
+                    if (n == 0 && prm.out_count) store4<double>(prm.out_count + vox, zero);
+                }
+            }
+        } else if (inside) {
+            // Dense overlap (more than 64 patches touch the box): walk the whole list per voxel.
+            for (int64_t x = x_lo; x < x_hi; ++x) {
+                const int64_t vox = (x * prm.Y + y) * prm.Z + z;
+                double cnt[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int64_t c0 = 0; c0 < prm.C; c0 += kCB) {
+                    double acc[kCB][4];
+#pragma unroll
+                    for (int cc = 0; cc < kCB; ++cc) {
+                        if (readback && c0 + cc < prm.C) read4(out + (c0 + cc) * vol + vox, acc[cc]);
+                        else { acc[cc][0] = acc[cc][1] = acc[cc][2] = acc[cc][3] = 0.0; }
+                    }
+                    for (int k = 0; k < total; ++k) {
+                        const int4 e = s_list[k];
+                        if (x < e.x || x >= e.x + prm.p0 || y < e.y || y >= e.y + prm.p1 || z + 3 < e.z ||
+                            z >= e.z + prm.p2)
+                            continue;
+                        const int64_t local = ((x - e.x) * prm.p1 + (y - e.y)) * prm.p2 + (z - e.z);
+                        add_patch(e, local, pin + (int64_t)e.w * prm.stride_p + c0 * pvol + local, c0, acc, cnt);
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < kCB; ++cc)
+                        if (c0 + cc < prm.C) store4<TO>(out + (c0 + cc) * vol + vox, acc[cc]);
+                }
+                if (n == 0 && prm.out_count) {
+                    double* d = prm.out_count + vox;
+                    if (readback) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cnt[q] += d[q];
+                    }
+                    store4<double>(d, cnt);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace vb
 
 using namespace vb;
 
-extern "C" int values_stitch_accumulate(const void* patches, int patch_dtype,
-                                        int64_t patch_stride_n, int64_t patch_stride_p,
-                                        const int32_t* patch_index, const int32_t* crop_lo,
-                                        int64_t n_sel, int64_t N, int64_t C,
-                                        const int64_t* patch3_host, const int64_t* vol3_host,
-                                        void* out_sum, int out_dtype, double* out_count,
-                                        int accumulate, void* stream) {
+extern "C" int values_stitch_accumulate_weighted(const void* patches, int patch_dtype,
+                                                 int64_t patch_stride_n, int64_t patch_stride_p,
+                                                 const int32_t* patch_index, const int32_t* crop_lo,
+                                                 const double* weight, int64_t n_sel, int64_t N,
+                                                 int64_t C, const int64_t* patch3_host,
+                                                 const int64_t* vol3_host, void* out_sum,
+                                                 int out_dtype, double* out_count, int accumulate,
+                                                 void* stream) {
     if (!patches || !crop_lo || !patch3_host || !vol3_host || !out_sum)
         return set_error(VALUES_ERR_INVALID_ARG, "stitch: NULL pointer");
     if (n_sel < 0 || N <= 0 || C <= 0)
@@ -136,17 +386,54 @@ extern "C" int values_stitch_accumulate(const void* patches, int patch_dtype,
     }
     StitchParams prm{};
     prm.patches = patches; prm.stride_n = patch_stride_n; prm.stride_p = patch_stride_p;
-    prm.patch_index = patch_index; prm.crop_lo = crop_lo;
+    prm.patch_index = patch_index; prm.crop_lo = crop_lo; prm.weight = weight;
     prm.n_sel = n_sel; prm.N = N; prm.C = C;
     prm.p0 = (int)patch3_host[0]; prm.p1 = (int)patch3_host[1]; prm.p2 = (int)patch3_host[2];
     prm.X = vol3_host[0]; prm.Y = vol3_host[1]; prm.Z = vol3_host[2];
     prm.out_sum = out_sum; prm.out_count = out_count; prm.accumulate = accumulate ? 1 : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    // vector kernel: 4 consecutive z voxels per thread (16-byte loads / stores)
+    const size_t pes = patch_dtype == VALUES_F64 ? 8 : (patch_dtype == VALUES_F32 ? 4 : 2);
+    const size_t oes = out_dtype == VALUES_F64 ? 8 : 4;
+    const bool vec_ok = g_stitch_path != 1 && prm.Z % 4 == 0 && prm.p2 % 4 == 0 &&
+                        (reinterpret_cast<uintptr_t>(patches) % (4 * pes)) == 0 &&
+                        (patch_stride_n % 4) == 0 && (patch_stride_p % 4) == 0 &&
+                        (reinterpret_cast<uintptr_t>(out_sum) % (4 * oes)) == 0 &&
+                        (!out_count || reinterpret_cast<uintptr_t>(out_count) % 32 == 0) &&
+                        (!weight || reinterpret_cast<uintptr_t>(weight) % 32 == 0);
+    if (vec_ok) {
+        // tile extent along z: short tiles keep the overlap list short (every thread walks all of it)
+        const int tzv = g_stitch_path == 32 ? 32 : (g_stitch_path == 64 ? 64 : 16);
+        prm.tiles_z = (int)ceil_div(prm.Z, tzv * 4);
+        prm.tiles_y = (int)ceil_div(prm.Y, kThreads / tzv);
+        const int64_t vtiles = (int64_t)prm.tiles_z * prm.tiles_y * ceil_div(prm.X, kXB);
+        if (vtiles > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "stitch: volume too large");
+        const dim3 vgrid((unsigned)vtiles, (unsigned)N);
+#define VB_STITCHV2(TP, TO, TZV) do { if (weight) stitch_vec_kernel<TP, TO, TZV, true><<<vgrid, kThreads, 0, st>>>(prm); \
+        else stitch_vec_kernel<TP, TO, TZV, false><<<vgrid, kThreads, 0, st>>>(prm); } while (0)
+#define VB_STITCHV3(TP, TO) do { if (tzv == 16) VB_STITCHV2(TP, TO, 16); \
+        else if (tzv == 32) VB_STITCHV2(TP, TO, 32); else VB_STITCHV2(TP, TO, 64); } while (0)
+        if (out_dtype == VALUES_F64) {
+            if (patch_dtype == VALUES_F64) VB_STITCHV3(double, double);
+            else if (patch_dtype == VALUES_F32) VB_STITCHV3(float, double);
+            else if (patch_dtype == VALUES_BF16) VB_STITCHV3(__nv_bfloat16, double);
+            else return set_error(VALUES_ERR_INVALID_ARG, "stitch: unknown patch dtype");
+        } else if (out_dtype == VALUES_F32) {
+            if (patch_dtype == VALUES_F32) VB_STITCHV3(float, float);
+            else if (patch_dtype == VALUES_BF16) VB_STITCHV3(__nv_bfloat16, float);
+            else return set_error(VALUES_ERR_INVALID_ARG, "stitch: f32 output needs f32/bf16 patches");
+        } else {
+            return set_error(VALUES_ERR_INVALID_ARG, "stitch: out dtype must be f64 or f32");
+        }
+#undef VB_STITCHV3
+#undef VB_STITCHV2
+        return check_launch("stitch_vec_kernel");
+    }
     prm.tiles_z = (int)ceil_div(prm.Z, kSZ);
     prm.tiles_y = (int)ceil_div(prm.Y, kSY);
     const int64_t tiles = (int64_t)prm.tiles_z * prm.tiles_y * prm.X;
     if (tiles > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "stitch: volume too large");
     const dim3 grid((unsigned)tiles, (unsigned)N);
-    cudaStream_t st = (cudaStream_t)stream;
 #define VB_STITCH(TP, TO) stitch_kernel<TP, TO><<<grid, kThreads, 0, st>>>(prm)
     if (out_dtype == VALUES_F64) {
         if (patch_dtype == VALUES_F64) VB_STITCH(double, double);
@@ -163,3 +450,18 @@ extern "C" int values_stitch_accumulate(const void* patches, int patch_dtype,
 #undef VB_STITCH
     return check_launch("stitch_kernel");
 }
+
+extern "C" int values_stitch_accumulate(const void* patches, int patch_dtype,
+                                        int64_t patch_stride_n, int64_t patch_stride_p,
+                                        const int32_t* patch_index, const int32_t* crop_lo,
+                                        int64_t n_sel, int64_t N, int64_t C,
+                                        const int64_t* patch3_host, const int64_t* vol3_host,
+                                        void* out_sum, int out_dtype, double* out_count,
+                                        int accumulate, void* stream) {
+    return values_stitch_accumulate_weighted(patches, patch_dtype, patch_stride_n, patch_stride_p,
+                                             patch_index, crop_lo, nullptr, n_sel, N, C, patch3_host,
+                                             vol3_host, out_sum, out_dtype, out_count, accumulate,
+                                             stream);
+}
+
+extern "C" void values_debug_set_stitch_path(int path) { vb::g_stitch_path = path; }

@@ -28,11 +28,15 @@ from .uncertainty import MAP_KEYS, uncertainty_fused
 
 
 class DataCarrier3D:
-    def __init__(self, device: Optional[torch.device] = None, accum_dtype: torch.dtype = torch.float64):
+    def __init__(self, device: Optional[torch.device] = None, accum_dtype: torch.dtype = torch.float64,
+                 patch_weight: Optional[torch.Tensor] = None):
         self.data: Dict[str, Dict] = {}
         self.save_dir = None
         self.device = device
         self.accum_dtype = accum_dtype  # fp64 = reference parity (np.zeros default)
+        # opt-in importance map [p, p, p] (e.g. stitching.gaussian_importance_map): softmax sums
+        # and `num_predictions` become weighted sums.  None = uniform, the reference's behaviour.
+        self.patch_weight = patch_weight
 
     def _dev(self) -> torch.device:
         if self.device is None:
@@ -80,10 +84,11 @@ class DataCarrier3D:
             crop_lo = torch.from_numpy(lo).to(dev)
             pidx = torch.tensor(idxs, dtype=torch.int32, device=dev)
             stitch_accumulate(sp.unsqueeze(0), crop_lo, entry["softmax_pred"][pred_idx:pred_idx + 1],
-                              entry["_count"] if pred_idx == 0 else None, patch_index=pidx, accumulate=True)
+                              entry["_count"] if pred_idx == 0 else None, patch_index=pidx, accumulate=True,
+                              weight=self.patch_weight)
             if sg is not None:
                 stitch_accumulate(sg.unsqueeze(0), crop_lo, entry["sigma"][pred_idx:pred_idx + 1],
-                                  None, patch_index=pidx, accumulate=True)
+                                  None, patch_index=pidx, accumulate=True, weight=self.patch_weight)
             if pred_idx == 0:  # image / label slabs (:138-153): bookkeeping, plain torch slicing
                 for i in idxs:
                     (x0, x1), (y0, y1), (z0, z1) = batch["crop_idx"][i]
@@ -104,7 +109,8 @@ class DataCarrier3D:
         cnt = v["_count"]
         n_pred, n_cls = v["softmax_pred"].shape[:2]
         size = tuple(cnt.shape)
-        sm = normalize_maps(v["softmax_pred"].reshape((n_pred * n_cls,) + size), cnt)
+        clip_min = 1.0 if self.patch_weight is None else 0.0
+        sm = normalize_maps(v["softmax_pred"].reshape((n_pred * n_cls,) + size), cnt, clip_min)
         sm = sm.reshape((n_pred, n_cls) + size)
         res = uncertainty_fused(sm.unsqueeze(0), maps=False, mean_argmax=True, sample_argmax=True)
         out = {
@@ -116,7 +122,7 @@ class DataCarrier3D:
         present = [k for k in MAP_KEYS if k in v]
         if present:
             maps = torch.stack([v[k].to(cnt.device) for k in present])
-            norm = normalize_maps(maps, cnt)
+            norm = normalize_maps(maps, cnt, clip_min)
             for i, k in enumerate(present):
                 out[k] = norm[i]
         return out

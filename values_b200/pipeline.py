@@ -30,9 +30,10 @@ class AggregationConfig:
     patch_mean: bool = False
     thresholds: Optional[Sequence[float]] = None  # (pred_entropy, aleatoric, epistemic)
     threshold_mean: bool = True
-    chunk_bytes: int = 256 << 20               # fp32 map scratch per chunk (8-10 128^3 volumes: enough
-                                               # K2b CTAs for several waves; K1 keeps the maps
-                                               # L2-friendly by reading its input evict-first)
+    chunk_bytes: int = 1 << 30                 # fp32 map scratch per chunk (32 128^3 volumes = 96 maps:
+                                               # K2b's 32x64x(z-chunk) tiles need ~100 maps per launch
+                                               # to fill 148 SMs x 2 CTAs for several waves; measured
+                                               # 4.28 ms/step at 256 MB -> 4.05 ms at 1 GB on cfg5)
     overlap: bool = False                      # run K2b of chunk i on a second stream under K1 of chunk
                                                # i+1 (K1 is HBM-bound, K2b shared-memory/issue-bound);
                                                # costs a second map scratch buffer

@@ -43,6 +43,7 @@ def stitch_accumulate(
     out_count: Optional[torch.Tensor] = None,  # fp64 [X, Y, Z]
     patch_index: Optional[torch.Tensor] = None,  # int32 [n_sel] or None (identity)
     accumulate: bool = True,
+    weight: Optional[torch.Tensor] = None,     # fp64 [p0, p1, p2] importance map (None = uniform)
 ) -> None:
     if patches.device.type != "cuda":
         raise RuntimeError("stitch_accumulate expects CUDA tensors (no CPU fallback)")
@@ -66,25 +67,48 @@ def stitch_accumulate(
                                   or tuple(out_count.shape) != tuple(out_sum.shape[2:])):
         raise ValueError("out_count must be contiguous fp64 [X, Y, Z]")
     dev = patches.device
+    if weight is not None:
+        if tuple(weight.shape) != tuple(patches.shape[3:]):
+            raise ValueError("weight must have the patch shape [p0, p1, p2]")
+        weight = weight.to(device=dev, dtype=torch.float64).contiguous()
     with torch.cuda.device(dev):
-        rc = _lib.lib.values_stitch_accumulate(
+        rc = _lib.lib.values_stitch_accumulate_weighted(
             patches.data_ptr(), _lib.dtype_code(patches.dtype), patches.stride()[0],
-            patches.stride()[1], _lib.ptr(patch_index), crop_lo.data_ptr(), n_sel, N, Cn,
+            patches.stride()[1], _lib.ptr(patch_index), crop_lo.data_ptr(), _lib.ptr(weight), n_sel, N, Cn,
             _lib.i64x3(patches.shape[3:]), _lib.i64x3(out_sum.shape[2:]), out_sum.data_ptr(),
             _lib.dtype_code(out_sum.dtype), _lib.ptr(out_count), int(accumulate),
             _lib.stream_ptr(dev))
     _lib.check(rc)
 
 
+def gaussian_importance_map(patch_shape: Sequence[int], sigma_scale: float = 0.125,
+                            device=None) -> torch.Tensor:
+    """Separable Gaussian patch weight, centre 1, sigma = sigma_scale * extent per axis, zeros
+    lifted to the smallest positive weight (the usual sliding-window-inference importance map).
+    The reference accumulates with UNIFORM weights; this is the opt-in
+    Gaussian-weighted variant BASELINE.json's north_star names.  fp64 [p0, p1, p2]."""
+    axes = []
+    for n in patch_shape:
+        c = (n - 1) / 2.0
+        x = torch.arange(n, dtype=torch.float64)
+        axes.append(torch.exp(-0.5 * ((x - c) / (sigma_scale * n)) ** 2))
+    w = axes[0][:, None, None] * axes[1][None, :, None] * axes[2][None, None, :]
+    w = w / w.max()
+    w = torch.clamp(w, min=float(w[w > 0].min()))
+    return w.to(device) if device is not None else w
+
+
 def stitch_volume(patches: torch.Tensor, crops, vol_shape: Sequence[int],
-                  out_dtype: torch.dtype = torch.float64) -> Tuple[torch.Tensor, torch.Tensor]:
+                  out_dtype: torch.dtype = torch.float64,
+                  weight: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All patches of one volume at once: patches [N, P, C, p,p,p] + P crops ->
     (raw sum [N, C, X, Y, Z], count fp64 [X, Y, Z]); every output voxel is written exactly
-    once (uncovered voxels are 0, as in the reference)."""
+    once (uncovered voxels are 0, as in the reference).  With `weight` [p,p,p] the sum is
+    weighted and `count` is the sum of weights (divide to normalise)."""
     dev = patches.device
     crop_lo = crops if isinstance(crops, torch.Tensor) else crops_to_lo(crops, dev)
     N, _, Cn = patches.shape[:3]
     out = torch.empty((N, Cn) + tuple(vol_shape), dtype=out_dtype, device=dev)
     cnt = torch.empty(tuple(vol_shape), dtype=torch.float64, device=dev)
-    stitch_accumulate(patches, crop_lo, out, cnt, accumulate=False)
+    stitch_accumulate(patches, crop_lo, out, cnt, accumulate=False, weight=weight)
     return out, cnt
