@@ -351,6 +351,9 @@ def main():
                 "kernel": "k1 fused N x C reduction (k1_tma_kernel)",
                 "algorithmic_bytes_per_voxel": bpv, "avg_launch_ms": k1_avg_ms,
                 "launches_timed": len(k1_ms), "k1_share_of_step": sum(k1_ms) / elapsed_ms,
+                # the whole step (K1 + K2b + score assembly) against the same roofline: algorithmic
+                # bytes of the fused pipeline (V * (N*C*s + 13)) over the step time
+                "pipeline_frac": (bpv * V * pool * args.steps) / (elapsed_ms * 1e-3) / 1e9 / peak,
                 "peak_source": peak_src}
 
     # end to end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -373,6 +376,7 @@ def main():
             "config": {"workload": wl["name"], "volumes_per_rank_per_step": pool,
                        "pool_bytes_per_rank": pool_bytes,
                        "l2": "inputs (pool >> 126 MB L2) stream from HBM every step",
+                       "map_chunk_bytes": cfg.chunk_bytes,
                        "aggregations": "image_level + threshold(0.98-quantile pilot) + patch_level(10)",
                        "sharding": f"volumes sharded over {world} rank(s), score table all_gather"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(), "e2e": e2e,

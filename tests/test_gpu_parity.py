@@ -286,6 +286,23 @@ def test_c3_batched_and_isclose_rule(vb, vo, patch_path):
     assert bbox[3].tolist() == [0, 0, 0] and score[3].item() == 0.0
 
 
+@pytest.mark.parametrize("shape", [(37, 50, 70), (128, 64, 96), (75, 128, 128)])
+def test_c3_workspace_garbage_is_harmless(vb, vo, shape, patch_path):
+    """Every workspace entry the finish pass reads must have been written by this call: a workspace
+    full of +inf / NaN bit patterns (what a reused scratch buffer may hold) must not leak into the
+    scores -- z-chunks whose last sub-chunk is short are the case that once did."""
+    rng = np.random.default_rng(shape[0])
+    maps = torch.from_numpy(rng.random((5,) + shape).astype(np.float32)).cuda()
+    ws_bytes = vb.aggregation.patch_max_workspace_bytes(5, shape, 10)
+    for fill in (0x7f, 0xff):
+        ws = torch.full((ws_bytes + 64,), fill, dtype=torch.uint8, device="cuda")
+        score, bbox = vb.patch_max(maps, 10, workspace=ws)
+        for i in range(5):
+            r = vo.patch_level_aggregation(maps[i].cpu().numpy(), 10)
+            np.testing.assert_allclose(score[i].item(), r["max_score"], rtol=1e-12)
+            assert bbox[i].tolist() == [b[0] for b in r["bounding_box"]]
+
+
 def test_c3_errors(vb):
     img = np.ones((8, 8))
     with pytest.raises(ValueError):

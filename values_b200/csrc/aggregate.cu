@@ -272,10 +272,11 @@ struct FusedParams {
     int tiles_x, tiles_y, chunks_z, zc;
     int zsub, zc_fine;            // pass 2 splits a pass-1 z-chunk into zsub pieces of zc_fine planes
     int64_t ntiles;
+    int64_t nent;                 // tile_max entries per map: ntiles (fused) or ntiles * zsub (march)
     double denom;
     int mean_flag;
     double rtol, atol;
-    double* tile_max;             // [M, ntiles]
+    double* tile_max;             // [M, nent]
     double* gmax;                 // [M]   written by the last pass-1 CTA of a map
     int* active;                  // [M, 1 + kMaxActive]: count (or -1 = walk every tile), tiles
     unsigned long long* best;     // [M]
@@ -295,7 +296,7 @@ template <int N> __device__ __forceinline__ double tree_sum(const double* v) {
 // Shared tail of the fused / march kernels.  PASS 1: tile maximum -> tile_max; the last CTA of a
 // map reduces them to the map maximum and lists the tiles np.isclose to it.  PASS 2: minimum
 // C-order index -> best (atomicMin, order-free); the last CTA publishes the bounding-box corner.
-template <int PASS, int NT = kFusedThreads>
+template <int PASS, int NT = kFusedThreads, bool FINE = false>
 __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t m, double tmax,
                                                 unsigned long long tbest, double* red, int& s_flag,
                                                 int& s_count) {
@@ -307,9 +308,11 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
         if (lane == 0) red[warp] = tmax;
         __syncthreads();
         if (tid == 0) {
-            double mm = red[0];
-            for (int w = 1; w < NT / 32; ++w) mm = nanmax(mm, red[w]);
-            prm.tile_max[m * prm.ntiles + blockIdx.x] = mm;
+            if (!FINE) {   // FINE: the march already stored one maximum per z sub-chunk
+                double mm = red[0];
+                for (int w = 1; w < NT / 32; ++w) mm = nanmax(mm, red[w]);
+                prm.tile_max[m * prm.nent + blockIdx.x] = mm;
+            }
             __threadfence();
             s_flag = atomicAdd(prm.tickets + 2 * m, 1u) == gridDim.x - 1;
             s_count = 0;
@@ -318,9 +321,9 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
         if (!s_flag) return;
         // last CTA of this map: map maximum (NaN propagates, as np.max) and the pass-2 work list
         __threadfence();
-        const double* tm = prm.tile_max + m * prm.ntiles;
+        const double* tm = prm.tile_max + m * prm.nent;
         double mm = ninf;
-        for (int64_t i = tid; i < prm.ntiles; i += NT) mm = nanmax(mm, __ldcg(tm + i));
+        for (int64_t i = tid; i < prm.nent; i += NT) mm = nanmax(mm, __ldcg(tm + i));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mm = nanmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
         if (lane == 0) red[warp] = mm;
@@ -328,7 +331,7 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
         double g = red[0];
         for (int w = 1; w < NT / 32; ++w) g = nanmax(g, red[w]);
         int* lst = prm.active + m * (1 + kMaxActive);
-        for (int64_t i = tid; i < prm.ntiles; i += NT) {   // list order is irrelevant (min index wins)
+        for (int64_t i = tid; i < prm.nent; i += NT) {   // list order is irrelevant (min index wins)
             if (np_isclose(__ldcg(tm + i), g, prm.rtol, prm.atol)) {
                 const int n = atomicAdd(&s_count, 1);
                 if (n < kMaxActive) lst[1 + n] = (int)i;
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const Fused
     const int tid = threadIdx.x;
     const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
     const int tiles_xy = prm.tiles_x * prm.tiles_y;
-    const int zsub = PASS == 2 ? prm.zsub : 1;
+    const int zsub = prm.zsub;
     const int zc_fine = PASS == 2 ? prm.zc_fine : prm.zc;
     double gmax = 0.0;
     unsigned long long tbest = ~0ull;
@@ -602,7 +605,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const Fused
         gmax = prm.gmax[m];
         list = prm.active + m * (1 + kMaxActive);
         const int n_act = list[0];
-        n_work = (n_act < 0 ? (int)prm.ntiles : n_act) * zsub;
+        n_work = n_act < 0 ? (int)prm.nent : n_act;    // entries are (tile, z sub-chunk) pairs
         work = blockIdx.x; work_step = gridDim.x;
     }
     // z-slide ownership: column cx of the input tile, rows g, g + G, ...
@@ -616,7 +619,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const Fused
     for (; work < n_work; work += work_step) {
         int tile, fine;
         if (PASS == 1) { tile = blockIdx.x; fine = 0; }
-        else { const int a = work / zsub; fine = work - a * zsub; tile = list[0] < 0 ? a : list[1 + a]; }
+        else { const int id = list[0] < 0 ? work : list[1 + work]; tile = id / zsub; fine = id - tile * zsub; }
         const int tx_i = tile % prm.tiles_x;
         const int ty_i = (tile / prm.tiles_x) % prm.tiles_y;
         const int zc_i = tile / tiles_xy;
@@ -712,6 +715,23 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const Fused
                     for (int k = 0; k < MT::RUN; ++k)
                         if ((valid >> k) & 1u) { tmax = fmax(tmax, o[k]); saw_nan |= o[k] != o[k]; }
                 }
+                // one maximum per z sub-chunk of prm.zc_fine output planes: pass 2 re-walks only the
+                // sub-chunks np.isclose to the map maximum, not the whole z-chunk of the tile
+                const int done = zi - (p0 - 1) + 1;              // output planes finished in this tile
+                if (done % prm.zc_fine == 0 || zi + 1 == nplanes) {
+                    if (saw_nan) tmax = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) tmax = nanmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
+                    __syncthreads();                             // red[] free (previous sub-chunk was read)
+                    if ((tid & 31) == 0) red[tid >> 5] = tmax;
+                    __syncthreads();
+                    if (tid == 0) {
+                        double mm = red[0];
+                        for (int w = 1; w < NT / 32; ++w) mm = nanmax(mm, red[w]);
+                        prm.tile_max[m * prm.nent + (int64_t)tile * zsub + (done - 1) / prm.zc_fine] = mm;
+                    }
+                    tmax = ninf; saw_nan = false;
+                }
             } else {
                 const int64_t oz = zo0 + zi - (p0 - 1);
 #pragma unroll
@@ -724,9 +744,12 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const Fused
                 }
             }
         }
+        if (PASS == 1 && tid == 0) {   // sub-chunks past the end of a short last z-chunk hold nothing
+            const int written = (int)((zo1 - zo0 + prm.zc_fine - 1) / prm.zc_fine);
+            for (int f = written; f < zsub; ++f) prm.tile_max[m * prm.nent + (int64_t)tile * zsub + f] = ninf;
+        }
     }
-    if (saw_nan) tmax = __longlong_as_double(0x7ff8000000000000LL);   // np.max: NaN propagates
-    box_pass_finish<PASS>(prm, m, tmax, tbest, red, s_flag, s_count);
+    box_pass_finish<PASS, kFusedThreads, true>(prm, m, tmax, tbest, red, s_flag, s_count);
 }
 
 // ------------------------------------------------------------------ K2b fast path (p2 <= 32)
@@ -1065,7 +1088,7 @@ static int run_patch_fused_pc(FusedParams prm, const FusedPlan& pl, int64_t M, c
         const int64_t mc = std::min<int64_t>(65535, M - m0);
         FusedParams q = prm;
         q.maps = reinterpret_cast<const T*>(prm.maps) + m0 * prm.stride_m;
-        q.tile_max = prm.tile_max + m0 * pl.ntiles;
+        q.tile_max = prm.tile_max + m0 * prm.nent;
         q.best = prm.best + m0;
         q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
         q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
@@ -1096,7 +1119,7 @@ static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
         const int64_t mc = std::min<int64_t>(65535, M - m0);
         FusedParams q = prm;
         q.maps = reinterpret_cast<const T*>(prm.maps) + m0 * prm.stride_m;
-        q.tile_max = prm.tile_max + m0 * pl.ntiles;
+        q.tile_max = prm.tile_max + m0 * prm.nent;
         q.best = prm.best + m0;
         q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
         q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
@@ -1106,7 +1129,8 @@ static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
         k1<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kFusedThreads, smem, st>>>(q);
         int rc = check_launch("box_march_kernel<1>");
         if (rc) return rc;
-        const unsigned g2 = (unsigned)std::min<int64_t>(pl.ntiles * pl.zsub, 4 * pl.zsub);
+        // pass 2: the work list normally holds one or two (tile, z sub-chunk) entries per map
+        const unsigned g2 = (unsigned)std::min<int64_t>(prm.nent, mc >= 16 ? 8 : 32);
         k2<<<dim3(g2, (unsigned)mc), kFusedThreads, smem, st>>>(q);
         if ((rc = check_launch("box_march_kernel<2>"))) return rc;
     }
@@ -1120,8 +1144,9 @@ static int run_patch_fused(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
 }
 
 // tile_max [M, ntiles] | gmax [M] | best [M] | tickets [M, 2] (one 8-byte slot) | active [M, 1 + kMaxActive] ints
+static int64_t fused_entries(const FusedPlan& pl) { return pl.march ? pl.ntiles * pl.zsub : pl.ntiles; }
 static size_t fused_workspace_bytes(int64_t M, const FusedPlan& pl) {
-    return (size_t)(M * pl.ntiles + 3 * M) * sizeof(double) + (size_t)M * (1 + kMaxActive) * sizeof(int);
+    return (size_t)(M * fused_entries(pl) + 3 * M) * sizeof(double) + (size_t)M * (1 + kMaxActive) * sizeof(int);
 }
 
 }  // namespace vb
@@ -1243,12 +1268,13 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
             prm.p0 = (int)patch3_host[0]; prm.p1 = (int)patch3_host[1]; prm.p2 = (int)patch3_host[2];
             prm.tiles_x = fp.tiles_x; prm.tiles_y = fp.tiles_y; prm.chunks_z = fp.chunks_z; prm.zc = fp.zc;
             prm.zsub = fp.zsub; prm.zc_fine = fp.zc_fine; prm.ntiles = fp.ntiles;
+            prm.nent = fused_entries(fp);
             prm.denom = denom; prm.mean_flag = mean_flag ? 1 : 0; prm.rtol = rtol; prm.atol = atol;
             prm.tile_max = ws;
-            prm.gmax = ws + M * fp.ntiles;
-            prm.best = reinterpret_cast<unsigned long long*>(ws + M * fp.ntiles + M);
-            prm.tickets = reinterpret_cast<unsigned int*>(ws + M * fp.ntiles + 2 * M);
-            prm.active = reinterpret_cast<int*>(ws + M * fp.ntiles + 3 * M);
+            prm.gmax = ws + M * prm.nent;
+            prm.best = reinterpret_cast<unsigned long long*>(ws + M * prm.nent + M);
+            prm.tickets = reinterpret_cast<unsigned int*>(ws + M * prm.nent + 2 * M);
+            prm.active = reinterpret_cast<int*>(ws + M * prm.nent + 3 * M);
             prm.max_score = max_score; prm.bbox_lo = bbox_lo;
             if (fp.march) {
                 if (dtype == VALUES_F32) return run_patch_march<float>(prm, fp, M, st);

@@ -234,6 +234,24 @@ struct CalibAcc {
             for (int k = 0; k < kCalibSlots; ++k) psum[k] += (k == slot) ? p : 0.0;
         }
     }
+    // the same for a voxel that stands for n_live (rater, voxel) pairs, n_true of them correct:
+    // confidence and slot depend on the voxel only, so the 21-way predicated add runs once per voxel
+    __device__ __forceinline__ void add_n(bool live, int slot, double p, unsigned n_live, unsigned n_true,
+                                          unsigned int* s_cnt, unsigned int* s_true) {
+        live = live && slot >= 0 && n_live > 0;
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const unsigned peers = __match_any_sync(active, (unsigned)slot);
+            const unsigned tot = __reduce_add_sync(peers, n_live), tru = __reduce_add_sync(peers, n_true);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+                atomicAdd(&s_cnt[slot], tot);
+                if (tru) atomicAdd(&s_true[slot], tru);
+            }
+            const double pn = p * (double)n_live;
+#pragma unroll
+            for (int k = 0; k < kCalibSlots; ++k) psum[k] += (k == slot) ? pn : 0.0;
+        }
+    }
 };
 
 // partials [blocks, 3 * 21] = { count, sum p, sum true } per slot
@@ -322,15 +340,16 @@ __global__ void __launch_bounds__(kThreads) calib_fused_kernel(const T* __restri
             slot = calib_slot(p, ed);
             pl = ld_elem(pred + v);
         }
-        for (int64_t r = 0; r < R; ++r) {
-            bool live = inside, t = false;
-            if (inside) {
+        unsigned n_live = 0, n_true = 0;
+        if (inside) {
+            for (int64_t r = 0; r < R; ++r) {
                 const TL rl = ld_elem(refs + r * V + v);
-                if (has_ignore && (long long)rl == ignore_value) live = false;
-                t = rl == pl;
+                const bool live = !(has_ignore && (long long)rl == ignore_value);
+                n_live += live ? 1u : 0u;
+                n_true += (live && rl == pl) ? 1u : 0u;
             }
-            acc.add(live, slot, p, t, s_cnt, s_true);
         }
+        acc.add_n(inside, slot, p, n_live, n_true, s_cnt, s_true);
     }
     __syncthreads();
     calib_flush(acc, s_cnt, s_true, red, partials);
