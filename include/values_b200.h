@@ -208,6 +208,17 @@ int values_calib_bins_fused(const void* unc, int dtype, const void* pred_seg, co
                             int n_bins, double* out, void* workspace, size_t workspace_bytes,
                             void* stream);
 
+/* Pairwise confusion matrices of label maps: the integer statistics behind calculate_ged and the
+ * torchmetrics `dice` calls around it (uncertainty_modeling/test_3D.py:284-358; per-sample arg-max
+ * maps come from values_uncertainty_fused's sample_argmax output).
+ *   labels_a [Na, V] (stride_a, 1), labels_b [Nb, V] (stride_b, 1), one label dtype (U8/I32/I64)
+ *   out uint64 [Na, Nb, C, C] (device, ACCUMULATES, caller zeroes):
+ *       out[ia, ib, a, b] += #{ v : A[ia, v] == a and B[ib, v] == b };  labels outside [0, C) are dropped.
+ *   n_classes <= 32.  Exact (integer atomics, order-free). */
+int values_confusion_counts(const void* labels_a, int64_t Na, int64_t stride_a, const void* labels_b,
+                            int64_t Nb, int64_t stride_b, int label_dtype, int64_t V, int n_classes,
+                            unsigned long long* out, void* stream);
+
 /* Tuning hooks for benchmarks and tests (process-wide; 0 restores the automatic choice):
  * voxel tiles per CTA of the K1 stream kernel, and its batch / occupancy variant. */
 void values_debug_set_k1_iter(int iter);

@@ -252,3 +252,41 @@ def test_calib_fused_vs_oracle_large(vb, vo, dtype, ldt):
         np.testing.assert_allclose(vb.calibration_error_image(unc, pred, refs, 4.0, -1.0, ignore),
                                    vo.calibration_error_image(unc, pred, refs, 4.0, -1.0, ignore),
                                    rtol=1e-12 if dtype == np.float64 else 1e-5)
+
+
+# ------------------------------------------------------------------ f2: confusion counts / Dice / GED
+@pytest.mark.parametrize("ldt", [torch.uint8, torch.int32, torch.int64])
+def test_confusion_counts_exact(vb, ldt):
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 5, size=(3, 37, 41, 29))
+    b = rng.integers(0, 6, size=(2, 37, 41, 29))      # label 5 >= C is dropped
+    got = vb.confusion_counts(torch.from_numpy(a).to(ldt).cuda(), torch.from_numpy(b).to(ldt).cuda(), 5).cpu().numpy()
+    for i in range(3):
+        for j in range(2):
+            want = np.zeros((5, 5), dtype=np.int64)
+            ok = b[j] < 5
+            np.add.at(want, (a[i][ok], b[j][ok]), 1)
+            np.testing.assert_array_equal(got[i, j], want)
+
+
+@pytest.mark.parametrize("n,c,r,shape,ignore", [(5, 2, 4, (40, 36, 32), 0), (10, 4, 3, (48, 64), 0),
+                                                 (3, 3, 1, (20, 20, 20), 0), (4, 3, 2, (24, 24, 24), 1)])
+def test_ged_vs_oracle(vb, vo, n, c, r, shape, ignore):
+    """calculate_ged against the numpy restatement (parity unpinned upstream: torchmetrics absent)."""
+    g = torch.Generator().manual_seed(n * 10 + c)
+    base = 2.0 * torch.randn(1, c, *shape, generator=g)
+    sm = torch.softmax(base + torch.randn(n, c, *shape, generator=g), dim=1)
+    lab = torch.argmax(base[0], dim=0)
+    gt = torch.stack([torch.where(torch.rand(shape, generator=g) < 0.9, lab, (lab + 1) % c) for _ in range(r)])
+    if ignore == 1:
+        gt[gt == 0] = 2          # no voxel carries label `ignore`... keep 1s: exercises both gt-gt branches
+    got = vb.calculate_ged(sm.cuda(), gt.cuda(), ignore_index=ignore)
+    want = vo.calculate_ged(sm.numpy(), gt.numpy(), ignore_index=ignore)
+    assert set(got) == set(want)
+    for k in want:
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-12, atol=1e-15, err_msg=k)
+    assert set(vb.calculate_ged(sm.cuda(), gt.cuda(), ignore_index=ignore, ged_only=True)) == {"ged"}
+    # identical predictions and raters: every distance is 0
+    one = torch.nn.functional.one_hot(lab, c).movedim(-1, 0).float().unsqueeze(0).repeat(3, *([1] * (lab.dim() + 1)))
+    z = vb.calculate_ged(one.cuda(), lab.unsqueeze(0).repeat(2, *([1] * lab.dim())).cuda())
+    assert abs(z["ged"]) < 1e-15 and z["max dice pred"] == 1.0

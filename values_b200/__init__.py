@@ -9,11 +9,12 @@ from . import _lib  # noqa: F401  (raises ValuesExtensionMissing when the .so is
 from .aggregation import (aggregate_uncertainties, image_level_aggregation, map_reduce,
                           normalize_maps, patch_level_aggregation, patch_max,
                           threshold_aggregation)
-from . import metrics, threshold
+from . import metrics, segmetrics, threshold
 from .data_carrier import DataCarrier3D
 from .metrics import (calc_ace, calib_stats, calibration_error, calibration_error_image,
                       compute_ncc, ncc_batched, ncc_main, platt_scale_confid)
 from .pipeline import AggregationConfig, PipelineResult, UncertaintyPipeline
+from .segmetrics import calculate_ged, confusion_counts, dice_from_confusion, mean_prediction_dice
 from .sharding import gather_scores, shard_range, shard_sizes
 from .stitching import gaussian_importance_map, patch_grid, stitch_accumulate, stitch_volume
 from .threshold import (calculate_foreground_quantile_image, calculate_threshold_image,
@@ -35,4 +36,5 @@ __all__ = [
     "calculate_threshold_image", "find_threshold", "quantile", "count_nonzero",
     "compute_ncc", "ncc_batched", "ncc_main", "calib_stats", "calc_ace", "platt_scale_confid",
     "calibration_error_image", "calibration_error",
+    "calculate_ged", "confusion_counts", "dice_from_confusion", "mean_prediction_dice",
 ]

@@ -365,6 +365,46 @@ __global__ void calib_reduce_kernel(const double* __restrict__ partials, int64_t
     out[k] = s;
 }
 
+// =============================================================================== confusion counts
+// out[(ia * Nb + ib) * C * C + a * C + b] += #{ v : A[ia, v] == a and B[ib, v] == b }   (labels >= C or
+// < 0 are dropped).  Every pair statistic of calculate_ged / torchmetrics' dice (test_3D.py:284-358) is a
+// function of these integer matrices.  Block-private shared histogram, warp-aggregated atomics: exact.
+constexpr int kMaxConfClasses = 32;
+
+template <typename TL>
+__global__ void __launch_bounds__(kThreads) confusion_kernel(const TL* __restrict__ A, int64_t stride_a,
+                                                             const TL* __restrict__ B, int64_t stride_b,
+                                                             int64_t Nb, int64_t V, int C, int64_t bpp,
+                                                             unsigned long long* __restrict__ out) {
+    __shared__ unsigned int sh[kMaxConfClasses * kMaxConfClasses];
+    const int64_t pair = blockIdx.x / bpp, blk = blockIdx.x - pair * bpp;
+    const int64_t ia = pair / Nb, ib = pair - ia * Nb;
+    const int cc = C * C;
+    for (int i = threadIdx.x; i < cc; i += kThreads) sh[i] = 0;
+    __syncthreads();
+    const TL* pa = A + ia * stride_a;
+    const TL* pb = B + ib * stride_b;
+    const int lane = threadIdx.x & 31;
+    const int64_t base = blk * (int64_t)(kThreads * kStatEPT) + threadIdx.x;
+    for (int i = 0; i < kStatEPT; ++i) {
+        const int64_t v = base + (int64_t)i * kThreads;
+        bool live = v < V;
+        long long a = 0, b = 0;
+        if (live) { a = (long long)ld_elem(pa + v); b = (long long)ld_elem(pb + v); }
+        live = live && a >= 0 && a < C && b >= 0 && b < C;
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const unsigned code = (unsigned)(a * C + b);
+            const unsigned peers = __match_any_sync(active, code);
+            if (lane == __ffs(peers) - 1) atomicAdd(&sh[code], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    unsigned long long* dst = out + pair * cc;
+    for (int i = threadIdx.x; i < cc; i += kThreads)
+        if (sh[i]) atomicAdd(dst + i, (unsigned long long)sh[i]);
+}
+
 static int stat_grid(int64_t n_units) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -565,4 +605,32 @@ extern "C" int values_calib_bins_fused(const void* unc, int dtype, const void* p
     else return set_error(VALUES_ERR_INVALID_ARG, "calib_bins_fused: map f32/f64, labels u8/i32/i64");
 #undef VB_CALIBF
     return calib_finish(partials, blocks, out, st);
+}
+
+extern "C" int values_confusion_counts(const void* labels_a, int64_t Na, int64_t stride_a,
+                                       const void* labels_b, int64_t Nb, int64_t stride_b,
+                                       int label_dtype, int64_t V, int n_classes,
+                                       unsigned long long* out, void* stream) {
+    if (Na < 0 || Nb < 0 || V < 0 || n_classes < 1 || n_classes > kMaxConfClasses)
+        return set_error(VALUES_ERR_INVALID_ARG, "confusion_counts: bad sizes (1 <= n_classes <= %d)", kMaxConfClasses);
+    if (!out) return set_error(VALUES_ERR_INVALID_ARG, "confusion_counts: NULL output");
+    if (Na == 0 || Nb == 0 || V == 0) return VALUES_OK;
+    if (!labels_a || !labels_b) return set_error(VALUES_ERR_INVALID_ARG, "confusion_counts: NULL input");
+    const int64_t bpp = ceil_div(V, kThreads * kStatEPT);
+    if (bpp * Na * Nb > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "confusion_counts: grid too large");
+    const unsigned grid = (unsigned)(bpp * Na * Nb);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (label_dtype) {
+        case VALUES_U8:
+            confusion_kernel<uint8_t><<<grid, kThreads, 0, st>>>((const uint8_t*)labels_a, stride_a, (const uint8_t*)labels_b, stride_b, Nb, V, n_classes, bpp, out);
+            break;
+        case VALUES_I32:
+            confusion_kernel<int32_t><<<grid, kThreads, 0, st>>>((const int32_t*)labels_a, stride_a, (const int32_t*)labels_b, stride_b, Nb, V, n_classes, bpp, out);
+            break;
+        case VALUES_I64:
+            confusion_kernel<int64_t><<<grid, kThreads, 0, st>>>((const int64_t*)labels_a, stride_a, (const int64_t*)labels_b, stride_b, Nb, V, n_classes, bpp, out);
+            break;
+        default: return set_error(VALUES_ERR_INVALID_ARG, "confusion_counts: labels must be u8, i32 or i64");
+    }
+    return check_launch("confusion_kernel");
 }

@@ -8,13 +8,14 @@ from __future__ import annotations
 import importlib
 import sys
 
-from . import aggregation, data_carrier, metrics, threshold, uncertainty
+from . import aggregation, data_carrier, metrics, segmetrics, threshold, uncertainty
 
 _PATCHES = {
     "uncertainty_modeling.test_3D": {
         "calculate_uncertainty": uncertainty.calculate_uncertainty,
         "calculate_one_minus_msr": uncertainty.calculate_one_minus_msr,
         "caculcate_uncertainty_multiple_pred": uncertainty.caculcate_uncertainty_multiple_pred,
+        "calculate_ged": segmetrics.calculate_ged,
         "DataCarrier3D": data_carrier.DataCarrier3D,
     },
     "uncertainty_modeling.test_2D": {
