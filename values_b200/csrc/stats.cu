@@ -355,14 +355,17 @@ __global__ void __launch_bounds__(kThreads) calib_fused_kernel(const T* __restri
     calib_flush(acc, s_cnt, s_true, red, partials);
 }
 
-// partials [n_blocks, K] -> out [K]  (K = 63): thread k sums column k in block order
-__global__ void calib_reduce_kernel(const double* __restrict__ partials, int64_t n_blocks, int K,
-                                    double* __restrict__ out) {
-    const int k = threadIdx.x;
-    if (k >= K) return;
-    double s = 0.0;
-    for (int64_t r = 0; r < n_blocks; ++r) s += partials[r * K + k];
-    out[k] = s;
+// partials [n_blocks, K] -> out [K]  (K = 63): block k sums column k, rows striped over the threads,
+// then a fixed-order block reduction (deterministic)
+__global__ void __launch_bounds__(kThreads) calib_reduce_kernel(const double* __restrict__ partials,
+                                                                int64_t n_blocks, int K,
+                                                                double* __restrict__ out) {
+    __shared__ double red[8];
+    const int k = blockIdx.x;
+    double acc[1] = {0.0};
+    for (int64_t r = threadIdx.x; r < n_blocks; r += kThreads) acc[0] += partials[r * K + k];
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) out[k] = acc[0];
 }
 
 // =============================================================================== confusion counts
@@ -537,7 +540,7 @@ static int calib_edges(const double* edges_host, int n_bins, CalibEdges& ed) {
 static int calib_finish(double* partials, int64_t blocks, double* out, cudaStream_t st) {
     int rc = check_launch("calib kernel");
     if (rc) return rc;
-    calib_reduce_kernel<<<1, 64, 0, st>>>(partials, blocks, 3 * kCalibSlots, out);
+    calib_reduce_kernel<<<3 * kCalibSlots, kThreads, 0, st>>>(partials, blocks, 3 * kCalibSlots, out);
     return check_launch("calib_reduce_kernel");
 }
 
