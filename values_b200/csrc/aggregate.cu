@@ -575,6 +575,7 @@ template <int TY, int TX, int PC> struct MarchTile {
     static constexpr int RUN = TY * TX / NT;                   // y-pass: consecutive rows per thread
     static constexpr size_t smem = (size_t)(R * pitchA + R * pitchB) * sizeof(double);
     static_assert(G >= 1 && TX % SEG == 0 && RUN * (NT / TX) == TY && R * NSEG <= NT, "tile shape");
+    static_assert(SEG % 2 == 0 && RUN % 2 == 0 && RUN / 2 <= PC && SEG / 2 <= PC, "two chains per task");
     static_assert((NSLOT - 1) * G <= R, "only the last slot of a thread can fall outside the tile");
 };
 
@@ -671,36 +672,40 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const Fused
                 if (last_in) a[(MT::NSLOT - 1) * MT::G * MT::pitchA] = zs[MT::NSLOT - 1];
             }
             __syncthreads();
-            // ---- x-pass: 16 sliding outputs per task, window kept in registers
+            // ---- x-pass: 16 outputs per task as two independent sliding chains of 8 (the sliding sum
+            // is a dependent fp64 chain; halving it is worth the second tree sum and the re-loads)
             if (tid < MT::R * MT::NSEG) {
                 const double* row = A + task_r * MT::pitchA + task_seg * MT::SEG;
                 double* dst = Bs + task_r * MT::pitchB + task_seg * MT::SEG;
-                double v[PC];
+                constexpr int H = MT::SEG / 2;
+                double va[PC], vb2[PC];
 #pragma unroll
-                for (int k = 0; k < PC; ++k) v[k] = row[k];
-                double s = tree_sum<PC>(v);
-                dst[0] = s;
+                for (int k = 0; k < PC; ++k) { va[k] = row[k]; vb2[k] = row[H + k]; }
+                double sa = tree_sum<PC>(va), sb = tree_sum<PC>(vb2);
+                dst[0] = sa; dst[H] = sb;
 #pragma unroll
-                for (int i = 1; i < MT::SEG; ++i) {
-                    const double in = row[i + PC - 1];
-                    s += in - v[(i - 1) % PC];
-                    v[(i - 1) % PC] = in;
-                    dst[i] = s;
+                for (int i = 1; i < H; ++i) {
+                    const double ia = row[i + PC - 1], ib = row[H + i + PC - 1];
+                    sa += ia - va[(i - 1) % PC];
+                    sb += ib - vb2[(i - 1) % PC];
+                    dst[i] = sa; dst[H + i] = sb;
                 }
             }
             __syncthreads();
-            // ---- y-pass: RUN sliding outputs down one column
+            // ---- y-pass: RUN outputs down one column, again as two independent chains
             const double* cb = Bs + oy0 * MT::pitchB + ox;
-            double c[PC];
-#pragma unroll
-            for (int j = 0; j < PC; ++j) c[j] = cb[j * MT::pitchB];
             double o[MT::RUN];
-            o[0] = tree_sum<PC>(c);
+            {
+                constexpr int H = MT::RUN / 2;
+                double ca[PC], cb2[PC];
 #pragma unroll
-            for (int k = 1; k < MT::RUN; ++k) {
-                const double in = cb[(k + PC - 1) * MT::pitchB];
-                o[k] = o[k - 1] + (in - c[(k - 1) % PC]);
-                c[(k - 1) % PC] = in;
+                for (int j = 0; j < PC; ++j) { ca[j] = cb[j * MT::pitchB]; cb2[j] = cb[(H + j) * MT::pitchB]; }
+                o[0] = tree_sum<PC>(ca); o[H] = tree_sum<PC>(cb2);
+#pragma unroll
+                for (int k = 1; k < H; ++k) {
+                    o[k] = o[k - 1] + (cb[(k + PC - 1) * MT::pitchB] - ca[k - 1]);
+                    o[H + k] = o[H + k - 1] + (cb[(H + k + PC - 1) * MT::pitchB] - cb2[k - 1]);
+                }
             }
             if (prm.mean_flag) {
 #pragma unroll
