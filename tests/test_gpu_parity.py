@@ -34,10 +34,13 @@ def vo():
     return values_oracle
 
 
-@pytest.fixture(params=[0, 4, 1, 2], ids=["k2b-auto", "k2b-fused", "k2b-stream", "k2b-tiled"])
+@pytest.fixture(params=[0, 6, 5, 4, 1, 2],
+                ids=["k2b-auto", "k2b-march-scalar-filter", "k2b-march-nofilter", "k2b-fused", "k2b-stream",
+                     "k2b-tiled"])
 def patch_path(request, vb):
-    """Every K2b implementation (fused tile kernel, streaming two-kernel path, generic tiled
-    path) must give the same scores and the same bounding boxes."""
+    """Every K2b implementation (march kernel behind the vector fp32 filter kernel / behind its own
+    fp32 instantiation / alone, fused tile kernel, streaming two-kernel path, generic tiled path)
+    must give the same scores and the same bounding boxes."""
     vb._lib.lib.values_debug_set_patch_path(request.param)
     yield request.param
     vb._lib.lib.values_debug_set_patch_path(0)
@@ -284,6 +287,83 @@ def test_c3_batched_and_isclose_rule(vb, vo, patch_path):
         np.testing.assert_allclose(score[i].item(), r["max_score"], rtol=1e-12)
         assert bbox[i].tolist() == [b[0] for b in r["bounding_box"]]
     assert bbox[3].tolist() == [0, 0, 0] and score[3].item() == 0.0
+
+
+def _filter_cases():
+    """fp32 maps at march-kernel sizes that stress the fp32 filter pass (it may only ever DROP
+    sub-chunks that cannot hold a window np.isclose to the maximum)."""
+    rng = np.random.default_rng(2024)
+    shape = (60, 70, 140)
+    cases = {}
+    base = rng.random(shape).astype(np.float32)
+    cases["random"] = base
+    cases["constant"] = np.full(shape, 0.37, np.float32)          # every window ties: list overflows
+    cases["zeros"] = np.zeros(shape, np.float32)
+    m = np.zeros(shape, np.float32)
+    m[3:13, 5:15, 100:110] = 0.5
+    m[40:50, 50:60, 7:17] = 0.5 * (1 + 4e-6)                      # later in C order, 4e-6 larger: the
+    cases["near_tie_close"] = m                                   # first block is still isclose -> wins
+    m = m.copy()
+    m[40:50, 50:60, 7:17] = 0.5 * (1 + 5e-5)                      # 5e-5 larger: not isclose -> second wins
+    cases["near_tie_far"] = m
+    cases["signed"] = (base - 0.5).astype(np.float32)             # negative values (MI can dip below 0)
+    m = (base * 1e-3).astype(np.float32)
+    m[20, 30, 40] = 1e4                                           # one huge voxel: large error bound
+    cases["spike"] = m
+    cases["huge"] = (base * 1e36).astype(np.float32)              # fp32 box sums overflow -> exact pass
+    m = base.copy()
+    m[30:50, 20:40, 60:90] = 0.0                                  # sparse blobs, as real maps
+    m[m < 0.9] = 0.0
+    cases["sparse"] = m
+    cases["smooth"] = (np.add.outer(np.add.outer(np.hanning(60), np.hanning(70)), np.hanning(140)) / 3).astype(np.float32)
+    return cases
+
+
+@pytest.mark.parametrize("mean", [False, True])
+def test_c3_filter_pass_is_exact(vb, vo, mean):
+    """The fp32 filter + listed exact pass (path 0) must give the same boxes and scores as the exact
+    march over every tile (path 5) -- scores to fp64 rounding, because a listed sub-chunk restarts
+    its z-window sums -- and both must match the oracle."""
+    cases = _filter_cases()
+    names = list(cases)
+    maps = torch.from_numpy(np.stack([cases[k] for k in names])).cuda()
+    res = {}
+    for path in (0, 6, 5):
+        vb._lib.lib.values_debug_set_patch_path(path)
+        try:
+            s, b = vb.patch_max(maps, 10, mean=mean)
+            res[path] = (s.cpu().numpy(), b.cpu().numpy())
+        finally:
+            vb._lib.lib.values_debug_set_patch_path(0)
+    for path in (0, 6):
+        np.testing.assert_allclose(res[path][0], res[5][0], rtol=1e-13, atol=0)
+        assert np.array_equal(res[path][1], res[5][1])
+    for i, k in enumerate(names):
+        r = vo.patch_level_aggregation(cases[k], 10, mean=mean)
+        np.testing.assert_allclose(res[0][0][i], r["max_score"], rtol=1e-12, err_msg=k)
+        assert res[0][1][i].tolist() == [b[0] for b in r["bounding_box"]], k
+
+
+def test_c3_filter_pass_nonfinite(vb):
+    """NaN / inf voxels send the map through the exact pass: same result as without the filter."""
+    rng = np.random.default_rng(7)
+    maps = rng.random((4, 40, 64, 96)).astype(np.float32)
+    maps[1, 20, 30, 50] = np.nan
+    maps[2, 5, 6, 7] = np.inf
+    maps[3, 39, 63, 95] = -np.inf
+    t = torch.from_numpy(maps).cuda()
+    res = {}
+    for path in (0, 6, 5):
+        vb._lib.lib.values_debug_set_patch_path(path)
+        try:
+            s, b = vb.patch_max(t, 10)
+            res[path] = (s.cpu().numpy(), b.cpu().numpy())
+        finally:
+            vb._lib.lib.values_debug_set_patch_path(0)
+    for path in (0, 6):
+        np.testing.assert_allclose(res[path][0], res[5][0], rtol=1e-13, atol=0, equal_nan=True)
+        assert np.array_equal(res[path][1], res[5][1])
+    assert np.isnan(res[0][0][1]) and res[0][1][1].tolist() == [-1, -1, -1]
 
 
 @pytest.mark.parametrize("shape", [(37, 50, 70), (128, 64, 96), (75, 128, 128)])

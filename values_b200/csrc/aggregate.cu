@@ -280,7 +280,9 @@ struct FusedParams {
     double* gmax;                 // [M]   written by the last pass-1 CTA of a map
     int* active;                  // [M, 1 + kMaxActive]: count (or -1 = walk every tile), tiles
     unsigned long long* best;     // [M]
-    unsigned int* tickets;        // [M, 2]  pass-1 / pass-2 arrival counters
+    unsigned int* tickets;        // [M, 4]  filter / pass-1 / pass-2 arrival counters, max |input| bits
+    int use_list;                 // pass 1 walks only the (tile, z sub-chunk) entries the fp32 filter listed
+    double err_coef;              // fp32 filter: |fp32 box sum - true box sum| <= err_coef * max |input|
     double* max_score;            // [M]
     int64_t* bbox_lo;             // [M, 3]
 };
@@ -299,10 +301,59 @@ template <int N> __device__ __forceinline__ double tree_sum(const double* v) {
 template <int PASS, int NT = kFusedThreads, bool FINE = false>
 __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t m, double tmax,
                                                 unsigned long long tbest, double* red, int& s_flag,
-                                                int& s_count) {
+                                                int& s_count, float amax = 0.f) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
-    if constexpr (PASS == 1) {
+    if constexpr (PASS == 0) {
+        // fp32 filter pass (march kernel only): tile_max holds fp32 sub-chunk maxima of box SUMS.
+        // The last CTA of a map turns them into the pass-1 work list: every (tile, z sub-chunk)
+        // whose true maximum could still be np.isclose to the true map maximum, given
+        // |fp32 sum - true sum| <= E = err_coef * max |input|.  With g the fp32 map maximum the
+        // true maximum G lies in [g - E, g + E]; a sub-chunk with fp32 maximum t holds a window
+        // close to G only if t + E >= G - atol - rtol |G| >= g - E - atol - rtol (|g| + E).
+        // Entries not listed are reset to -inf, so the exact pass-1 finish ignores them.  Anything
+        // non-finite (NaN / inf inputs, fp32 overflow) or a list that overflows sends the whole
+        // map through the exact pass.
+        const unsigned int abits = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));  // amax >= +0
+        if (lane == 0) atomicMax(prm.tickets + 4 * m + 3, abits);
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_flag = atomicAdd(prm.tickets + 4 * m, 1u) == gridDim.x - 1;
+            s_count = 0;
+        }
+        __syncthreads();
+        if (!s_flag) return;
+        __threadfence();
+        double* tm = prm.tile_max + m * prm.nent;
+        double mm = ninf;
+        for (int64_t i = tid; i < prm.nent; i += NT) mm = nanmax(mm, __ldcg(tm + i));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mm = nanmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        if (lane == 0) red[warp] = mm;
+        __syncthreads();
+        double g = red[0];
+        for (int w = 1; w < NT / 32; ++w) g = nanmax(g, red[w]);
+        const double a = (double)__uint_as_float(atomicMax(prm.tickets + 4 * m + 3, 0u));  // atomic read
+        const double E = prm.err_coef * a;
+        const double atol_s = prm.mean_flag ? prm.atol * prm.denom : prm.atol;   // the filter compares sums
+        const double cut = g - 2.0 * E - atol_s - prm.rtol * (fabs(g) + E);
+        // false for NaN / inf inputs, and when an fp32 box sum could overflow
+        const bool finite = fabs(g) < 1e300 && a * ((double)prm.p0 * prm.p1 * prm.p2) < 1e37 && E < 1e300;
+        int* lst = prm.active + m * (1 + kMaxActive);
+        if (finite) {
+            for (int64_t i = tid; i < prm.nent; i += NT) {
+                if (__ldcg(tm + i) >= cut) {
+                    const int n = atomicAdd(&s_count, 1);
+                    if (n < kMaxActive) lst[1 + n] = (int)i;
+                } else {
+                    tm[i] = ninf;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) lst[0] = (!finite || s_count > kMaxActive) ? -1 : s_count;
+    } else if constexpr (PASS == 1) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tmax = nanmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
         if (lane == 0) red[warp] = tmax;
@@ -314,7 +365,7 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
                 prm.tile_max[m * prm.nent + blockIdx.x] = mm;
             }
             __threadfence();
-            s_flag = atomicAdd(prm.tickets + 2 * m, 1u) == gridDim.x - 1;
+            s_flag = atomicAdd(prm.tickets + 4 * m + 1, 1u) == gridDim.x - 1;
             s_count = 0;
         }
         __syncthreads();
@@ -355,7 +406,7 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            s_flag = atomicAdd(prm.tickets + 2 * m + 1, 1u) == gridDim.x - 1;
+            s_flag = atomicAdd(prm.tickets + 4 * m + 2, 1u) == gridDim.x - 1;
         }
         __syncthreads();
         if (s_flag && tid == 0) {
@@ -559,7 +610,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_fused_kernel(const Fused
 // plane sums.  That frees shared memory for 32 x 64 tiles (halo 1.28 x 1.14 instead of
 // 1.56 x 1.14), lets the x-pass produce 16 and the y-pass 8 outputs per task (25 resp. 17
 // shared loads), and makes the p0-1 warm-up planes of a z-chunk cost a register add instead of
-// a full plane of x/y passes.  Two block barriers per OUTPUT plane.
+// a full plane of x/y passes.  The three stages are software-pipelined over planes with
+// double-buffered shared memory: ONE block barrier per output plane.
 // Input rows / columns past the map edge are CLAMPED, not zero-filled: they only ever feed
 // windows that are not fully inside the map, and those outputs are masked -- so every load is
 // unconditional (uniform plane pointer + 32-bit per-thread offset).  Requires the in-plane patch
@@ -573,42 +625,68 @@ template <int TY, int TX, int PC> struct MarchTile {
     static constexpr int pitchA = W | 1, pitchB = TX + 1;      // odd pitches: rows striped over lanes
     static constexpr int SEG = 16, NSEG = TX / SEG;            // x-pass task = 16 outputs of one row
     static constexpr int RUN = TY * TX / NT;                   // y-pass: consecutive rows per thread
-    static constexpr size_t smem = (size_t)(R * pitchA + R * pitchB) * sizeof(double);
+    template <typename ACC> static constexpr size_t smem_bytes() {
+        return (size_t)2 * (R * pitchA + R * pitchB) * sizeof(ACC);   // double-buffered
+    }
     static_assert(G >= 1 && TX % SEG == 0 && RUN * (NT / TX) == TY && R * NSEG <= NT, "tile shape");
     static_assert(SEG % 2 == 0 && RUN % 2 == 0 && RUN / 2 <= PC && SEG / 2 <= PC, "two chains per task");
     static_assert((NSLOT - 1) * G <= R, "only the last slot of a thread can fall outside the tile");
 };
 
-template <typename T, int TY, int TX, int PC, int PASS>
-__global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const FusedParams prm) {
+template <int N, typename A> __device__ __forceinline__ A tree_sum_t(const A* v) {
+    if constexpr (N == 1) return v[0];
+    else return tree_sum_t<N / 2, A>(v) + tree_sum_t<N - N / 2, A>(v + N / 2);
+}
+__device__ __forceinline__ double acc_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float acc_max(float a, float b) { return fmaxf(a, b); }
+constexpr int tree_depth(int n) { return n <= 1 ? 0 : 1 + tree_depth(n - n / 2); }
+
+// PASS 0 (ACC = float, fp32 maps only): the FILTER.  The same march in fp32 -- half the shared
+// memory traffic and registers, no fp32->fp64 conversions, 4-cycle add chains -- over every tile,
+// storing one fp32 maximum of box sums per z sub-chunk and the largest |input|.  fp32 sliding sums
+// are not the answer (np.isclose decisions need fp64), but with a rigorous error bound they say
+// which sub-chunks can possibly hold the maximum or a window np.isclose to it (box_pass_finish<0>);
+// PASS 1 then computes the exact fp64 maxima of only those (prm.use_list), PASS 2 the first index.
+// Results are bit-identical to running PASS 1 over everything.
+template <typename T, typename ACC, int TY, int TX, int PC, int PASS, int MINB>
+__global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const FusedParams prm) {
     using MT = MarchTile<TY, TX, PC>;
     constexpr int NT = kFusedThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[NT / 32];
     __shared__ int s_flag;
     __shared__ int s_count;
-    double* A = reinterpret_cast<double*>(smem_raw);          // [R][pitchA] z-window sums
-    double* Bs = A + MT::R * MT::pitchA;                      // [R][pitchB] z-x sums
+    ACC* A = reinterpret_cast<ACC*>(smem_raw);                // [2][R][pitchA] z-window sums
+    ACC* Bs = A + 2 * MT::R * MT::pitchA;                     // [2][R][pitchB] z-x sums
     const int p0 = prm.p0;
     const int64_t m = blockIdx.y;
     const int tid = threadIdx.x;
     const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+    const ACC ninf_a = (ACC)ninf;
     const int tiles_xy = prm.tiles_x * prm.tiles_y;
     const int zsub = prm.zsub;
-    const int zc_fine = PASS == 2 ? prm.zc_fine : prm.zc;
     double gmax = 0.0;
     unsigned long long tbest = ~0ull;
-    double tmax = ninf;
+    ACC tmax = ninf_a;
+    float amax = 0.f;
     bool saw_nan = false;
     int n_work = 1, work = 0, work_step = 1;
-    const int* list = nullptr;
+    const int* list = prm.active + m * (1 + kMaxActive);
+    // listed: the work items are (tile, z sub-chunk) entries of the list (all entries if it
+    // overflowed) instead of this CTA's own whole tile
+    bool listed = false;
     if (PASS == 2) {
         gmax = prm.gmax[m];
-        list = prm.active + m * (1 + kMaxActive);
         const int n_act = list[0];
-        n_work = n_act < 0 ? (int)prm.nent : n_act;    // entries are (tile, z sub-chunk) pairs
+        n_work = n_act < 0 ? (int)prm.nent : n_act;
         work = blockIdx.x; work_step = gridDim.x;
+        listed = true;
+    } else if (PASS == 1 && prm.use_list && list[0] >= 0) {
+        n_work = list[0];
+        work = blockIdx.x; work_step = gridDim.x;
+        listed = true;
     }
+    const int zc_fine = listed ? prm.zc_fine : prm.zc;
     // z-slide ownership: column cx of the input tile, rows g, g + G, ...
     const int cx = min(tid % MT::CW, MT::W - 1), g = min(tid / MT::CW, MT::G - 1);
     const bool zstore = tid % MT::CW < MT::W && tid / MT::CW < MT::G;
@@ -619,7 +697,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const Fused
     const unsigned int D1 = (unsigned int)prm.D1, D2 = (unsigned int)prm.D2;
     for (; work < n_work; work += work_step) {
         int tile, fine;
-        if (PASS == 1) { tile = blockIdx.x; fine = 0; }
+        if (!listed) { tile = blockIdx.x; fine = 0; }
         else { const int id = list[0] < 0 ? work : list[1 + work]; tile = id / zsub; fine = id - tile * zsub; }
         const int tx_i = tile % prm.tiles_x;
         const int ty_i = (tile / prm.tiles_x) % prm.tiles_y;
@@ -635,10 +713,10 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const Fused
 #pragma unroll
         for (int i = 0; i < MT::NSLOT; ++i)
             off[i] = min(y0 + g + i * MT::G, D1 - 1) * D2 + min(x0 + cx, D2 - 1);
-        double zs[MT::NSLOT];
+        ACC zs[MT::NSLOT];
         T nw[MT::NSLOT], od[MT::NSLOT];
 #pragma unroll
-        for (int i = 0; i < MT::NSLOT; ++i) { zs[i] = 0.0; od[i] = (T)0; }
+        for (int i = 0; i < MT::NSLOT; ++i) { zs[i] = (ACC)0; od[i] = (T)0; }
         unsigned int valid = 0;   // bit k: output (oy0 + k, ox) lies inside the map
 #pragma unroll
         for (int k = 0; k < MT::RUN; ++k)
@@ -650,111 +728,122 @@ __global__ void __launch_bounds__(kFusedThreads, 2) box_march_kernel(const Fused
 #pragma unroll
             for (int i = 0; i < MT::NSLOT; ++i) nw[i] = In<T>::load_one(pn + off[i]);
         }
-        for (int zi = 0; zi < nplanes; ++zi) {
+        // Software pipeline over planes, ONE block barrier per plane: in the same phase the CTA
+        // stores the z-window sums of output plane t (A[t & 1]), x-passes plane t-1
+        // (A[(t-1) & 1] -> Bs[(t-1) & 1]) and y-passes plane t-2 (Bs[t & 1]); two drain steps.
+        const int nout = nplanes - (p0 - 1);
+        for (int zi = 0; zi < nplanes + 2; ++zi) {
+            const int t = zi - (p0 - 1);
+            if (zi < nplanes) {
 #pragma unroll
-            for (int i = 0; i < MT::NSLOT; ++i) zs[i] += (double)nw[i] - (double)od[i];
-            if (zi + 1 < nplanes) {    // entering plane zi+1 and leaving plane zi+1-p0: in flight
-                const T* pn = src + (int64_t)(zi + 1) * plane_elems;       // during the x / y passes
+                for (int i = 0; i < MT::NSLOT; ++i) {
+                    zs[i] += (ACC)nw[i] - (ACC)od[i];
+                    if constexpr (PASS == 0) amax = fmaxf(amax, fabsf((float)nw[i]));
+                }
+                if (zi + 1 < nplanes) {    // entering plane zi+1 and leaving plane zi+1-p0: in flight
+                    const T* pn = src + (int64_t)(zi + 1) * plane_elems;   // during the x / y passes
 #pragma unroll
-                for (int i = 0; i < MT::NSLOT; ++i) nw[i] = In<T>::load_one(pn + off[i]);
-                if (zi + 1 >= p0) {
-                    const T* po = pn - (int64_t)p0 * plane_elems;
+                    for (int i = 0; i < MT::NSLOT; ++i) nw[i] = In<T>::load_one(pn + off[i]);
+                    if (zi + 1 >= p0) {
+                        const T* po = pn - (int64_t)p0 * plane_elems;
 #pragma unroll
-                    for (int i = 0; i < MT::NSLOT; ++i) od[i] = In<T>::load_one(po + off[i]);
+                        for (int i = 0; i < MT::NSLOT; ++i) od[i] = In<T>::load_one(po + off[i]);
+                    }
+                }
+                if (t < 0) continue;                  // z-window still filling: registers only
+                if (zstore) {
+                    ACC* a = A + (t & 1) * MT::R * MT::pitchA + g * MT::pitchA + cx;
+#pragma unroll
+                    for (int i = 0; i < MT::NSLOT - 1; ++i) a[i * MT::G * MT::pitchA] = zs[i];
+                    if (last_in) a[(MT::NSLOT - 1) * MT::G * MT::pitchA] = zs[MT::NSLOT - 1];
                 }
             }
-            if (zi < p0 - 1) continue;                // z-window still filling: registers only
-            __syncthreads();                          // previous plane's y-pass is done with Bs (and A)
-            if (zstore) {
-                double* a = A + g * MT::pitchA + cx;
-#pragma unroll
-                for (int i = 0; i < MT::NSLOT - 1; ++i) a[i * MT::G * MT::pitchA] = zs[i];
-                if (last_in) a[(MT::NSLOT - 1) * MT::G * MT::pitchA] = zs[MT::NSLOT - 1];
-            }
-            __syncthreads();
-            // ---- x-pass: 16 outputs per task as two independent sliding chains of 8 (the sliding sum
-            // is a dependent fp64 chain; halving it is worth the second tree sum and the re-loads)
-            if (tid < MT::R * MT::NSEG) {
-                const double* row = A + task_r * MT::pitchA + task_seg * MT::SEG;
-                double* dst = Bs + task_r * MT::pitchB + task_seg * MT::SEG;
+            // ---- x-pass of plane t-1: 16 outputs per task as two independent sliding chains of 8
+            // (the sliding sum is a dependent chain; halving it is worth the second tree sum)
+            if (t >= 1 && t - 1 < nout && tid < MT::R * MT::NSEG) {
+                const ACC* row = A + ((t - 1) & 1) * MT::R * MT::pitchA + task_r * MT::pitchA + task_seg * MT::SEG;
+                ACC* dst = Bs + ((t - 1) & 1) * MT::R * MT::pitchB + task_r * MT::pitchB + task_seg * MT::SEG;
                 constexpr int H = MT::SEG / 2;
-                double va[PC], vb2[PC];
+                ACC va[PC], vb2[PC];
 #pragma unroll
                 for (int k = 0; k < PC; ++k) { va[k] = row[k]; vb2[k] = row[H + k]; }
-                double sa = tree_sum<PC>(va), sb = tree_sum<PC>(vb2);
+                ACC sa = tree_sum_t<PC, ACC>(va), sb = tree_sum_t<PC, ACC>(vb2);
                 dst[0] = sa; dst[H] = sb;
 #pragma unroll
                 for (int i = 1; i < H; ++i) {
-                    const double ia = row[i + PC - 1], ib = row[H + i + PC - 1];
+                    const ACC ia = row[i + PC - 1], ib = row[H + i + PC - 1];
                     sa += ia - va[(i - 1) % PC];
                     sb += ib - vb2[(i - 1) % PC];
                     dst[i] = sa; dst[H + i] = sb;
                 }
             }
-            __syncthreads();
-            // ---- y-pass: RUN outputs down one column, again as two independent chains
-            const double* cb = Bs + oy0 * MT::pitchB + ox;
-            double o[MT::RUN];
-            {
-                constexpr int H = MT::RUN / 2;
-                double ca[PC], cb2[PC];
+            // ---- y-pass of plane t-2: RUN outputs down one column, again as two independent chains
+            if (t >= 2 && t - 2 < nout) {
+                const ACC* cb = Bs + (t & 1) * MT::R * MT::pitchB + oy0 * MT::pitchB + ox;
+                ACC o[MT::RUN];
+                {
+                    constexpr int H = MT::RUN / 2;
+                    ACC ca[PC], cb2[PC];
 #pragma unroll
-                for (int j = 0; j < PC; ++j) { ca[j] = cb[j * MT::pitchB]; cb2[j] = cb[(H + j) * MT::pitchB]; }
-                o[0] = tree_sum<PC>(ca); o[H] = tree_sum<PC>(cb2);
+                    for (int j = 0; j < PC; ++j) { ca[j] = cb[j * MT::pitchB]; cb2[j] = cb[(H + j) * MT::pitchB]; }
+                    o[0] = tree_sum_t<PC, ACC>(ca); o[H] = tree_sum_t<PC, ACC>(cb2);
 #pragma unroll
-                for (int k = 1; k < H; ++k) {
-                    o[k] = o[k - 1] + (cb[(k + PC - 1) * MT::pitchB] - ca[k - 1]);
-                    o[H + k] = o[H + k - 1] + (cb[(H + k + PC - 1) * MT::pitchB] - cb2[k - 1]);
+                    for (int k = 1; k < H; ++k) {
+                        o[k] = o[k - 1] + (cb[(k + PC - 1) * MT::pitchB] - ca[k - 1]);
+                        o[H + k] = o[H + k - 1] + (cb[(H + k + PC - 1) * MT::pitchB] - cb2[k - 1]);
+                    }
                 }
-            }
-            if (prm.mean_flag) {
+                if constexpr (PASS != 0) {     // the filter compares box SUMS (finish<0> scales atol instead)
+                    if (prm.mean_flag) {
 #pragma unroll
-                for (int k = 0; k < MT::RUN; ++k) o[k] = box_mean_div(o[k], prm.denom);
-            }
-            if (PASS == 1) {
-                if (all_valid) {
+                        for (int k = 0; k < MT::RUN; ++k) o[k] = box_mean_div(o[k], prm.denom);
+                    }
+                }
+                if constexpr (PASS <= 1) {
+                    if (all_valid) {
 #pragma unroll
-                    for (int k = 0; k < MT::RUN; ++k) { tmax = fmax(tmax, o[k]); saw_nan |= o[k] != o[k]; }
+                        for (int k = 0; k < MT::RUN; ++k) { tmax = acc_max(tmax, o[k]); saw_nan |= o[k] != o[k]; }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < MT::RUN; ++k)
+                            if ((valid >> k) & 1u) { tmax = acc_max(tmax, o[k]); saw_nan |= o[k] != o[k]; }
+                    }
+                    // one maximum per z sub-chunk of prm.zc_fine output planes: pass 2 re-walks only the
+                    // sub-chunks np.isclose to the map maximum, not the whole z-chunk of the tile
+                    const int done = t - 1;                          // output planes finished in this work item
+                    if (done % prm.zc_fine == 0 || done == nout) {
+                        double tm = saw_nan ? __longlong_as_double(0x7ff8000000000000LL) : (double)tmax;
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) tm = nanmax(tm, __shfl_xor_sync(0xffffffffu, tm, off));
+                        if ((tid & 31) == 0) red[tid >> 5] = tm;   // red[] is free: the last read precedes a barrier
+                        __syncthreads();
+                        if (tid == 0) {
+                            double mm = red[0];
+                            for (int w = 1; w < NT / 32; ++w) mm = nanmax(mm, red[w]);
+                            prm.tile_max[m * prm.nent + (int64_t)tile * zsub + fine + (done - 1) / prm.zc_fine] = mm;
+                        }
+                        tmax = ninf_a; saw_nan = false;
+                    }
                 } else {
+                    const int64_t oz = zo0 + (t - 2);
 #pragma unroll
-                    for (int k = 0; k < MT::RUN; ++k)
-                        if ((valid >> k) & 1u) { tmax = fmax(tmax, o[k]); saw_nan |= o[k] != o[k]; }
-                }
-                // one maximum per z sub-chunk of prm.zc_fine output planes: pass 2 re-walks only the
-                // sub-chunks np.isclose to the map maximum, not the whole z-chunk of the tile
-                const int done = zi - (p0 - 1) + 1;              // output planes finished in this tile
-                if (done % prm.zc_fine == 0 || zi + 1 == nplanes) {
-                    if (saw_nan) tmax = __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) tmax = nanmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
-                    __syncthreads();                             // red[] free (previous sub-chunk was read)
-                    if ((tid & 31) == 0) red[tid >> 5] = tmax;
-                    __syncthreads();
-                    if (tid == 0) {
-                        double mm = red[0];
-                        for (int w = 1; w < NT / 32; ++w) mm = nanmax(mm, red[w]);
-                        prm.tile_max[m * prm.nent + (int64_t)tile * zsub + (done - 1) / prm.zc_fine] = mm;
-                    }
-                    tmax = ninf; saw_nan = false;
-                }
-            } else {
-                const int64_t oz = zo0 + zi - (p0 - 1);
-#pragma unroll
-                for (int k = 0; k < MT::RUN; ++k) {
-                    if (((valid >> k) & 1u) && np_isclose(o[k], gmax, prm.rtol, prm.atol)) {
-                        const unsigned long long lin =
-                            (unsigned long long)((oz * prm.O1 + (y0 + oy0 + k)) * prm.O2 + (x0 + ox));
-                        tbest = lin < tbest ? lin : tbest;
+                    for (int k = 0; k < MT::RUN; ++k) {
+                        if (((valid >> k) & 1u) && np_isclose((double)o[k], gmax, prm.rtol, prm.atol)) {
+                            const unsigned long long lin =
+                                (unsigned long long)((oz * prm.O1 + (y0 + oy0 + k)) * prm.O2 + (x0 + ox));
+                            tbest = lin < tbest ? lin : tbest;
+                        }
                     }
                 }
             }
+            __syncthreads();
         }
-        if (PASS == 1 && tid == 0) {   // sub-chunks past the end of a short last z-chunk hold nothing
+        if (PASS <= 1 && !listed && tid == 0) {   // sub-chunks past the end of a short last z-chunk hold nothing
             const int written = (int)((zo1 - zo0 + prm.zc_fine - 1) / prm.zc_fine);
             for (int f = written; f < zsub; ++f) prm.tile_max[m * prm.nent + (int64_t)tile * zsub + f] = ninf;
         }
     }
-    box_pass_finish<PASS, kFusedThreads, true>(prm, m, tmax, tbest, red, s_flag, s_count);
+    box_pass_finish<PASS, kFusedThreads, true>(prm, m, 0.0, tbest, red, s_flag, s_count, amax);
 }
 
 // ------------------------------------------------------------------ K2b fast path (p2 <= 32)
@@ -1068,11 +1157,13 @@ static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch
         // CTAs neither run in lock-step waves nor perfectly smoothly: average both models
         const int64_t smooth = std::max(ceil_div(ctas * (zc + warm), 2 * 148), zc + warm);
         const int64_t waves = ceil_div(ctas, 2 * 148) * (zc + warm);
-        const int64_t pass2 = ceil_div(zc, 8) + warm;
+        const int64_t pass2 = ceil_div(zc, pl.march ? 32 : 8) + warm;
         const int64_t cost = (smooth + waves) / 2 + pass2;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; pl.zc = (int)zc; }
     }
-    pl.zsub = (int)std::min<int64_t>(8, pl.zc);
+    // the listed passes (exact maxima of the filter's candidates, first index) walk single sub-chunks:
+    // serial latency, so the march kernel's sub-chunks are short
+    pl.zsub = (int)std::min<int64_t>(pl.march ? 32 : 8, pl.zc);
     pl.zc_fine = (int)ceil_div(pl.zc, pl.zsub);
     pl.chunks_z = (int)ceil_div(pl.O0, pl.zc);
     pl.ntiles = (int64_t)pl.tiles_x * pl.tiles_y * pl.chunks_z;
@@ -1097,8 +1188,8 @@ static int run_patch_fused_pc(FusedParams prm, const FusedPlan& pl, int64_t M, c
         q.best = prm.best + m0;
         q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
         q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
-        q.tickets = prm.tickets + 2 * m0;
-        if (cudaMemsetAsync(q.tickets, 0, (size_t)mc * 2 * sizeof(unsigned int), st) != cudaSuccess)
+        q.tickets = prm.tickets + 4 * m0;
+        if (cudaMemsetAsync(q.tickets, 0, (size_t)mc * 4 * sizeof(unsigned int), st) != cudaSuccess)
             return set_error(VALUES_ERR_CUDA, "patch_max: cudaMemsetAsync failed");
         k1<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kFusedThreads, smem, st>>>(q);
         int rc = check_launch("box_fused_kernel<1>");
@@ -1111,15 +1202,266 @@ static int run_patch_fused_pc(FusedParams prm, const FusedPlan& pl, int64_t M, c
     return VALUES_OK;
 }
 
+// ------------------------------------------------------------------ K2b filter, vector form
+// The same filter pass (PASS 0 above: fp32 box-sum maxima per (tile, z sub-chunk) + a bound on
+// max |input|) rebuilt for instruction count, which is what bounds the march: 56 thread
+// instructions per voxel in fp64, ~45 in its fp32 instantiation, ~12 here.
+//  * z-stage: a thread owns float4s of the input tile (LDG.128 for the entering and the leaving
+//    plane, packed f32x2 adds, STS.128) -- 1.75 instructions per element instead of 7;
+//  * x-stage: one task = 16 outputs of one row from 7 LDS.128, one sliding chain, 4 STS.128;
+//  * y-stage: one task = 2 adjacent columns x 8 rows, LDS.64 + packed adds, on the upper four warps
+//    while the lower warps run the x-stage of the next plane;
+//  * the three stages are software-pipelined over planes (double-buffered shared memory): one block
+//    barrier per plane;
+//  * no NaN bookkeeping: max |input| is bounded by the OR of the inputs' magnitude bits (>= the
+//    maximum, < twice it, all-ones exponent iff a NaN / inf was seen; one LOP3 per two elements),
+//    and box_pass_finish<0> sends a map with non-finite inputs or possible fp32 overflow through
+//    the exact pass, so every sum here is finite.
+// Tiling, z-chunks and sub-chunk entries are the march kernel's (FusedPlan), so PASS 1 / PASS 2
+// consume its list unchanged.  Needs 16-byte aligned rows: D2 % 4 == 0, aligned base and map stride.
+struct FilterTile {
+    static constexpr int NT = 256, TY = 32, TX = 64, PC = 10;
+    static constexpr int R = TY + PC - 1;                      // 41 input rows
+    static constexpr int W4 = (TX + PC - 1 + 3) / 4;           // 19 float4 per input row
+    static constexpr int NTASK = R * W4;                       // 779 float4 per plane
+    static constexpr int NSLOT = 4;                            // three per thread + 11 left over (warp 0)
+    static constexpr int S3 = NTASK - 3 * NT;
+    static constexpr int pitchA = 84, pitchB = 68;             // == 20 / 4 mod 32 words: row-striped
+                                                               // LDS.128 / STS.128 are conflict-free
+    static constexpr int BUF = 4096;                           // floats between the two buffers of A / Bs:
+                                                               // a power of two, so the buffer toggles by XOR
+    static constexpr int XRUN = 16, NSEG = TX / XRUN;          // x task: 16 outputs of one row
+    static constexpr int YRUN = 8;                             // y task: 2 columns x 8 rows
+    static constexpr int YT0 = NT - (TX / 2) * (TY / YRUN);    // first y-stage thread (128)
+    static constexpr size_t smem = (size_t)4 * BUF * sizeof(float);   // A0 | A1 | B0 | B1
+    static_assert(W4 * 4 <= pitchA && TX <= pitchB && R * NSEG <= NT && YT0 >= 0 && S3 > 0 && S3 <= 32, "tile shape");
+    static_assert(R * pitchA <= BUF && R * pitchB <= BUF, "buffer size");
+    static_assert(XRUN + PC - 1 <= 28, "x task reads 7 float4");
+};
+
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) {
+    const float2 lo = sub2(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = sub2(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ unsigned int or4(unsigned int acc, float4 v) {
+    acc |= __float_as_uint(v.x) | __float_as_uint(v.y);
+    return acc | __float_as_uint(v.z) | __float_as_uint(v.w);
+}
+
+// Measured alternatives (B200, 96 maps of 128^3): this shape 487 us; the y-stage as 4 columns x 8
+// rows on two warps (fewer instructions, longer per-warp chain) 569 us; 384 threads at 80 registers
+// (24 warps / SM, two float4 slots per thread, 8-output x tasks) 668 us -- more instructions and the
+// one-plane prefetch distance no longer covers the L2 latency.
+__global__ void __launch_bounds__(FilterTile::NT, 2) box_filter_kernel(const FusedParams prm) {
+    using FT = FilterTile;
+    constexpr int NT = FT::NT, PC = FT::PC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[NT / 32];
+    __shared__ float ymax[2][4];
+    __shared__ int s_flag;
+    __shared__ int s_count;
+    float* A = reinterpret_cast<float*>(smem_raw);             // [2][BUF] z-window sums, rows of pitchA
+    float* Bs = A + 2 * FT::BUF;                               // [2][BUF] z-x sums, rows of pitchB
+    const int p0 = prm.p0;
+    const int64_t m = blockIdx.y;
+    const int tid = threadIdx.x;
+    const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+    const int tile = blockIdx.x;
+    const int tiles_xy = prm.tiles_x * prm.tiles_y;
+    const int tx_i = tile % prm.tiles_x, ty_i = (tile / prm.tiles_x) % prm.tiles_y, zc_i = tile / tiles_xy;
+    const int64_t zo0 = (int64_t)zc_i * prm.zc;
+    const int64_t zo1 = min(zo0 + prm.zc, prm.O0);
+    const unsigned int x0 = (unsigned int)tx_i * FT::TX, y0 = (unsigned int)ty_i * FT::TY;
+    const unsigned int D1 = (unsigned int)prm.D1, D2 = (unsigned int)prm.D2;
+    const int nplanes = (int)(zo1 - zo0) + p0 - 1, nout = (int)(zo1 - zo0);
+    const unsigned int plane_elems = D1 * D2;
+    const float* src = reinterpret_cast<const float*>(prm.maps) + m * prm.stride_m + zo0 * (int64_t)plane_elems;
+    // z-stage ownership: slot i of this thread is float4 task (row, float4 column) of the input tile;
+    // rows / columns past the map edge are clamped (they only feed masked outputs).  One running
+    // pointer per slot for the entering plane and one for the leaving plane (two 64-bit adds per
+    // load instead of a full address computation) and one shared-memory pointer that toggles
+    // between the two buffers by XOR.
+    const bool has3 = tid < FT::S3;
+    const float4* pnw[FT::NSLOT];
+    const float4* pod[FT::NSLOT];
+    unsigned int sa[FT::NSLOT];                                 // shared-memory byte address of the slot
+    const int64_t plane4 = plane_elems / 4;
+    const unsigned int a_base = (unsigned int)__cvta_generic_to_shared(A);
+#pragma unroll
+    for (int i = 0; i < FT::NSLOT; ++i) {
+        const int task = min(tid + NT * i, FT::NTASK - 1);
+        const int r = task / FT::W4, c4 = task - r * FT::W4;
+        pnw[i] = reinterpret_cast<const float4*>(src + (min(y0 + r, D1 - 1) * D2 + min(x0 + 4 * c4, D2 - 4)));
+        pod[i] = pnw[i] - plane4;                             // advanced (to plane 0) before its first use
+        sa[i] = a_base + (unsigned int)(r * FT::pitchA + 4 * c4) * 4u;
+    }
+    // x-stage task (rows striped over lanes) and y-stage task (column pairs over lanes)
+    const int task_r = tid % FT::R, task_seg = tid / FT::R;
+    const int yt = tid - FT::YT0, cp = yt & 31, rg = yt >> 5;
+    int nvr = 0;                                                // valid output rows of this y task
+    bool cv0 = false, cv1 = false;
+    if (yt >= 0) {
+        nvr = max(0, min(FT::YRUN, (int)prm.O1 - (int)(y0 + rg * FT::YRUN)));
+        cv0 = x0 + 2 * cp < prm.O2; cv1 = x0 + 2 * cp + 1 < prm.O2;
+    }
+    const bool all_valid = nvr == FT::YRUN && cv1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 zs[FT::NSLOT], nw[FT::NSLOT], od[FT::NSLOT];
+#pragma unroll
+    for (int i = 0; i < FT::NSLOT; ++i) { zs[i] = zero4; od[i] = zero4; nw[i] = zero4; }
+    unsigned int abits = 0;
+    float tmax = -__int_as_float(0x7f800000);
+    int pend = -1;                                              // sub-chunk whose maxima sit in ymax[pend & 1]
+    nw[0] = __ldg(pnw[0]); nw[1] = __ldg(pnw[1]); nw[2] = __ldg(pnw[2]);
+    if (has3) nw[3] = __ldg(pnw[3]);
+    for (int zi = 0; zi < nplanes + 2; ++zi) {
+        const int t = zi - (p0 - 1);
+        if (zi < nplanes) {
+            const bool ld_new = zi + 1 < nplanes, ld_old = ld_new && zi + 1 >= p0;
+#define VB_Z_SLOT(i)                                                                              \
+            {                                                                                     \
+                zs[i] = add4(zs[i], sub4(nw[i], od[i]));                                          \
+                abits = or4(abits, nw[i]);                                                        \
+                if (ld_new) { pnw[i] += plane4; nw[i] = __ldg(pnw[i]); }                          \
+                if (ld_old) { pod[i] += plane4; od[i] = __ldg(pod[i]); }                          \
+                if (t >= 0) {                                                                     \
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa[i]),         \
+                                 "f"(zs[i].x), "f"(zs[i].y), "f"(zs[i].z), "f"(zs[i].w) : "memory"); \
+                    sa[i] ^= FT::BUF * 4u;                                                        \
+                }                                                                                 \
+            }
+            VB_Z_SLOT(0)
+            VB_Z_SLOT(1)
+            VB_Z_SLOT(2)
+            if (has3) VB_Z_SLOT(3)
+#undef VB_Z_SLOT
+            if (t < 0) continue;                               // z-window still filling: registers only
+        }
+        if (pend >= 0 && tid == 0) {                           // maxima of a finished sub-chunk (written
+            const float* ym = ymax[pend & 1];                  // before the last barrier)
+            prm.tile_max[m * prm.nent + (int64_t)tile * prm.zsub + pend] =
+                (double)fmaxf(fmaxf(ym[0], ym[1]), fmaxf(ym[2], ym[3]));
+        }
+        pend = -1;
+        // ---- x-stage of plane t-1: 16 outputs of one row, one sliding chain
+        if (t >= 1 && t - 1 < nout && tid < FT::R * FT::NSEG) {
+            const float* row = A + ((t - 1) & 1) * FT::BUF + task_r * FT::pitchA + task_seg * FT::XRUN;
+            float v[28];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const float4 q = *reinterpret_cast<const float4*>(row + 4 * k);
+                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            }
+            float o[FT::XRUN];
+            o[0] = tree_sum_t<PC, float>(v);
+#pragma unroll
+            for (int i = 1; i < FT::XRUN; ++i) o[i] = o[i - 1] + (v[i + PC - 1] - v[i - 1]);
+            float* dst = Bs + ((t - 1) & 1) * FT::BUF + task_r * FT::pitchB + task_seg * FT::XRUN;
+#pragma unroll
+            for (int k = 0; k < FT::XRUN / 4; ++k)
+                *reinterpret_cast<float4*>(dst + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        }
+        // ---- y-stage of plane t-2: 2 columns x 8 rows per thread of the upper four warps
+        if (t >= 2 && t - 2 < nout && yt >= 0) {
+            const float* cb = Bs + (t & 1) * FT::BUF + rg * FT::YRUN * FT::pitchB + 2 * cp;
+            float2 c[FT::YRUN + PC - 1];
+#pragma unroll
+            for (int j = 0; j < FT::YRUN + PC - 1; ++j) c[j] = *reinterpret_cast<const float2*>(cb + j * FT::pitchB);
+            float2 o[FT::YRUN];
+            {
+                float2 q[PC / 2];
+#pragma unroll
+                for (int j = 0; j < PC / 2; ++j) q[j] = __fadd2_rn(c[2 * j], c[2 * j + 1]);
+                o[0] = __fadd2_rn(__fadd2_rn(__fadd2_rn(q[0], q[1]), __fadd2_rn(q[2], q[3])), q[4]);
+            }
+#pragma unroll
+            for (int k = 1; k < FT::YRUN; ++k) o[k] = __fadd2_rn(o[k - 1], sub2(c[k + PC - 1], c[k - 1]));
+            if (all_valid) {
+#pragma unroll
+                for (int k = 0; k < FT::YRUN; ++k) tmax = fmaxf(tmax, fmaxf(o[k].x, o[k].y));
+            } else {
+#pragma unroll
+                for (int k = 0; k < FT::YRUN; ++k) {
+                    if (k < nvr && cv0) tmax = fmaxf(tmax, o[k].x);
+                    if (k < nvr && cv1) tmax = fmaxf(tmax, o[k].y);
+                }
+            }
+            const int done = t - 1;                            // output planes finished in this tile
+            if (done % prm.zc_fine == 0 || done == nout) {     // one maximum per z sub-chunk
+                const int sub = (done - 1) / prm.zc_fine;
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o2));
+                if (cp == 0) ymax[sub & 1][rg] = tmax;
+                tmax = -__int_as_float(0x7f800000);
+            }
+        }
+        {   // uniform: which sub-chunk (if any) the y-stage just closed
+            const int done = t - 1;
+            if (t >= 2 && done <= nout && (done % prm.zc_fine == 0 || done == nout)) pend = (done - 1) / prm.zc_fine;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (pend >= 0) {
+            const float* ym = ymax[pend & 1];
+            prm.tile_max[m * prm.nent + (int64_t)tile * prm.zsub + pend] =
+                (double)fmaxf(fmaxf(ym[0], ym[1]), fmaxf(ym[2], ym[3]));
+        }
+        // sub-chunks past the end of a short last z-chunk hold nothing
+        const int written = (int)((zo1 - zo0 + prm.zc_fine - 1) / prm.zc_fine);
+        for (int f = written; f < prm.zsub; ++f) prm.tile_max[m * prm.nent + (int64_t)tile * prm.zsub + f] = ninf;
+    }
+    box_pass_finish<0, NT, true>(prm, m, 0.0, ~0ull, red, s_flag, s_count, __uint_as_float(abits & 0x7fffffffu));
+}
+
+// err_coef of the fp32 filter: a bound on |fp32 box sum - exact box sum| / max |input| for the
+// filter kernels' operation order (u = 2^-24, every fp32 add / subtract rounds to nearest, no
+// underflow error in additions).  With a = max |input|, Z = p0 a (bound on a z-window sum):
+//   z-slide, K = zc + p0 - 1 steps of zs = fl(zs + fl(new - old)):  ez <= K (p0 + 2) u a
+//   x-pass, tree over pc (depth d) + at most xs slides s = fl(s + fl(in - out)):
+//                                                                   ex <= pc ez + [d pc + xs (pc + 2)] u Z
+//   y-pass, tree over pc (depth dy) + at most ys slides:            ey <= pc ex + [dy pc + ys (pc + 2)] u pc Z
+// doubled to cover the second-order terms and the exact pass's own fp64 rounding.  (The vector
+// kernel's a is the OR bound, up to twice the true maximum: conservative.)
+static double filter_err_coef(int zc, int p0, int pc, int xs, int ys, int dy = 0) {
+    const double u = 5.9604644775390625e-8;
+    const double K = zc + p0 - 1, d = tree_depth(pc);
+    const double ez = K * (p0 + 2);
+    const double ex = pc * ez + (d * pc + xs * (pc + 2)) * p0;
+    const double ey = pc * ex + ((dy ? dy : d) * pc + ys * (pc + 2)) * (double)pc * p0;
+    return 2.0 * u * ey;
+}
+
 template <typename T>
 static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cudaStream_t st) {
     using MT = MarchTile<32, 64, 10>;
-    auto k1 = box_march_kernel<T, 32, 64, 10, 1>;
-    auto k2 = box_march_kernel<T, 32, 64, 10, 2>;
-    const size_t smem = MT::smem;
+    using FT = FilterTile;
+    static_assert(FT::TY == 32 && FT::TX == 64 && FT::PC == 10, "the filter shares the march kernel's tiling");
+    constexpr bool kCanFilter = std::is_same<T, float>::value;
+    // g_patch_path: 5 = no filter, 6 = the march kernel's own fp32 instantiation as the filter
+    const bool filter = kCanFilter && g_patch_path != 5;
+    // (a 2-D image is one plane per tile: nothing to pipeline, the scalar filter is faster there)
+    const bool vec = filter && g_patch_path != 6 && prm.zc >= 4 && prm.D2 % 4 == 0 && prm.stride_m % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(prm.maps) & 15) == 0;
+    auto k0 = box_march_kernel<float, float, 32, 64, 10, 0, 3>;   // instantiated for fp32 maps only
+    auto k1 = box_march_kernel<T, double, 32, 64, 10, 1, 2>;
+    auto k2 = box_march_kernel<T, double, 32, 64, 10, 2, 2>;
+    const size_t smem = MT::smem_bytes<double>(), smem0 = vec ? FT::smem : MT::smem_bytes<float>();
     if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        (filter && !vec && cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0) != cudaSuccess) ||
+        (vec && cudaFuncSetAttribute(box_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0) != cudaSuccess))
         return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute(%zu) failed", smem);
+    prm.use_list = filter ? 1 : 0;
+    prm.err_coef = vec ? filter_err_coef(prm.zc, prm.p0, 10, FT::XRUN - 1, FT::YRUN - 1)
+                       : filter_err_coef(prm.zc, prm.p0, 10, MT::SEG / 2 - 1, MT::RUN / 2 - 1);
     for (int64_t m0 = 0; m0 < M; m0 += 65535) {  // gridDim.y limit
         const int64_t mc = std::min<int64_t>(65535, M - m0);
         FusedParams q = prm;
@@ -1128,12 +1470,21 @@ static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
         q.best = prm.best + m0;
         q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
         q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
-        q.tickets = prm.tickets + 2 * m0;
-        if (cudaMemsetAsync(q.tickets, 0, (size_t)mc * 2 * sizeof(unsigned int), st) != cudaSuccess)
+        q.tickets = prm.tickets + 4 * m0;
+        if (cudaMemsetAsync(q.tickets, 0, (size_t)mc * 4 * sizeof(unsigned int), st) != cudaSuccess)
             return set_error(VALUES_ERR_CUDA, "patch_max: cudaMemsetAsync failed");
+        int rc;
+        if (vec) {
+            box_filter_kernel<<<dim3((unsigned)pl.ntiles, (unsigned)mc), FT::NT, smem0, st>>>(q);
+            if ((rc = check_launch("box_filter_kernel"))) return rc;
+        } else if (filter) {
+            k0<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kFusedThreads, smem0, st>>>(q);
+            if ((rc = check_launch("box_march_kernel<0>"))) return rc;
+        }
+        // pass 1: every tile, or (after the filter) the few listed sub-chunks -- the grid stays
+        // ntiles wide because a map whose list overflowed is walked tile by tile
         k1<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kFusedThreads, smem, st>>>(q);
-        int rc = check_launch("box_march_kernel<1>");
-        if (rc) return rc;
+        if ((rc = check_launch("box_march_kernel<1>"))) return rc;
         // pass 2: the work list normally holds one or two (tile, z sub-chunk) entries per map
         const unsigned g2 = (unsigned)std::min<int64_t>(prm.nent, mc >= 16 ? 8 : 32);
         k2<<<dim3(g2, (unsigned)mc), kFusedThreads, smem, st>>>(q);
@@ -1148,10 +1499,10 @@ static int run_patch_fused(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
     return run_patch_fused_pc<T, TY, TX, 0>(prm, pl, M, st);
 }
 
-// tile_max [M, ntiles] | gmax [M] | best [M] | tickets [M, 2] (one 8-byte slot) | active [M, 1 + kMaxActive] ints
+// tile_max [M, nent] | gmax [M] | best [M] | tickets [M, 4] (two 8-byte slots) | active [M, 1 + kMaxActive] ints
 static int64_t fused_entries(const FusedPlan& pl) { return pl.march ? pl.ntiles * pl.zsub : pl.ntiles; }
 static size_t fused_workspace_bytes(int64_t M, const FusedPlan& pl) {
-    return (size_t)(M * fused_entries(pl) + 3 * M) * sizeof(double) + (size_t)M * (1 + kMaxActive) * sizeof(int);
+    return (size_t)(M * fused_entries(pl) + 4 * M) * sizeof(double) + (size_t)M * (1 + kMaxActive) * sizeof(int);
 }
 
 }  // namespace vb
@@ -1228,7 +1579,7 @@ extern "C" int values_normalize_maps(const void* maps, int dtype, int64_t M, int
 extern "C" size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* shape3_host,
                                                    const int64_t* patch3_host) {
     if (M <= 0 || !shape3_host || !patch3_host) return 0;
-    if (g_patch_path == 0 || g_patch_path == 4) {
+    if (g_patch_path == 0 || g_patch_path >= 4) {
         FusedPlan fp;
         if (make_fused_plan(M, shape3_host, patch3_host, fp) != VALUES_OK) return 0;
         if (fp.ty) return fused_workspace_bytes(M, fp);
@@ -1256,7 +1607,7 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
     double* ws = reinterpret_cast<double*>(workspace);
     const double denom =
         mean_flag ? (double)patch3_host[0] * (double)patch3_host[1] * (double)patch3_host[2] : 1.0;
-    if (g_patch_path == 0 || g_patch_path == 4) {
+    if (g_patch_path == 0 || g_patch_path >= 4) {
         FusedPlan fp;
         int rc = make_fused_plan(M, shape3_host, patch3_host, fp);
         if (rc) return rc;
@@ -1279,7 +1630,7 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
             prm.gmax = ws + M * prm.nent;
             prm.best = reinterpret_cast<unsigned long long*>(ws + M * prm.nent + M);
             prm.tickets = reinterpret_cast<unsigned int*>(ws + M * prm.nent + 2 * M);
-            prm.active = reinterpret_cast<int*>(ws + M * prm.nent + 3 * M);
+            prm.active = reinterpret_cast<int*>(ws + M * prm.nent + 4 * M);
             prm.max_score = max_score; prm.bbox_lo = bbox_lo;
             if (fp.march) {
                 if (dtype == VALUES_F32) return run_patch_march<float>(prm, fp, M, st);
