@@ -732,6 +732,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
         // stores the z-window sums of output plane t (A[t & 1]), x-passes plane t-1
         // (A[(t-1) & 1] -> Bs[(t-1) & 1]) and y-passes plane t-2 (Bs[t & 1]); two drain steps.
         const int nout = nplanes - (p0 - 1);
+        int sub_planes = 0, sub_idx = 0;      // planes finished in the current z sub-chunk, its index
         for (int zi = 0; zi < nplanes + 2; ++zi) {
             const int t = zi - (p0 - 1);
             if (zi < nplanes) {
@@ -810,8 +811,8 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
                     }
                     // one maximum per z sub-chunk of prm.zc_fine output planes: pass 2 re-walks only the
                     // sub-chunks np.isclose to the map maximum, not the whole z-chunk of the tile
-                    const int done = t - 1;                          // output planes finished in this work item
-                    if (done % prm.zc_fine == 0 || done == nout) {
+                    // (counted: a runtime modulo per plane costs ~25 instructions)
+                    if (++sub_planes == prm.zc_fine || t - 1 == nout) {
                         double tm = saw_nan ? __longlong_as_double(0x7ff8000000000000LL) : (double)tmax;
 #pragma unroll
                         for (int off = 16; off > 0; off >>= 1) tm = nanmax(tm, __shfl_xor_sync(0xffffffffu, tm, off));
@@ -820,9 +821,9 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
                         if (tid == 0) {
                             double mm = red[0];
                             for (int w = 1; w < NT / 32; ++w) mm = nanmax(mm, red[w]);
-                            prm.tile_max[m * prm.nent + (int64_t)tile * zsub + fine + (done - 1) / prm.zc_fine] = mm;
+                            prm.tile_max[m * prm.nent + (int64_t)tile * zsub + fine + sub_idx] = mm;
                         }
-                        tmax = ninf_a; saw_nan = false;
+                        tmax = ninf_a; saw_nan = false; sub_planes = 0; ++sub_idx;
                     }
                 } else {
                     const int64_t oz = zo0 + (t - 2);
@@ -1319,6 +1320,7 @@ __global__ void __launch_bounds__(FilterTile::NT, 2) box_filter_kernel(const Fus
     unsigned int abits = 0;
     float tmax = -__int_as_float(0x7f800000);
     int pend = -1;                                              // sub-chunk whose maxima sit in ymax[pend & 1]
+    int sub = 0, sub_planes = 0;                                // current z sub-chunk, its planes done so far
     nw[0] = __ldg(pnw[0]); nw[1] = __ldg(pnw[1]); nw[2] = __ldg(pnw[2]);
     if (has3) nw[3] = __ldg(pnw[3]);
     for (int zi = 0; zi < nplanes + 2; ++zi) {
@@ -1350,6 +1352,10 @@ __global__ void __launch_bounds__(FilterTile::NT, 2) box_filter_kernel(const Fus
                 (double)fmaxf(fmaxf(ym[0], ym[1]), fmaxf(ym[2], ym[3]));
         }
         pend = -1;
+        // uniform: does the y-stage of this step finish z sub-chunk `sub` (zc_fine output planes, fewer
+        // at the end of the tile)?  Counted, not computed: a runtime modulo costs ~25 instructions.
+        bool closes = false;
+        if (t >= 2 && t - 2 < nout) closes = ++sub_planes == prm.zc_fine || t - 1 == nout;
         // ---- x-stage of plane t-1: 16 outputs of one row, one sliding chain
         if (t >= 1 && t - 1 < nout && tid < FT::R * FT::NSEG) {
             const float* row = A + ((t - 1) & 1) * FT::BUF + task_r * FT::pitchA + task_seg * FT::XRUN;
@@ -1393,19 +1399,14 @@ __global__ void __launch_bounds__(FilterTile::NT, 2) box_filter_kernel(const Fus
                     if (k < nvr && cv1) tmax = fmaxf(tmax, o[k].y);
                 }
             }
-            const int done = t - 1;                            // output planes finished in this tile
-            if (done % prm.zc_fine == 0 || done == nout) {     // one maximum per z sub-chunk
-                const int sub = (done - 1) / prm.zc_fine;
+            if (closes) {                                      // one maximum per z sub-chunk
 #pragma unroll
                 for (int o2 = 16; o2 > 0; o2 >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o2));
                 if (cp == 0) ymax[sub & 1][rg] = tmax;
                 tmax = -__int_as_float(0x7f800000);
             }
         }
-        {   // uniform: which sub-chunk (if any) the y-stage just closed
-            const int done = t - 1;
-            if (t >= 2 && done <= nout && (done % prm.zc_fine == 0 || done == nout)) pend = (done - 1) / prm.zc_fine;
-        }
+        if (closes) { pend = sub; ++sub; sub_planes = 0; }
         __syncthreads();
     }
     if (tid == 0) {
