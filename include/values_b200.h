@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VALUES_ABI_VERSION 3
+#define VALUES_ABI_VERSION 4
 
 typedef enum {
     VALUES_F32 = 0, VALUES_F64 = 1, VALUES_BF16 = 2,
@@ -219,12 +219,22 @@ int values_confusion_counts(const void* labels_a, int64_t Na, int64_t stride_a, 
                             int64_t Nb, int64_t stride_b, int label_dtype, int64_t V, int n_classes,
                             unsigned long long* out, void* stream);
 
+/* Axis-order conversion for the hand-off files: medpy.io.load / save
+ * (data_carrier_3D.py:233-371, experiment_dataloader.py:38-49, aggregate_uncertainties.py:77-79)
+ * present a NIfTI payload -- stored x-fastest, a C-order [Z][Y][X] array -- to Python as an array
+ * indexed [x][y][z]; cv2's [H][W] image likewise becomes [W][H].
+ *   in  [n0, n1, n2] C-order, out [n2, n1, n0] C-order: out[c][b][a] = in[a][b][c]
+ *   elem_bytes 1, 2, 4 or 8 (pure byte movement, any dtype of that size); in != out. */
+int values_reverse_axes(const void* in, void* out, int elem_bytes, int64_t n0, int64_t n1,
+                        int64_t n2, void* stream);
+
 /* Tuning hooks for benchmarks and tests (process-wide; 0 restores the automatic choice):
  * voxel tiles per CTA of the K1 stream kernel, and its batch / occupancy variant. */
 void values_debug_set_k1_iter(int iter);
 void values_debug_set_k1_variant(int variant);
 /* K2b implementation: 0 automatic (march kernel for 10x10 in-plane patches, else fused tile kernel),
- * 1 streaming two-kernel path, 2 generic tiled path, 4 fused tile kernel. */
+ * 1 streaming two-kernel path, 2 generic tiled path, 4 fused tile kernel, 5 march kernel without its
+ * fp32 filter pass, 6 march kernel behind its own fp32 instantiation instead of the vector filter. */
 void values_debug_set_patch_path(int path);
 /* K3 implementation: 0 automatic (vector kernel when rows are 16-byte aligned), 1 scalar kernel. */
 void values_debug_set_stitch_path(int path);

@@ -163,6 +163,73 @@ def k4_cases(ref):
     print("k4_stats", len(out), "arrays")
 
 
+def formats_cases(ref, carrier):
+    """the reference's own file-level hand-off, run unmodified on the stitch case above
+    with medpy.io.save / load replaced by values_b200.formats.save / load (medpy is absent here):
+      * DataCarrier3D.save_data -> every array it hands to save(), keyed by relative path;
+      * ExperimentDataloader + aggregate_uncertainties on the directory it wrote -> the
+        aggregated_<unc>.json contents (hydra.utils.instantiate replaced by a direct call of the
+        reference's own aggregation functions, jsbeautifier by the identity)."""
+    import importlib
+    import json
+    import tempfile
+    from pathlib import Path
+
+    from values_b200 import formats  # host I/O only; no kernel runs here
+
+    dc = ref.modules["data_carrier_3D"]
+    agg = ref.modules["aggregate_uncertainties"]
+    edl = importlib.import_module("evaluation.experiment_dataloader")
+    ev = importlib.import_module("evaluation.experiment_version")
+    recorded = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        def rec_save(arr, path, hdr=False):
+            recorded[os.path.relpath(path, tmp)] = np.asarray(arr)
+            formats.save(arr, path, hdr)
+
+        dc.save = rec_save
+        carrier.save_data(root_dir=tmp, exp_name="Dropout", version=0, org_data_path=None, test_split="id")
+        edl.load, edl.save = formats.load, formats.save
+        agg.load = formats.load
+
+        def instantiate(cfg, **kwargs):
+            cfg = dict(cfg)
+            fn = getattr(agg, cfg.pop("_target_").rsplit(".", 1)[1])
+            return fn(**cfg, **kwargs)
+
+        agg.hydra.utils.instantiate = instantiate
+        agg.jsbeautifier.beautify = lambda text, opts=None: text
+        target = "evaluation.uncertainty_aggregation.aggregate_uncertainties."
+        aggregations = {
+            "patch_level": {"_target_": target + "patch_level_aggregation", "patch_size": 10},
+            "image_level": {"_target_": target + "image_level_aggregation"},
+            "threshold": {"_target_": target + "threshold_aggregation", "threshold": 0.3},
+        }
+        unc_types = ["predictive_uncertainty", "aleatoric_uncertainty", "epistemic_uncertainty"]
+        version = ev.ExperimentVersion(
+            base_path=Path(tmp), naming_scheme_version="{version}", pred_model="Dropout",
+            image_ending=".nii.gz", unc_ending=".nii.gz", unc_types=unc_types, aggregations=aggregations,
+            n_reference_segs=1, version=0, seed=123)
+        loader = edl.ExperimentDataloader(version, "id")
+        agg.aggregate_uncertainties(loader, aggregations)
+        aggregated = {}
+        for unc in unc_types:
+            with open(loader.dataset_path / f"aggregated_{unc}.json") as f:
+                aggregated[unc] = json.load(f)
+        meta = {
+            "image_ids": loader.image_ids,
+            "unc_dirs": {k: os.path.relpath(v, tmp) for k, v in loader.unc_path_dict.items()},
+            "pred_seg_files": sorted(os.path.relpath(p, tmp) for p in loader.get_pred_seg_paths(loader.image_ids[0])),
+            "gt_unc_map_sum": float(np.sum(loader.get_gt_unc_map(loader.image_ids[0]))),
+            "aggregated": aggregated, "aggregations": aggregations,
+        }
+    np.savez_compressed(os.path.join(HERE, "save_data_3d.npz"),
+                        **{k.replace(os.sep, "|"): v for k, v in recorded.items()})
+    with open(os.path.join(HERE, "save_data_3d.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("save_data_3d", len(recorded), "files")
+
+
 def main():
     ref = ref_loader.load()
     if "--only-k4" in sys.argv:
@@ -284,6 +351,7 @@ def main():
         mean_seg=np.argmax(np.mean(sm, axis=0), axis=0).astype(np.uint8),
     )
     print("stitch_3d", len(crops), "patches")
+    formats_cases(ref, carrier)
     k4_cases(ref)
 
 

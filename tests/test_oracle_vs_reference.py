@@ -59,3 +59,36 @@ def test_k4_stats_random(ref):
             assert ra[2] == rb[2] and ref.calc_ace(corr, conf) == vo.calc_ace(corr, conf)
     seg = (rng.random((6, 7, 8)) < 0.2).astype(np.uint8)
     assert ref.calculate_foreground_quantile_image(seg) == vo.calculate_foreground_quantile_image(seg)
+
+
+def test_experiment_dataloader_mirror_matches_reference_class(ref, tmp_path):
+    """the reference's ExperimentDataloader (medpy.io replaced by values_b200.formats,
+    medpy being absent) and our mirror must agree on ids, paths and every array they hand out."""
+    import importlib
+    from pathlib import Path
+
+    from test_formats import exp_version, make_results_dir   # tests/ is on sys.path (rootdir conftest)
+    from values_b200 import formats
+    from values_b200.experiment_dataloader import ExperimentDataloader
+
+    edl = importlib.import_module("evaluation.experiment_dataloader")
+    edl.load, edl.save = formats.load, formats.save
+    for pred_model in ("Dropout", "Softmax"):
+        root = Path(tmp_path) / pred_model
+        d, _ = make_results_dir(root, pred_model=pred_model)
+        if pred_model == "Softmax":
+            import shutil
+
+            shutil.rmtree(d / "pred_entropy")
+        a = edl.ExperimentDataloader(exp_version(root, pred_model=pred_model), "id")
+        b = ExperimentDataloader(exp_version(root, pred_model=pred_model), "id")
+        assert a.image_ids == b.image_ids and a.unc_path_dict == b.unc_path_dict
+        assert a.dataset_path == b.dataset_path and a.ref_seg_dir == b.ref_seg_dir
+        for image_id in a.image_ids:
+            assert sorted(a.get_pred_seg_paths(image_id)) == sorted(b.get_pred_seg_paths(image_id))
+            np.testing.assert_array_equal(a.get_mean_pred_seg(image_id), b.get_mean_pred_seg(image_id))
+            np.testing.assert_array_equal(a.get_reference_segs(image_id), b.get_reference_segs(image_id))
+            np.testing.assert_array_equal(a.get_gt_unc_map(image_id), b.get_gt_unc_map(image_id))
+            np.testing.assert_array_equal(a.get_max_softmax_pred(image_id), b.get_max_softmax_pred(image_id))
+            for unc in a.unc_path_dict:
+                np.testing.assert_array_equal(a.get_unc_map(image_id, unc), b.get_unc_map(image_id, unc))

@@ -9,7 +9,9 @@ from . import _lib  # noqa: F401  (raises ValuesExtensionMissing when the .so is
 from .aggregation import (aggregate_uncertainties, image_level_aggregation, map_reduce,
                           normalize_maps, patch_level_aggregation, patch_max,
                           threshold_aggregation)
-from . import metrics, segmetrics, threshold
+from . import formats, metrics, segmetrics, threshold
+from .experiment_dataloader import ExperimentDataloader
+from .formats import load_to_device, reverse_axes, save_from_device
 from .data_carrier import DataCarrier3D
 from .metrics import (calc_ace, calib_stats, calibration_error, calibration_error_image,
                       compute_ncc, ncc_batched, ncc_main, platt_scale_confid)
@@ -37,4 +39,5 @@ __all__ = [
     "compute_ncc", "ncc_batched", "ncc_main", "calib_stats", "calc_ace", "platt_scale_confid",
     "calibration_error_image", "calibration_error",
     "calculate_ged", "confusion_counts", "dice_from_confusion", "mean_prediction_dice",
+    "formats", "ExperimentDataloader", "load_to_device", "save_from_device", "reverse_axes",
 ]

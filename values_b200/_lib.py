@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libvalues_b200.so")
 
 F32, F64, BF16, U8, I32, I64 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 3  # include/values_b200.h VALUES_ABI_VERSION
+ABI_VERSION = 4  # include/values_b200.h VALUES_ABI_VERSION
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 _LABEL_DTYPES = {torch.uint8: U8, torch.int32: I32, torch.int64: I64}
 
@@ -62,6 +62,7 @@ def _load() -> C.CDLL:
         "values_calib_bins_fused": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, i64, i64, dbl, dbl, C.c_int,
                                               i64, pdbl, C.c_int, vp, vp, sz, vp]),
         "values_confusion_counts": (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, i64, C.c_int, vp, vp]),
+        "values_reverse_axes": (C.c_int, [vp, vp, C.c_int, i64, i64, i64, vp]),
         "values_debug_set_k1_iter": (None, [C.c_int]),
         "values_debug_set_k1_variant": (None, [C.c_int]),
         "values_debug_set_patch_path": (None, [C.c_int]),
@@ -85,7 +86,7 @@ EXPORTED = [
     "values_normalize_maps", "values_count_nonzero", "values_radix_histogram",
     "values_min_key_above", "values_pair_moments_workspace_bytes", "values_pair_moments",
     "values_calib_bins_workspace_bytes", "values_calib_bins", "values_calib_bins_fused",
-    "values_confusion_counts",
+    "values_confusion_counts", "values_reverse_axes",
     "values_debug_set_k1_iter", "values_debug_set_k1_variant",
     "values_debug_set_patch_path", "values_debug_set_stitch_path",
 ]

@@ -31,6 +31,12 @@ def _as_map(image, device: torch.device) -> torch.Tensor:
     if isinstance(image, np.ndarray):
         if image.dtype not in (np.float32, np.float64):
             image = image.astype(np.float64)
+        if image.ndim in (2, 3) and image.flags.f_contiguous and not image.flags.c_contiguous:
+            # what medpy.io.load returns (a transposed view of the x-fastest payload): upload it as it
+            # lies in memory and reverse the axes on the GPU instead of a strided host copy
+            from .formats import reverse_axes
+
+            return reverse_axes(torch.from_numpy(image.T).to(device, non_blocking=True))
         image = torch.from_numpy(np.ascontiguousarray(image))
     if not isinstance(image, torch.Tensor):
         raise TypeError(f"image must be a numpy array or torch tensor, got {type(image)}")
@@ -218,15 +224,16 @@ def aggregate_uncertainties(exp_dataloader, aggregations, load_fn=None, save: bo
     """Drop-in for aggregate_uncertainties.py:70-96: for every uncertainty type and image, run
     every configured aggregation and write `aggregated_<unc>.json`.
 
-    `load_fn(path) -> ndarray` defaults to medpy.io.load (as the reference) when medpy is
-    installed.  Unlike the reference the image is loaded and uploaded ONCE per image, not once
-    per aggregation (:77-79).  Returns {unc: {image_key: {aggregation: result}}}.
+    `load_fn(path) -> ndarray or CUDA tensor` defaults to values_b200.formats.load_to_device (the
+    file's payload is uploaded as it lies on disk and brought into medpy's [x, y, z] index order on
+    the GPU).  Unlike the reference the image is loaded and uploaded ONCE per image, not once per
+    aggregation (:77-79).  Returns {unc: {image_key: {aggregation: result}}}.
     """
     if load_fn is None:
-        from medpy.io import load as _medpy_load  # not installed in the build image
+        from .formats import load_to_device
 
         def load_fn(path):
-            return _medpy_load(path)[0]
+            return load_to_device(path)[0]
 
     dev = _lib.require_cuda()
     results = {}

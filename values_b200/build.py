@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvalues_b200.so")
 OBJ_DIR = os.path.join(PKG, "build")
-SOURCES = ["api.cu", "uncertainty.cu", "aggregate.cu", "stitch.cu", "stats.cu"]
+SOURCES = ["api.cu", "uncertainty.cu", "aggregate.cu", "stitch.cu", "stats.cu", "formats.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "values_b200.h")]
 
 NVCC_FLAGS = [

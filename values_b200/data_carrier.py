@@ -11,8 +11,9 @@ Same entry point and `.data` layout as the reference (data_carrier_3D.py:99-135)
 The arrays are CUDA tensors instead of numpy arrays (no device->host copy per patch, which
 is what the reference does at :161); `numpy_data()` materialises the reference's numpy
 layout.  The reference hardcodes C=2 (:120); here C is taken from the softmax batch.
-File output (NIfTI via medpy, :181-371) is host I/O and out of scope; `normalized()`
-provides the arithmetic of the save path (:208-217, 253-259, 281-285, 323-363).
+`normalized()` is the arithmetic of the save path (:208-217, 253-259, 281-285, 323-363) on the
+device; `save_data()` writes the reference's directory layout of `.nii.gz` files (:181-371)
+through values_b200.formats (axis reversal on the GPU, one D2H copy per file, gzip on the host).
 """
 from __future__ import annotations
 
@@ -113,9 +114,16 @@ class DataCarrier3D:
         sm = normalize_maps(v["softmax_pred"].reshape((n_pred * n_cls,) + size), cnt, clip_min)
         sm = sm.reshape((n_pred, n_cls) + size)
         res = uncertainty_fused(sm.unsqueeze(0), maps=False, mean_argmax=True, sample_argmax=True)
+        mean_sm = None
+        if n_pred > 1:   # np.mean(axis=0) (:254): samples added in index order, one IEEE division
+            mean_sm = sm[0].clone()
+            for i in range(1, n_pred):
+                mean_sm += sm[i]
+            # (a CUDA divisor: torch turns division by a host scalar into a multiplication by 1/n)
+            mean_sm /= torch.tensor(float(n_pred), dtype=mean_sm.dtype, device=mean_sm.device)
         out = {
             "softmax_pred": sm,
-            "mean_softmax_pred": sm.mean(dim=0) if n_pred > 1 else None,
+            "mean_softmax_pred": mean_sm,
             "mean_seg": res.mean_argmax[0],
             "pred_seg": res.sample_argmax[0],
         }
@@ -126,6 +134,80 @@ class DataCarrier3D:
             for i, k in enumerate(present):
                 out[k] = norm[i]
         return out
+
+    # ------------------------------------------------------------------ file output
+    def _create_save_dirs(self, root_dir: str, exp_name: str, version: int, sigma_save_dir: bool,
+                          test_split: str = "id") -> None:
+        """data_carrier_3D.py:19-57 (its `if id is None` branch is dead: `id` is the builtin)."""
+        import os
+
+        self.save_dir = os.path.join(root_dir, exp_name, "test_results", str(version), test_split)
+        self.save_input_dir = os.path.join(self.save_dir, "input")
+        self.save_gt_dir = os.path.join(self.save_dir, "gt_seg")
+        self.save_pred_dir = os.path.join(self.save_dir, "pred_seg")
+        self.save_pred_prob_dir = os.path.join(self.save_dir, "pred_prob")
+        dirs = [self.save_dir, self.save_input_dir, self.save_gt_dir, self.save_pred_dir, self.save_pred_prob_dir]
+        if sigma_save_dir:
+            self.save_pred_sigma_dir = os.path.join(self.save_dir, "sigma")
+            dirs.append(self.save_pred_sigma_dir)
+        for d in dirs:
+            os.makedirs(d, exist_ok=True)
+
+    def save_data(self, root_dir: str, exp_name: str, version: int, org_data_path: str = None,
+                  test_split: str = "id") -> None:
+        """Drop-in for data_carrier_3D.py:181-371: same directories, file names, dtypes (fp64 maps,
+        probabilities, image and labels; uint8 segmentations) and arithmetic; files are written by
+        values_b200.formats.save_from_device instead of medpy.io.save."""
+        import os
+
+        from . import formats
+
+        sigma_save_dir = "sigma" in list(self.data.values())[0]
+        self._create_save_dirs(root_dir, exp_name, version, sigma_save_dir, test_split)
+        clip_min = 1.0 if self.patch_weight is None else 0.0
+        for key, value in self.data.items():
+            name = key.split("/")[-1].split(".")[0]
+            cnt = value["_count"]
+            norm = self.normalized(key)
+            header = False
+            if org_data_path:
+                _, header = formats.load(os.path.join(org_data_path, name + ".nii.gz"))
+            data = normalize_maps(value["data"].unsqueeze(0), cnt, clip_min)[0]
+            formats.save_from_device(data, os.path.join(self.save_input_dir, name + ".nii.gz"), header)
+            if value["seg"].shape[0] > 0:
+                gt_seg = normalize_maps(value["seg"].to(torch.float64), cnt, clip_min)   # int32 / fp64 -> fp64
+                for seg_idx in range(gt_seg.shape[0]):
+                    formats.save_from_device(gt_seg[seg_idx], os.path.join(
+                        self.save_gt_dir, "{}_{}.nii.gz".format(name, str(seg_idx).zfill(2))), header)
+            softmax_pred = norm["softmax_pred"]
+            if softmax_pred.shape[0] > 1:
+                formats.save_from_device(norm["mean_seg"], os.path.join(
+                    self.save_pred_dir, "{}_{}.nii.gz".format(name, "mean")), header)
+                mean_softmax_pred = norm["mean_softmax_pred"]
+                for class_idx in range(mean_softmax_pred.shape[0]):
+                    formats.save_from_device(mean_softmax_pred[class_idx], os.path.join(
+                        self.save_pred_prob_dir,
+                        "{}_{}_{}.nii.gz".format(name, "mean", str(class_idx + 1).zfill(2))), header)
+            if sigma_save_dir and "sigma" in value:
+                n_pred, n_cls = value["sigma"].shape[:2]
+                sigma = normalize_maps(value["sigma"].reshape((n_pred * n_cls,) + tuple(cnt.shape)), cnt,
+                                       clip_min).reshape(value["sigma"].shape)
+            for pred_idx in range(softmax_pred.shape[0]):
+                formats.save_from_device(norm["pred_seg"][pred_idx], os.path.join(
+                    self.save_pred_dir, "{}_{}.nii.gz".format(name, str(pred_idx + 1).zfill(2))), header)
+                for class_idx in range(softmax_pred.shape[1]):
+                    formats.save_from_device(softmax_pred[pred_idx, class_idx], os.path.join(
+                        self.save_pred_prob_dir, "{}_{}_{}.nii.gz".format(
+                            name, str(pred_idx + 1).zfill(2), str(class_idx + 1).zfill(2))), header)
+                    if "sigma" in value and pred_idx == 0:
+                        formats.save_from_device(sigma[pred_idx, class_idx], os.path.join(
+                            self.save_pred_sigma_dir, "{}_{}.nii.gz".format(name, str(class_idx + 1).zfill(2))),
+                            header)
+            for unc in MAP_KEYS:
+                if unc in value:
+                    unc_dir = os.path.join(self.save_dir, unc)
+                    os.makedirs(unc_dir, exist_ok=True)
+                    formats.save_from_device(norm[unc], os.path.join(unc_dir, name + ".nii.gz"), header)
 
     def numpy_data(self) -> Dict[str, Dict]:
         """The reference's `.data` layout with numpy arrays (torch fp32 maps stay torch CPU
