@@ -44,11 +44,31 @@ _PATCHES = {
 }
 
 
-def install(import_missing: bool = False) -> dict:
+def _file_io_patches() -> dict:
+    """SURVEY 8 f4, opt-in: the reference's medpy.io.load / save names and its ExperimentDataloader.
+    (Our ExperimentDataloader does not instantiate hydra datamodule configs; experiments that set
+    `datamodule_config` should keep the reference class and only take the load / save rebinding.)"""
+    from . import experiment_dataloader, formats
+
+    io = {"load": formats.load, "save": formats.save}
+    return {
+        "uncertainty_modeling.data_carrier_3D": dict(io),
+        "evaluation.experiment_dataloader": dict(io, ExperimentDataloader=experiment_dataloader.ExperimentDataloader),
+        "evaluation.uncertainty_aggregation.aggregate_uncertainties": {"load": formats.load},
+        "evaluation.uncertainty_aggregation.find_threshold": {"load": formats.load},
+    }
+
+
+def install(import_missing: bool = False, file_io: bool = False) -> dict:
     """Rebind the hot-path names in every reference module that is already imported (or, with
-    import_missing=True, importable).  Returns {module: {name: original}} for `uninstall`."""
+    import_missing=True, importable); file_io=True also rebinds the medpy.io names and
+    ExperimentDataloader.  Returns {module: {name: original}} for `uninstall`."""
     saved = {}
-    for mod_name, names in _PATCHES.items():
+    patches = {k: dict(v) for k, v in _PATCHES.items()}
+    if file_io:
+        for mod_name, names in _file_io_patches().items():
+            patches.setdefault(mod_name, {}).update(names)
+    for mod_name, names in patches.items():
         mod = sys.modules.get(mod_name)
         if mod is None and import_missing:
             try:

@@ -268,13 +268,14 @@ def calculate_threshold_image(quantile_path, image, method: str, distributed: bo
 def find_threshold(results_dict: Dict, quantile_path, save_path, load_fn=None) -> Dict:
     """Drop-in for find_threshold.py:71-117, to its evident intent: the reference calls
     calculate_threshold_image with two arguments (:94) although it takes three; the quantile file
-    is the missing first argument.  `load_fn(path) -> ndarray` defaults to medpy.io.load.
+    is the missing first argument.  `load_fn(path) -> ndarray or CUDA tensor` defaults to
+    values_b200.formats.load_to_device (medpy.io.load's result, on the device).
     Returns the dict it writes to threshold_analysis.json."""
     if load_fn is None:
-        from medpy.io import load as _medpy_load  # not installed in the build image
+        from .formats import load_to_device
 
         def load_fn(path):
-            return _medpy_load(path)[0]
+            return load_to_device(path)[0]
 
     if not os.path.isfile(quantile_path):
         quantile_path = Path(quantile_path) / "quantile_analysis.json"
