@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Small K2b / formats run for compute-sanitizer (memcheck, racecheck) on the GPU box:
+
+    compute-sanitizer --tool racecheck python tools/sanitize_k2.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import values_b200 as vb
+from values_b200 import _lib
+
+g = torch.Generator(device="cuda").manual_seed(1)
+for shape in [(40, 64, 96), (23, 50, 76)]:
+    maps = torch.rand((3,) + shape, generator=g, device="cuda")
+    ref = None
+    for path in (5, 6, 0):
+        _lib.lib.values_debug_set_patch_path(path)
+        s, b = vb.patch_max(maps, 10)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = (s.clone(), b.clone())
+        assert torch.equal(ref[1], b) and torch.allclose(ref[0], s, rtol=1e-13, atol=0), (shape, path)
+_lib.lib.values_debug_set_patch_path(0)
+x = torch.rand((33, 17, 70), generator=g, device="cuda")
+assert torch.equal(vb.reverse_axes(x), x.permute(2, 1, 0).contiguous())
+torch.cuda.synchronize()
+print("sanitize_k2: ok")
