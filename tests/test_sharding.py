@@ -39,6 +39,12 @@ def _worker(rank, world, port, n_items, out_dir):
     local = torch.arange(lo, hi, dtype=torch.float64).unsqueeze(1) * torch.tensor([1.0, 10.0, 100.0], dtype=torch.float64)
     full = gather_scores(local, n_items)
     torch.save(full, os.path.join(out_dir, f"r{rank}.pt"))
+    from values_b200.sharding import AsyncScoreGather
+
+    g = AsyncScoreGather(torch.device("cpu"))        # no CUDA: the synchronous gather behind the same API
+    again = g.submit(local, n_items)
+    g.wait()
+    assert torch.equal(again, full)
     try:
         gather_scores(local[:-1] if hi > lo else torch.zeros(1, 3, dtype=torch.float64), n_items)
         raised = False

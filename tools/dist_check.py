@@ -52,6 +52,18 @@ def main():
     if not torch.equal(full[:, 0], torch.arange(n_items, device=dev, dtype=torch.float64)):
         ok = False
         print(f"rank {rank}: gather_scores mismatch", flush=True)
+    # the same gather on a side stream, several in flight, while the main stream keeps computing
+    gat = vb.AsyncScoreGather(dev)
+    outs = []
+    for k in range(6):
+        tab = local_tab + 1000.0 * k
+        outs.append(gat.submit(tab, n_items))
+        torch.rand(1 << 24, device=dev).sum()          # main-stream work the gathers overlap with
+    gat.wait()
+    for k, out in enumerate(outs):
+        if not torch.equal(out[:, 0], torch.arange(n_items, device=dev, dtype=torch.float64) + 1000.0 * k):
+            ok = False
+            print(f"rank {rank}: AsyncScoreGather mismatch at {k}", flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

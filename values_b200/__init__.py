@@ -17,7 +17,7 @@ from .metrics import (calc_ace, calib_stats, calibration_error, calibration_erro
                       compute_ncc, ncc_batched, ncc_main, platt_scale_confid)
 from .pipeline import AggregationConfig, PipelineResult, UncertaintyPipeline
 from .segmetrics import calculate_ged, confusion_counts, dice_from_confusion, mean_prediction_dice
-from .sharding import gather_scores, shard_range, shard_sizes
+from .sharding import AsyncScoreGather, gather_scores, shard_range, shard_sizes
 from .stitching import gaussian_importance_map, patch_grid, stitch_accumulate, stitch_volume
 from .threshold import (calculate_foreground_quantile_image, calculate_threshold_image,
                         count_nonzero, find_threshold, get_foreground_quantile, quantile,
@@ -33,7 +33,7 @@ __all__ = [
     "aggregate_uncertainties", "patch_max", "map_reduce", "normalize_maps",
     "DataCarrier3D", "patch_grid", "stitch_accumulate", "stitch_volume", "gaussian_importance_map",
     "UncertaintyPipeline", "AggregationConfig", "PipelineResult",
-    "shard_range", "shard_sizes", "gather_scores",
+    "shard_range", "shard_sizes", "gather_scores", "AsyncScoreGather",
     "calculate_foreground_quantile_image", "get_foreground_quantile", "save_foreground_quantiles",
     "calculate_threshold_image", "find_threshold", "quantile", "count_nonzero",
     "compute_ncc", "ncc_batched", "ncc_main", "calib_stats", "calc_ace", "platt_scale_confid",

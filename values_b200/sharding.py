@@ -45,3 +45,37 @@ def gather_scores(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor
     dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
     out = out.view((world, pad) + tuple(tail))
     return torch.cat([out[r, : sizes[r]] for r in range(world)], dim=0)
+
+
+class AsyncScoreGather:
+    """The score gather on a side stream, so that a rank's next batch does not wait for the slowest
+    rank's current one: `submit` orders the all_gather after the work already queued on the current
+    stream and returns at once; `wait` makes the current stream wait for every gather submitted so
+    far (call it before reading a table, and before the end of a timed region).  Without CUDA
+    (gloo tests) it degrades to the synchronous `gather_scores`."""
+
+    def __init__(self, device=None, group=None, keep: int = 4):
+        self.group = group
+        self.keep = keep
+        self._tables = []   # the last `keep` results (and their inputs) stay referenced until waited for
+        self.stream = None
+        if device is not None and torch.device(device).type == "cuda":
+            self.device = torch.device(device)
+            self.stream = torch.cuda.Stream(self.device)
+
+    def submit(self, local: torch.Tensor, n_items: int) -> torch.Tensor:
+        if self.stream is None:
+            return gather_scores(local, n_items, self.group)
+        main = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(main)
+        with torch.cuda.stream(self.stream):
+            out = gather_scores(local, n_items, self.group)
+        local.record_stream(self.stream)
+        self._tables.append((local, out))
+        if len(self._tables) > self.keep:
+            self._tables.pop(0)
+        return out
+
+    def wait(self) -> None:
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
