@@ -92,3 +92,34 @@ def test_experiment_dataloader_mirror_matches_reference_class(ref, tmp_path):
             np.testing.assert_array_equal(a.get_max_softmax_pred(image_id), b.get_max_softmax_pred(image_id))
             for unc in a.unc_path_dict:
                 np.testing.assert_array_equal(a.get_unc_map(image_id, unc), b.get_unc_map(image_id, unc))
+
+
+def test_patch_install_rebinds_and_restores_reference_names(ref):
+    """values_b200.patch.install() puts the B200 path behind the
+    reference's own module attributes (which is also how hydra resolves its `_target_` strings),
+    uninstall() restores them.  Rebinding only -- nothing is computed here."""
+    import importlib
+
+    import values_b200 as vb
+    import values_b200.patch as patch
+
+    t3d, dc, agg = ref.modules["test_3D"], ref.modules["data_carrier_3D"], ref.modules["aggregate_uncertainties"]
+    edl = importlib.import_module("evaluation.experiment_dataloader")
+    before = (t3d.calculate_uncertainty, dc.DataCarrier3D, agg.patch_level_aggregation, dc.save, edl.ExperimentDataloader)
+    saved = patch.install(file_io=True)
+    try:
+        assert t3d.calculate_uncertainty is vb.calculate_uncertainty
+        assert t3d.caculcate_uncertainty_multiple_pred is vb.caculcate_uncertainty_multiple_pred
+        assert dc.DataCarrier3D is vb.DataCarrier3D
+        target = "evaluation.uncertainty_aggregation.aggregate_uncertainties.patch_level_aggregation"
+        mod, _, name = target.rpartition(".")
+        assert getattr(importlib.import_module(mod), name) is vb.patch_level_aggregation      # hydra's lookup
+        assert agg.aggregate_uncertainties is vb.aggregate_uncertainties
+        assert ref.modules["find_threshold"].find_threshold is vb.find_threshold
+        assert ref.modules["ncc"].compute_ncc is vb.compute_ncc and ref.modules["ace"].calc_ace is vb.calc_ace
+        assert dc.save is vb.formats.save and edl.load is vb.formats.load
+        assert edl.ExperimentDataloader is vb.ExperimentDataloader
+    finally:
+        patch.uninstall(saved)
+    after = (t3d.calculate_uncertainty, dc.DataCarrier3D, agg.patch_level_aggregation, dc.save, edl.ExperimentDataloader)
+    assert all(a is b for a, b in zip(before, after))

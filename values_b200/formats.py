@@ -198,8 +198,7 @@ def _nifti_header_bytes(shape_xyz: Sequence[int], dtype: np.dtype, hdr) -> bytes
             c = 0.5 * np.sqrt(yd); b = 0.25 * (rot[0, 1] + rot[1, 0]) / c; d = 0.25 * (rot[1, 2] + rot[2, 1]) / c
         else:
             d = 0.5 * np.sqrt(zd); b = 0.25 * (rot[0, 2] + rot[2, 0]) / d; c = 0.25 * (rot[1, 2] + rot[2, 1]) / d
-    pixdim = [qfac] + spacing + [1.0] * (7 - nd) if nd < 7 else [qfac] + spacing
-    pixdim = (pixdim + [0.0] * 8)[:8]
+    pixdim = [qfac] + spacing + [1.0] * (7 - nd)
     itemsize = np.dtype(dtype).itemsize
     return _HDR.pack(
         348, b"", b"", 0, 0, b"r", 0, *dim, 0.0, 0.0, 0.0, 0, code, 8 * itemsize, 0,
