@@ -236,6 +236,11 @@ void values_debug_set_k1_variant(int variant);
  * 1 streaming two-kernel path, 2 generic tiled path, 4 fused tile kernel, 5 march kernel without its
  * fp32 filter pass, 6 march kernel behind its own fp32 instantiation instead of the vector filter. */
 void values_debug_set_patch_path(int path);
+/* Pure host function: the error bound of K2b's fp32 filter pass, |fp32 box sum - exact box sum| <=
+ * coef * max |input| for 10x10 in-plane patches, z-chunks of zc output planes and p0 planes per window
+ * (vector_kernel: 1 = box_filter_kernel, 0 = the march kernel's fp32 instantiation).
+ * tests/test_filter_bound.py checks it against an emulation of the kernels' operation order. */
+double values_patch_filter_err_coef(int zc, int p0, int vector_kernel);
 /* K3 implementation: 0 automatic (vector kernel when rows are 16-byte aligned), 1 scalar kernel. */
 void values_debug_set_stitch_path(int path);
 

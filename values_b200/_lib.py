@@ -63,6 +63,7 @@ def _load() -> C.CDLL:
                                               i64, pdbl, C.c_int, vp, vp, sz, vp]),
         "values_confusion_counts": (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, i64, C.c_int, vp, vp]),
         "values_reverse_axes": (C.c_int, [vp, vp, C.c_int, i64, i64, i64, vp]),
+        "values_patch_filter_err_coef": (dbl, [C.c_int, C.c_int, C.c_int]),
         "values_debug_set_k1_iter": (None, [C.c_int]),
         "values_debug_set_k1_variant": (None, [C.c_int]),
         "values_debug_set_patch_path": (None, [C.c_int]),
@@ -86,7 +87,7 @@ EXPORTED = [
     "values_normalize_maps", "values_count_nonzero", "values_radix_histogram",
     "values_min_key_above", "values_pair_moments_workspace_bytes", "values_pair_moments",
     "values_calib_bins_workspace_bytes", "values_calib_bins", "values_calib_bins_fused",
-    "values_confusion_counts", "values_reverse_axes",
+    "values_confusion_counts", "values_reverse_axes", "values_patch_filter_err_coef",
     "values_debug_set_k1_iter", "values_debug_set_k1_variant",
     "values_debug_set_patch_path", "values_debug_set_stitch_path",
 ]

@@ -1463,7 +1463,7 @@ static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
         return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute(%zu) failed", smem);
     prm.use_list = filter ? 1 : 0;
     prm.err_coef = vec ? filter_err_coef(prm.zc, prm.p0, 10, FT::XRUN - 1, FT::YRUN - 1)
-                       : filter_err_coef(prm.zc, prm.p0, 10, MT::SEG / 2 - 1, MT::RUN / 2 - 1);
+                       : filter_err_coef(prm.zc, prm.p0, 10, MT::SEG / 2 - 1, MT::RUN / 2 - 1);   // == values_patch_filter_err_coef
     for (int64_t m0 = 0; m0 < M; m0 += 65535) {  // gridDim.y limit
         const int64_t mc = std::min<int64_t>(65535, M - m0);
         FusedParams q = prm;
@@ -1696,3 +1696,11 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
 }
 
 extern "C" void values_debug_set_patch_path(int path) { g_patch_path = path; }
+
+extern "C" double values_patch_filter_err_coef(int zc, int p0, int vector_kernel) {
+    using MT = MarchTile<32, 64, 10>;
+    using FT = FilterTile;
+    if (zc <= 0 || p0 <= 0) return 0.0;
+    return vector_kernel ? filter_err_coef(zc, p0, 10, FT::XRUN - 1, FT::YRUN - 1)
+                         : filter_err_coef(zc, p0, 10, MT::SEG / 2 - 1, MT::RUN / 2 - 1);
+}
