@@ -119,7 +119,8 @@ def test_c2_vs_oracle(vb, vo, n, c, spatial, dtype):
 
 
 @pytest.mark.parametrize("n,c,spatial,dtype", [
-    (16, 4, (64, 64, 40), torch.float32),   # RS = 4 stages
+    (16, 4, (64, 64, 40), torch.float32),   # RS = 8 (two sub-batches of 4); variants 13 / 14: RS = 4 / 8 x 3 stages
+    (12, 3, (40, 64, 24), torch.float32),   # RS = 4
     (10, 20, (96, 132), torch.float32),     # RS = 5
     (6, 3, (50, 64), torch.float32),        # RS = 2, ragged last tile
     (7, 5, (40, 52), torch.float32),        # RS = 1
@@ -132,7 +133,7 @@ def test_k1_kernels_agree(vb, n, c, spatial, dtype):
     x = softmax_stack(n * 7 + c, 3 * n, c, spatial).reshape(3, n, c, *spatial).to(dtype).cuda()
     outs = []
     try:
-        for variant, it in [(0, 0), (0, 1), (0, 3), (8, 0), (8, 2)]:
+        for variant, it in [(0, 0), (0, 1), (0, 3), (8, 0), (8, 2), (13, 0), (14, 0)]:
             vb._lib.lib.values_debug_set_k1_variant(variant)
             vb._lib.lib.values_debug_set_k1_iter(it)
             r = vb.uncertainty_fused(x, mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05))

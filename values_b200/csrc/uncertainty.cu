@@ -715,24 +715,30 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
         for (int c = 0; c < C; ++c) {
             for (int n = 0; n < N; n += RS) {
                 mbar_wait(full_bar + stage, phase);
-                Raw<T, VEC> raw[RS];
+                // rows of a stage are consumed SB at a time (registers), the stage is one mbarrier round trip
+                constexpr int SB = RS > 5 ? RS / 2 : RS;
+                static_assert(RS % SB == 0, "sub-batches");
 #pragma unroll
-                for (int u = 0; u < RS; ++u) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(ring + stage * kStageBytes + u * kRowBytes + tid * 16);
-                    raw[u].w[0] = q.x; raw[u].w[1] = q.y; raw[u].w[2] = q.z; raw[u].w[3] = q.w;
-                }
-                if (EARLY) {   // hand the slot back as soon as the warp has read it
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty_bar + stage);
-                }
-                if (active) {
+                for (int h = 0; h < RS; h += SB) {
+                    Raw<T, VEC> raw[SB];
 #pragma unroll
-                    for (int u = 0; u < RS; ++u) {
-                        A p[VEC];
-                        unpack(raw[u], p);
-                        if (M::kFlagged) bad |= sign_or(raw[u]);
-                        add_rows<VEC>(S, p);
-                        M::rows(e, p);
+                    for (int u = 0; u < SB; ++u) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(ring + stage * kStageBytes + (h + u) * kRowBytes + tid * 16);
+                        raw[u].w[0] = q.x; raw[u].w[1] = q.y; raw[u].w[2] = q.z; raw[u].w[3] = q.w;
+                    }
+                    if (EARLY && h + SB == RS) {   // hand the slot back as soon as the warp has read it
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty_bar + stage);
+                    }
+                    if (active) {
+#pragma unroll
+                        for (int u = 0; u < SB; ++u) {
+                            A p[VEC];
+                            unpack(raw[u], p);
+                            if (M::kFlagged) bad |= sign_or(raw[u]);
+                            add_rows<VEC>(S, p);
+                            M::rows(e, p);
+                        }
                     }
                 }
                 if (!EARLY) {
@@ -957,12 +963,19 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, cudaStream_t st) 
         if constexpr (sizeof(T) != 8) {
             // default: bulk-copy ring, RS samples per stage (one mbarrier round trip per stage)
             if (v == 0) {
+                // N = 8k (MC-dropout / TTA 8, 16): 8 rows per stage, consumed 4 at a time -- half the
+                // mbarrier round trips and loop overhead per element (K1 is issue-bound, not HBM-bound:
+                // 70 % issue slots); measured on cfg5 0.90 -> 0.94 of the HBM peak at 24 volumes per
+                // launch, equal at 8, outputs bit-identical
+                if (prm.N % 8 == 0) return launch_tma<T, NV, 3, 8, 2>(prm, B, st);
                 if (prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4>(prm, B, st);
                 if (prm.N % 5 == 0) return launch_tma<T, NV, 3, 5, 3>(prm, B, st);
                 if (prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8>(prm, B, st);
                 return launch_tma<T, NV, 3, 1, 8>(prm, B, st);
             }
             if (v == 5) return launch_tma<T, NV, 3, 1, 8>(prm, B, st);
+            if (v == 13 && prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4>(prm, B, st);   // 4 rows per stage, 4 stages
+            if (v == 14 && prm.N % 8 == 0) return launch_tma<T, NV, 2, 8, 3>(prm, B, st);
             if (v == 7 && prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4, true>(prm, B, st);  // racy on purpose (test)
             if (v == 10 && prm.N % 5 == 0) return launch_tma<T, NV, 2, 5, 4>(prm, B, st);
             if (v == 11 && prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8>(prm, B, st);
