@@ -626,6 +626,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      " selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t a, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     " selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t a) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 q;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a) : "memory");
+    return q;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -691,6 +706,14 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
     // ---------------- consumers
     const A Nf = (A)prm.N;
     const int lane = tid & 31;
+    // Shared-memory addresses and per-tile flags live in registers the compiler cannot re-derive
+    // (the empty asm makes them opaque): at the 72-register cap it otherwise rebuilds them from
+    // %tid / %cluster_ctaid and a 64-bit compare in EVERY stage -- ~20 of 420 instructions, and K1 is
+    // issue-bound.
+    uint32_t ring_tid = smem_u32(ring) + (uint32_t)tid * 16u;
+    uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    int is_lane0 = lane == 0;
+    asm volatile("" : "+r"(ring_tid), "+r"(full0), "+r"(empty0), "+r"(is_lane0));
     double psum[6];
     int pcnt[3];
 #pragma unroll
@@ -703,7 +726,8 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
         const int64_t t0 = (blk * prm.iter + it) * tile_vox;
         if (t0 >= prm.V) break;                     // uniform: the producer stops at the same tile
         const int64_t v0 = t0 + (int64_t)tid * VEC;
-        const bool active = v0 < prm.V;             // only the last tile of a volume is ragged
+        int active = v0 < prm.V;                    // only the last tile of a volume is ragged
+        asm volatile("" : "+r"(active));
         A S[VEC], best[VEC];
         float e[VEC], E[VEC], PE[VEC], Sacc[VEC];
         int idx[VEC];
@@ -714,7 +738,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
         }
         for (int c = 0; c < C; ++c) {
             for (int n = 0; n < N; n += RS) {
-                mbar_wait(full_bar + stage, phase);
+                mbar_wait_addr(full0 + stage * 8, phase);
                 // rows of a stage are consumed SB at a time (registers), the stage is one mbarrier round trip
                 constexpr int SB = RS > 5 ? RS / 2 : RS;
                 static_assert(RS % SB == 0, "sub-batches");
@@ -723,12 +747,12 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                     Raw<T, VEC> raw[SB];
 #pragma unroll
                     for (int u = 0; u < SB; ++u) {
-                        const uint4 q = *reinterpret_cast<const uint4*>(ring + stage * kStageBytes + (h + u) * kRowBytes + tid * 16);
+                        const uint4 q = lds128(ring_tid + stage * kStageBytes + (h + u) * kRowBytes);
                         raw[u].w[0] = q.x; raw[u].w[1] = q.y; raw[u].w[2] = q.z; raw[u].w[3] = q.w;
                     }
                     if (EARLY && h + SB == RS) {   // hand the slot back as soon as the warp has read it
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(empty_bar + stage);
+                        if (is_lane0) mbar_arrive_addr(empty0 + stage * 8);
                     }
                     if (active) {
 #pragma unroll
@@ -748,7 +772,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                     // stage, and that arithmetic cannot issue before the loads complete.
                     asm volatile("" ::"f"(e[0]), "r"(bad) : "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(empty_bar + stage);
+                    if (is_lane0) mbar_arrive_addr(empty0 + stage * 8);
                 }
                 if (++stage == kTmaStages) { stage = 0; phase ^= 1u; }
             }
