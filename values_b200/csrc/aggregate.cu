@@ -1260,7 +1260,10 @@ __device__ __forceinline__ unsigned int or4(unsigned int acc, float4 v) {
 // rows on two warps (fewer instructions, longer per-warp chain) 569 us; 384 threads at 80 registers
 // (24 warps / SM, two float4 slots per thread, 8-output x tasks) 668 us -- more instructions and the
 // one-plane prefetch distance no longer covers the L2 latency; the y-stage as 2 columns x 4 rows on
-// all eight warps (even work per warp, 3.25 instead of 2.1 shared loads per output) 644 us total vs 507.
+// all eight warps (even work per warp, 3.25 instead of 2.1 shared loads per output) 644 us total vs 507;
+// x / y task addresses held in opaque registers (what lifted K1, which is issue-bound): 87 fewer
+// instructions in the loop, no change in time -- this kernel waits on barriers and shared-memory
+// round trips, not on issue slots.
 __global__ void __launch_bounds__(FilterTile::NT, 2) box_filter_kernel(const FusedParams prm) {
     using FT = FilterTile;
     constexpr int NT = FT::NT, PC = FT::PC;
