@@ -255,6 +255,7 @@ def main():
     ap.add_argument("--pool", type=int, default=0, help="override volumes per rank per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap", action="store_true", help="K2b + score assembly on a side stream under the next K1")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.pool:
@@ -290,7 +291,10 @@ def main():
     thr = tuple(float(torch.quantile(m.reshape(-1)[sub].float(), 0.98).item())
                 for m in (pilot.pred_entropy, pilot.expected_entropy, pilot.mutual_information))
     del pilot
-    cfg = vb.AggregationConfig(patch_size=wl["patch"], thresholds=thr)
+    # --overlap: K2b and the score assembly of a batch run on a side stream under K1 of the next batch
+    # (+2-4 % throughput on cfg5; off by default because K1's launch time then includes the contention
+    # and no longer measures the kernel against its roofline)
+    cfg = vb.AggregationConfig(patch_size=wl["patch"], thresholds=thr, overlap=args.overlap)
     pipe = vb.UncertaintyPipeline(cfg)
     k1_events = []
     pipe.k1_timer = k1_events  # (start, end, n_volumes) per K1 launch, recorded on the launch stream
@@ -301,10 +305,10 @@ def main():
 
     def step():
         res = pipe.run(stack, mean_argmax=True)
-        table = res.scores.reshape(pool, -1)
         if world > 1:
-            table = gatherer.submit(table, pool * world)
-        return table
+            table, ready = res.table_async()
+            gatherer.submit(table.reshape(pool, -1), pool * world, after=ready)
+        return res
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -321,7 +325,8 @@ def main():
     with ClockSampler(local_rank) as clocks:
         e0.record()
         for _ in range(args.steps):
-            table = step()
+            res = step()
+        res.wait()                  # the main stream waits for the last batch's K2b + score table
         if world > 1:
             gatherer.wait()
         e1.record()
@@ -383,6 +388,8 @@ def main():
                        "pool_bytes_per_rank": pool_bytes,
                        "l2": "inputs (pool >> 126 MB L2) stream from HBM every step",
                        "map_chunk_bytes": cfg.chunk_bytes,
+                       "streams": "K2b + score assembly on a side stream under the next batch's K1" if cfg.overlap
+                                  else "single stream",
                        "aggregations": "image_level + threshold(0.98-quantile pilot) + patch_level(10)",
                        "sharding": f"volumes sharded over {world} rank(s), score table all_gather per step"
                                    + (" on a side stream" if world > 1 else "")},

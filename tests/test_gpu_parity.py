@@ -573,6 +573,26 @@ def test_pipeline_chunking_and_overlap_do_not_change_results(vb):
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
 
 
+def test_pipeline_overlap_across_runs(vb):
+    """Overlap mode lets run() return with K2b and the score assembly still queued on the side stream:
+    back-to-back runs on DIFFERENT inputs (scratch maps alternate, per-run score buffers) must each
+    give the single-stream result, whenever the tables are read."""
+    B, n, c, spatial = 3, 4, 3, (40, 44, 64)
+    xs = [softmax_stack(200 + i, B * n, c, spatial).reshape(B, n, c, *spatial).cuda() for i in range(5)]
+    thr = (0.5, 0.4, 0.03)
+    plain = vb.UncertaintyPipeline(vb.AggregationConfig(patch_size=10, thresholds=thr))
+    want = [plain.run(x, mean_argmax=True).scores.clone() for x in xs]
+    torch.cuda.synchronize()
+    pipe = vb.UncertaintyPipeline(vb.AggregationConfig(patch_size=10, thresholds=thr, overlap=True))
+    for _ in range(3):
+        res = [pipe.run(x, mean_argmax=True) for x in xs]          # nothing waits in between
+        assert all(r.ready is not None for r in res)
+        for r, w in zip(reversed(res), reversed(want)):             # read in any order
+            assert torch.equal(r.scores, w)
+    table, ready = res[0].table_async()
+    assert ready is res[0].ready and table is res[0]._scores
+
+
 def test_full_size_properties(vb):
     """BASELINE sizes, checked through size-independent properties (no oracle at this size)."""
     n, c, s = 16, 4, (128, 128, 128)

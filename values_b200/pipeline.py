@@ -34,20 +34,39 @@ class AggregationConfig:
                                                # K2b's 32x64x(z-chunk) tiles need ~100 maps per launch
                                                # to fill 148 SMs x 2 CTAs for several waves; measured
                                                # 4.28 ms/step at 256 MB -> 4.05 ms at 1 GB on cfg5)
-    overlap: bool = False                      # run K2b of chunk i on a second stream under K1 of chunk
-                                               # i+1 (K1 is HBM-bound, K2b shared-memory/issue-bound);
-                                               # costs a second map scratch buffer
+    overlap: bool = False                      # K2b and the score assembly run on a second stream, under
+                                               # K1 of the next chunk -- also of the NEXT run() (K1 is
+                                               # HBM-bound, K2b latency-bound); costs a second map scratch
+                                               # buffer.  The result's `scores` wait for that stream when
+                                               # they are first touched (PipelineResult.wait)
 
 
 @dataclass
 class PipelineResult:
-    scores: torch.Tensor                       # [B, 3, N_COLS] fp64, device; map order pe, ee, mi
+    _scores: torch.Tensor                      # [B, 3, N_COLS] fp64, device; map order pe, ee, mi
     maps: Optional[torch.Tensor] = None        # [3, B, *S] fp32 if kept
     mean_argmax: Optional[torch.Tensor] = None  # [B, *S] uint8
     ssn: bool = False
     patch_size: Optional[List[int]] = None
     thresholds: Optional[Sequence[float]] = None
     threshold_mean: bool = True
+    ready: Optional[torch.cuda.Event] = None   # overlap mode: recorded on the side stream once the table is complete
+
+    def wait(self) -> "PipelineResult":
+        """Make the current stream wait for the score table (a no-op outside overlap mode, where the
+        table is produced in stream order).  Never blocks the host."""
+        if self.ready is not None:
+            torch.cuda.current_stream(self._scores.device).wait_event(self.ready)
+        return self
+
+    @property
+    def scores(self) -> torch.Tensor:
+        return self.wait()._scores
+
+    def table_async(self):
+        """(score table, event or None): the table WITHOUT making the current stream wait for it -- for
+        consumers that order themselves behind the event (AsyncScoreGather.submit(..., after=event))."""
+        return self._scores, self.ready
 
     def map_index(self, unc_type: str) -> int:
         """Row of the score table for a reference uncertainty key (SSN swaps EE and MI)."""
@@ -89,7 +108,9 @@ class PipelineResult:
 class UncertaintyPipeline:
     """K1 -> K2b over chunks of volumes with every buffer preallocated and reused: per chunk
     the host issues two C-ABI calls (one K1 launch + a 4-byte memset, two K2b launches) and
-    nothing else; the score table is assembled once per run.  Never synchronises."""
+    nothing else; the score table is assembled once per run.  Never synchronises the host.
+    With cfg.overlap the K2b launches and the assembly go to a side stream and run() returns with the
+    main stream free for the next run's K1."""
 
     def __init__(self, cfg: Optional[AggregationConfig] = None):
         self.cfg = cfg or AggregationConfig()
@@ -97,7 +118,7 @@ class UncertaintyPipeline:
         # optional list; when set, (start_event, end_event, n_volumes) is appended per K1 launch
         # (CUDA events on the launching stream -- bench.py's roofline measurement)
         self.k1_timer: Optional[list] = None
-        self._side: Dict[torch.device, torch.cuda.Stream] = {}
+        self._side: Dict[torch.device, dict] = {}
 
     def _chunk(self, B: int, V: int) -> int:
         per_volume = 3 * V * 4  # three fp32 maps
@@ -109,6 +130,8 @@ class UncertaintyPipeline:
         n = int(np.prod(shape)) if len(shape) else 1
         t = self._bufs.get(key)
         if t is None or t.numel() < n:
+            if t is not None and dev in self._side:   # the side stream may still be using the old scratch
+                torch.cuda.current_stream(dev).wait_stream(self._side[dev]["stream"])
             t = torch.empty(max(n, 1), dtype=dtype, device=dev)
             self._bufs[key] = t
         return t[:n].view(shape)
@@ -129,34 +152,45 @@ class UncertaintyPipeline:
         if thr is not None and ssn:
             thr = (thr[0], thr[2], thr[1])
         cb = self._chunk(B, V)
-        overlap = cfg.overlap and patch is not None and B > cb
+        overlap = cfg.overlap and patch is not None
         if overlap:
             main = torch.cuda.current_stream(dev)
-            side = self._side.get(dev)
-            if side is None:
-                side = self._side[dev] = torch.cuda.Stream(dev, priority=-1)
-            side.wait_stream(main)
-            k2_done = [None, None]
+            st = self._side.get(dev)
+            if st is None:   # side stream, the K2b-done event of each scratch buffer, the buffer to use next
+                st = self._side[dev] = {"stream": torch.cuda.Stream(dev, priority=-1), "done": [None, None], "next": 0}
+            side = st["stream"]
         if keep_maps:   # K1 writes straight into the kept [B, 3, *S] buffer, chunk by chunk
             maps_all = torch.empty((B, 3) + spatial, dtype=torch.float32, device=dev)
         else:
             maps_buf = self._buf("maps", (cb, 3) + spatial, torch.float32, dev)
             maps_buf2 = self._buf("maps2", (cb, 3) + spatial, torch.float32, dev) if overlap else maps_buf
-        k1_scores = self._buf("k1_scores", (B, 3, 3), torch.float64, dev)
+        if overlap:   # per-run outputs: the side stream may still be reading the previous run's
+            k1_scores = torch.empty((B, 3, 3), dtype=torch.float64, device=dev)
+        else:
+            k1_scores = self._buf("k1_scores", (B, 3, 3), torch.float64, dev)
         am = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev) if mean_argmax else None
         k1_ws_bytes = _lib.lib.values_uncertainty_workspace_bytes(cb, V, _lib.dtype_code(probs.dtype))
         k1_ws = self._buf("k1_ws", (max(k1_ws_bytes, 8),), torch.uint8, dev)
         if patch is not None:
-            ps = self._buf("patch_score", (B * 3,), torch.float64, dev)
-            bb = self._buf("patch_bbox", (B * 3, 3), torch.int64, dev)
+            if overlap:
+                ps = torch.empty((B * 3,), dtype=torch.float64, device=dev)
+                bb = torch.empty((B * 3, 3), dtype=torch.int64, device=dev)
+            else:
+                ps = self._buf("patch_score", (B * 3,), torch.float64, dev)
+                bb = self._buf("patch_bbox", (B * 3, 3), torch.int64, dev)
             k2_ws = self._buf("k2_ws", (max(patch_max_workspace_bytes(cb * 3, spatial, patch), 8),),
-                              torch.uint8, dev)
+                              torch.uint8, dev)   # one workspace: K2b launches are serialised on one stream
         for ci, b0 in enumerate(range(0, B, cb)):
             b1 = min(b0 + cb, B)
             nb = b1 - b0
-            buf = maps_all[b0:b1] if keep_maps else (maps_buf2 if ci & 1 else maps_buf)[:nb]
-            if overlap and k2_done[ci & 1] is not None:
-                main.wait_event(k2_done[ci & 1])   # K2b of chunk ci-2 has released this scratch
+            if overlap:
+                slot = st["next"]
+                st["next"] ^= 1
+                if st["done"][slot] is not None and not keep_maps:
+                    main.wait_event(st["done"][slot])   # the K2b that last read this scratch has finished
+            else:
+                slot = 0
+            buf = maps_all[b0:b1] if keep_maps else (maps_buf2 if slot else maps_buf)[:nb]
             if self.k1_timer is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
@@ -179,15 +213,28 @@ class UncertaintyPipeline:
                     patch_max(buf.view((3 * nb,) + spatial), patch, mean=cfg.patch_mean,
                               rtol=ISCLOSE_RTOL, atol=ISCLOSE_ATOL, out_score=ps[3 * b0:3 * b1],
                               out_bbox=bb[3 * b0:3 * b1], workspace=k2_ws)
-                    k2_done[ci & 1] = torch.cuda.Event()
-                    k2_done[ci & 1].record(side)
-        if overlap:
-            main.wait_stream(side)
-        scores = torch.zeros((B, 3, N_COLS), dtype=torch.float64, device=dev)
-        scores[:, :, :3] = k1_scores
-        if patch is not None:
-            scores[:, :, COL_PATCH_MAX] = ps.view(B, 3)
-            scores[:, :, COL_BBOX + 3 - nd:COL_BBOX + 3] = bb.view(B, 3, 3)[:, :, 3 - nd:]
-        return PipelineResult(scores=scores, maps=maps_all.permute(1, 0, *range(2, 2 + nd)) if keep_maps else None,
+                    st["done"][slot] = torch.cuda.Event()
+                    st["done"][slot].record(side)
+
+        def assemble():
+            scores = torch.zeros((B, 3, N_COLS), dtype=torch.float64, device=dev)
+            scores[:, :, :3] = k1_scores
+            if patch is not None:
+                scores[:, :, COL_PATCH_MAX] = ps.view(B, 3)
+                scores[:, :, COL_BBOX + 3 - nd:COL_BBOX + 3] = bb.view(B, 3, 3)[:, :, 3 - nd:]
+            return scores
+
+        ready = None
+        if overlap:   # the table is put together behind the last K2b, on the side stream
+            with torch.cuda.stream(side):
+                scores = assemble()
+                ready = torch.cuda.Event()
+                ready.record(side)
+            for t in (k1_scores, ps, bb):
+                t.record_stream(side)     # allocated on the main stream, last read on the side stream
+            scores.record_stream(main)    # allocated on the side stream, read by the caller on main
+        else:
+            scores = assemble()
+        return PipelineResult(_scores=scores, ready=ready, maps=maps_all.permute(1, 0, *range(2, 2 + nd)) if keep_maps else None,
                               mean_argmax=am, ssn=ssn, patch_size=patch,
                               thresholds=cfg.thresholds, threshold_mean=cfg.threshold_mean)

@@ -63,11 +63,16 @@ class AsyncScoreGather:
             self.device = torch.device(device)
             self.stream = torch.cuda.Stream(self.device)
 
-    def submit(self, local: torch.Tensor, n_items: int) -> torch.Tensor:
+    def submit(self, local: torch.Tensor, n_items: int, after=None) -> torch.Tensor:
+        """`after`: a CUDA event that marks `local` complete (PipelineResult.table_async); without it
+        the gather is ordered behind everything queued on the current stream."""
         if self.stream is None:
             return gather_scores(local, n_items, self.group)
         main = torch.cuda.current_stream(self.device)
-        self.stream.wait_stream(main)
+        if after is not None:
+            self.stream.wait_event(after)
+        else:
+            self.stream.wait_stream(main)
         with torch.cuda.stream(self.stream):
             out = gather_scores(local, n_items, self.group)
         local.record_stream(self.stream)
