@@ -230,7 +230,7 @@ class UncertaintyPipeline:
                 scores = assemble()
                 ready = torch.cuda.Event()
                 ready.record(side)
-            for t in (k1_scores, ps, bb):
+            for t in (k1_scores, ps, bb) + ((maps_all,) if keep_maps else ()):
                 t.record_stream(side)     # allocated on the main stream, last read on the side stream
             scores.record_stream(main)    # allocated on the side stream, read by the caller on main
         else:
