@@ -345,6 +345,31 @@ def test_c3_filter_pass_is_exact(vb, vo, mean):
         assert res[0][1][i].tolist() == [b[0] for b in r["bounding_box"]], k
 
 
+@pytest.mark.parametrize("p0", [1, 4, 16, 33])
+def test_c3_filter_pass_other_window_depths(vb, vo, p0):
+    """The march kernel and its filter fix only the in-plane window (10 x 10); the window depth p0 is
+    a run-time value (z-slide length, leaving-plane offset, error coefficient)."""
+    rng = np.random.default_rng(40 + p0)
+    maps = rng.random((3, 33, 52, 88)).astype(np.float32)
+    maps[1, 10:20, 30:40, 60:70] += 0.25
+    t = torch.from_numpy(maps).cuda()
+    res = {}
+    for path in (0, 6, 5):
+        vb._lib.lib.values_debug_set_patch_path(path)
+        try:
+            s, b = vb.patch_max(t, [p0, 10, 10])
+            res[path] = (s.cpu().numpy(), b.cpu().numpy())
+        finally:
+            vb._lib.lib.values_debug_set_patch_path(0)
+    for path in (0, 6):
+        np.testing.assert_allclose(res[path][0], res[5][0], rtol=1e-13, atol=0)
+        assert np.array_equal(res[path][1], res[5][1])
+    for i in range(3):
+        r = vo.patch_level_aggregation(maps[i], [p0, 10, 10])
+        np.testing.assert_allclose(res[0][0][i], r["max_score"], rtol=1e-12)
+        assert res[0][1][i].tolist() == [b[0] for b in r["bounding_box"]]
+
+
 def test_c3_filter_pass_nonfinite(vb):
     """NaN / inf voxels send the map through the exact pass: same result as without the filter."""
     rng = np.random.default_rng(7)
