@@ -125,6 +125,8 @@ def test_c2_vs_oracle(vb, vo, n, c, spatial, dtype):
     (6, 3, (50, 64), torch.float32),        # RS = 2, ragged last tile
     (7, 5, (40, 52), torch.float32),        # RS = 1
     (8, 4, (33, 64), torch.bfloat16),
+    (16, 4, (24, 40, 26), torch.float64),   # fp64: class-outer ring kernel (per-sample accumulators) vs
+    (8, 2, (30, 50), torch.float64),        # the sample-outer kernel (variant 15)
 ])
 def test_k1_kernels_agree(vb, n, c, spatial, dtype):
     """The bulk-copy (TMA ring) kernel and the register-stream kernel share their arithmetic and
@@ -133,7 +135,7 @@ def test_k1_kernels_agree(vb, n, c, spatial, dtype):
     x = softmax_stack(n * 7 + c, 3 * n, c, spatial).reshape(3, n, c, *spatial).to(dtype).cuda()
     outs = []
     try:
-        for variant, it in [(0, 0), (0, 1), (0, 3), (8, 0), (8, 2), (13, 0), (14, 0)]:
+        for variant, it in [(0, 0), (0, 1), (0, 3), (8, 0), (8, 2), (13, 0), (14, 0), (15, 0)]:
             vb._lib.lib.values_debug_set_k1_variant(variant)
             vb._lib.lib.values_debug_set_k1_iter(it)
             r = vb.uncertainty_fused(x, mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05))

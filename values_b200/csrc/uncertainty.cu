@@ -749,7 +749,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // RS rows (samples of one class) share a stage and one mbarrier round trip; N % RS == 0.
-template <typename T, int VEC, int MINB, int RS, int kTmaStages, bool EARLY>
+// NS > 0 (fp64 stacks): the number of samples is the compile-time NS and every sample keeps its own
+// fp32 entropy accumulator H[n], so each H_n still adds its classes in index order and EE is their
+// sequential fp32 sum -- the reference's order (test_3D.py:499-507) -- while the rows stream
+// class-outer through the ring like the fp32 path.  Bit-identical to the sample-outer k1_smem_kernel.
+template <typename T, int VEC, int MINB, int RS, int kTmaStages, bool EARLY, int NS = 0>
 __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Params prm) {
     using A = typename In<T>::acc_t;
     using M = Math<T>;
@@ -832,8 +836,14 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
         for (int j = 0; j < VEC; ++j) {
             S[j] = (A)0; e[j] = 0.f; E[j] = 0.f; PE[j] = 0.f; idx[j] = 0; best[j] = (A)0; Sacc[j] = 0.f;
         }
+        float H[NS > 0 ? NS : 1][VEC];
+#pragma unroll
+        for (int n = 0; n < (NS > 0 ? NS : 1); ++n) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) H[n][j] = 0.f;
+        }
         for (int c = 0; c < C; ++c) {
-            for (int n = 0; n < N; n += RS) {
+            auto stage_body = [&](const int n) {
                 mbar_wait_addr(full0 + stage * 8, phase);
                 // rows of a stage are consumed SB at a time (registers), the stage is one mbarrier round trip
                 constexpr int SB = RS > 5 ? RS / 2 : RS;
@@ -857,7 +867,12 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                             unpack(raw[u], p);
                             if (M::kFlagged) bad |= sign_or(raw[u]);
                             add_rows<VEC>(S, p);
-                            M::rows(e, p);
+                            if constexpr (NS > 0) {
+#pragma unroll
+                                for (int j = 0; j < VEC; ++j) accum_term(H[n + h + u][j], p[j]);
+                            } else {
+                                M::rows(e, p);
+                            }
                         }
                     }
                 }
@@ -866,11 +881,17 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                     // issued right after them races with the next bulk copy -- measured).  The
                     // empty asm pins the arrive behind arithmetic that consumed every row of the
                     // stage, and that arithmetic cannot issue before the loads complete.
-                    asm volatile("" ::"f"(e[0]), "r"(bad) : "memory");
+                    asm volatile("" ::"f"(NS > 0 ? H[n + RS - 1][0] : e[0]), "r"(bad) : "memory");
                     __syncwarp();
                     if (is_lane0) mbar_arrive_addr(empty0 + stage * 8);
                 }
                 if (++stage == kTmaStages) { stage = 0; phase ^= 1u; }
+            };
+            if constexpr (NS > 0) {
+#pragma unroll
+                for (int n = 0; n < NS; n += RS) stage_body(n);     // unrolled: H[] is indexed statically
+            } else {
+                for (int n = 0; n < N; n += RS) stage_body(n);
             }
             if (active) {   // class c complete: mean, arg-max, PE term
                 A m[VEC];
@@ -887,6 +908,13 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
             }
         }
         if (!active) continue;
+        if constexpr (NS > 0) {   // EE numerator: the samples' entropies added in index order (fp32)
+#pragma unroll
+            for (int n = 0; n < NS; ++n) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) E[j] += H[n][j];
+            }
+        }
         if (M::kFlagged) {
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
@@ -1052,14 +1080,14 @@ static int launch_stream(K1Params& prm, int64_t B, cudaStream_t st) {
     return check_launch("k1_stream_kernel");
 }
 
-template <typename T, int VEC, int MINB, int RS, int STAGES, bool EARLY = false>
+template <typename T, int VEC, int MINB, int RS, int STAGES, bool EARLY = false, int NS = 0>
 static int launch_tma(K1Params& prm, int64_t B, cudaStream_t st) {
     const int64_t tiles = ceil_div(ceil_div(prm.V, VEC), kThreads);
     prm.iter = g_k1_iter_override > 0 ? g_k1_iter_override : choose_iter(tiles * B, MINB, prm.N * prm.C);
     prm.blocks_per_vol = ceil_div(tiles, prm.iter);
     const int64_t grid = prm.blocks_per_vol * B;
     if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
-    auto kern = k1_tma_kernel<T, VEC, MINB, RS, STAGES, EARLY>;
+    auto kern = k1_tma_kernel<T, VEC, MINB, RS, STAGES, EARLY, NS>;
     const size_t smem = (size_t)STAGES * RS * kThreads * 16;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return set_error(VALUES_ERR_CUDA, "cudaFuncSetAttribute(k1_tma_kernel) failed");
@@ -1114,6 +1142,14 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, cudaStream_t st) 
         }
         if (v == 1) return launch_stream<T, NV, 4, 2, false>(prm, B, st);
         return launch_stream<T, NV, 4, 3, false>(prm, B, st);
+    }
+    if constexpr (sizeof(T) == 8) {
+        // fp64 stacks with the TTA / MC-dropout sample counts: class-outer ring kernel with one fp32
+        // accumulator per sample (variant 15 keeps the sample-outer kernel, for the bit-identity test)
+        if (prm.need_ent && !prm.samax && aligned && g_k1_variant != 15) {
+            if (prm.N == 16) return launch_tma<T, NV, 2, 4, 4, false, 16>(prm, B, st);
+            if (prm.N == 8) return launch_tma<T, NV, 2, 4, 4, false, 8>(prm, B, st);
+        }
     }
     // per-sample arg-max / arg-max only: sample-outer kernel with class sums in shared memory
     int rc = 1;
