@@ -103,3 +103,27 @@ def test_fp32_box_sums_stay_within_the_filter_bound(vector_kernel, p0, zc):
         err = float(np.abs(got - want).max())
         assert err <= coef * amax, (name, err, coef * amax)
         assert err <= 0.25 * coef * amax, (name, err / (coef * amax))   # and with room to spare
+
+
+def test_fp64_log_table_accuracy():
+    """The table-driven fp64 log of K1's fp64 path (fast_log_f64, values_b200/csrc/uncertainty.cu):
+    the algorithm restated in numpy (tools/check_log64.py) stays within 5e-14 of a 120-bit log, and the
+    table in the kernel source is the one that script builds."""
+    import os
+    import re
+    import sys
+
+    pytest.importorskip("mpmath")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import check_log64
+
+    check_log64.main()                                   # asserts the error bound
+    inv, lnc = check_log64.build()
+    src = open(os.path.join(root, "values_b200", "csrc", "uncertainty.cu")).read()
+    body = src[src.index("kLog64Tab[129] = {"):]
+    body = body[:body.index("};")]
+    vals = [float.fromhex(v) for v in re.findall(r"-?0x[0-9a-f.]+p[+-]?\d+", body)]
+    assert len(vals) == 258
+    np.testing.assert_array_equal(np.asarray(vals[0::2]), inv)
+    np.testing.assert_array_equal(np.asarray(vals[1::2]), lnc)
