@@ -57,7 +57,7 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """SM clocks and throttle reasons sampled DURING the timed region (NVML, ~5 ms period, in a
+    """SM clocks and throttle reasons sampled DURING the timed region (NVML, ~2 ms period, in a
     thread of this process; nvidia-smi -lms cannot start fast enough for a 100 ms region)."""
 
     HW_SLOWDOWN, SW_POWER_CAP = 0x8, 0x4
@@ -72,6 +72,9 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # first calls resolve the NVML entry points (slow): do that before the timed region
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         except Exception:
             self.nv = None
 
@@ -84,7 +87,7 @@ class ClockSampler:
                 self.rows.append((sm, reasons))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def __enter__(self):
         if self.nv is not None:
@@ -248,7 +251,8 @@ def reference_arm(args, wl, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)   # ~170 ms timed: enough for several NVML clock samples
+    ap.add_argument("--steps", type=int, default=20)   # ~70 ms timed (cfg5); past ~100 ms of back-to-back K1 the
+                                                        # 1000 W power cap engages (sw_power_cap, -8 %: profiles/r01m_bench_cfg5_50steps.json)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
