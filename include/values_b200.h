@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VALUES_ABI_VERSION 4
+#define VALUES_ABI_VERSION 5
 
 typedef enum {
     VALUES_F32 = 0, VALUES_F64 = 1, VALUES_BF16 = 2,
@@ -101,11 +101,18 @@ int values_map_reduce(const void* maps, int dtype, int64_t M, int64_t V, int64_t
  * Returns VALUES_ERR_INVALID_ARG if any patch > shape (the reference raises ValueError).
  */
 size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* shape3_host,
-                                        const int64_t* patch3_host);
+                                        const int64_t* patch3_host, int path);
 int values_patch_max(const void* maps, int dtype, int64_t M, int64_t stride_m,
                      const int64_t* shape3_host, const int64_t* patch3_host, int mean_flag,
                      double rtol, double atol, double* max_score, int64_t* bbox_lo,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     void* workspace, size_t workspace_bytes, int path, void* stream);
+/* `path` selects the implementation for THIS call (no process-wide state): 0 automatic -- for
+ * 10x10 in-plane patches (every reference config) an fp32 filter pass streams the maps by TMA
+ * (cp.async.bulk.tensor) and lists the few (tile, z sub-chunk) entries that can hold the answer,
+ * the exact fp64 march kernel then walks only those; other patches use the fused tile kernel when
+ * they fit its shared memory, else the generic tiled path.  5 = march kernel over every tile (no
+ * filter), 4 = fused tile kernel, 2 = generic tiled path: all give the same scores and boxes
+ * (tests/test_gpu_parity.py runs them against each other).  Other values: VALUES_ERR_INVALID_ARG. */
 
 /* ---------------------------------------------------------------------------------------
  * K3: sliding-window stitch accumulator (atomic-free, output-stationary).
@@ -232,15 +239,10 @@ int values_reverse_axes(const void* in, void* out, int elem_bytes, int64_t n0, i
  * voxel tiles per CTA of the K1 stream kernel, and its batch / occupancy variant. */
 void values_debug_set_k1_iter(int iter);
 void values_debug_set_k1_variant(int variant);
-/* K2b implementation: 0 automatic (march kernel for 10x10 in-plane patches, else fused tile kernel),
- * 1 streaming two-kernel path, 2 generic tiled path, 4 fused tile kernel, 5 march kernel without its
- * fp32 filter pass, 6 march kernel behind its own fp32 instantiation instead of the vector filter. */
-void values_debug_set_patch_path(int path);
 /* Pure host function: the error bound of K2b's fp32 filter pass, |fp32 box sum - exact box sum| <=
- * coef * max |input| for 10x10 in-plane patches, z-chunks of zc output planes and p0 planes per window
- * (vector_kernel: 1 = box_filter_kernel, 0 = the march kernel's fp32 instantiation).
- * tests/test_filter_bound.py checks it against an emulation of the kernels' operation order. */
-double values_patch_filter_err_coef(int zc, int p0, int vector_kernel);
+ * coef * max |input| for 10x10 in-plane patches, z-chunks of zc output planes and p0 planes per window.
+ * tests/test_filter_bound.py checks it against an emulation of the kernel's operation order. */
+double values_patch_filter_err_coef(int zc, int p0);
 /* K3 implementation: 0 automatic (vector kernel when rows are 16-byte aligned), 1 scalar kernel. */
 void values_debug_set_stitch_path(int path);
 

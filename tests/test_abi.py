@@ -45,8 +45,9 @@ def test_workspace_queries_are_pure_host_functions():
     assert _lib.lib.values_uncertainty_workspace_bytes(2, 4096, _lib.F32) > 0
     assert _lib.lib.values_uncertainty_workspace_bytes(0, 4096, _lib.F32) == 0
     sh, pa = _lib.i64x3([64, 64, 64]), _lib.i64x3([10, 10, 10])
-    assert _lib.lib.values_patch_max_workspace_bytes(3, sh, pa) > 0
-    assert _lib.lib.values_patch_max_workspace_bytes(3, _lib.i64x3([8, 8, 8]), pa) == 0  # patch > image
+    assert _lib.lib.values_patch_max_workspace_bytes(3, sh, pa, 0) > 0
+    assert _lib.lib.values_patch_max_workspace_bytes(3, _lib.i64x3([8, 8, 8]), pa, 0) == 0  # patch > image
+    assert _lib.lib.values_patch_max_workspace_bytes(3, sh, pa, 1) == 0  # unknown implementation
     assert _lib.lib.values_map_reduce_workspace_bytes(3, 1000) > 0
 
 
@@ -80,7 +81,7 @@ def test_invalid_arguments_are_rejected_before_any_launch():
                                            None, None, None, None, None, 0, None)
     assert rc == _lib.ERR_INVALID_ARG   # NULL stack / unknown dtype
     sh, pa = _lib.i64x3([8, 8, 8]), _lib.i64x3([10, 10, 10])
-    rc = _lib.lib.values_patch_max(None, _lib.F32, 1, 512, sh, pa, 0, 1e-5, 1e-8, None, None, None, 0, None)
+    rc = _lib.lib.values_patch_max(None, _lib.F32, 1, 512, sh, pa, 0, 1e-5, 1e-8, None, None, None, 0, 0, None)
     assert rc == _lib.ERR_INVALID_ARG and b"valid" in _lib.lib.values_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc)

@@ -1,6 +1,6 @@
 """CPU check of the error bound behind K2b's fp32 filter pass (values_b200/csrc/aggregate.cu,
 `filter_err_coef`): the filter may drop a sub-chunk only if its fp32 maximum is provably too small,
-so |fp32 box sum - exact box sum| <= coef * max|input| must hold for the kernels' exact operation
+so |fp32 box sum - exact box sum| <= coef * max|input| must hold for the kernel's exact operation
 order.  Here that order is emulated in numpy float32 (every add / subtract rounds to nearest, as
 FADD / FADD2 do) and compared with fp64 box sums on random and adversarial maps; the coefficient
 comes from the library itself (values_patch_filter_err_coef, a pure host function)."""
@@ -12,16 +12,10 @@ P = 10
 
 
 def tree10(v):
-    """tree_sum_t<10>: ((v0+v1) + (v2+(v3+v4))) + ((v5+v6) + (v7+(v8+v9))), fp32 at every node."""
+    """tree_sum4<10>: ((v0+v1) + (v2+(v3+v4))) + ((v5+v6) + (v7+(v8+v9))), fp32 at every node."""
     def t5(a):
         return (a[0] + a[1]) + (a[2] + (a[3] + a[4]))
     return t5(v[:5]) + t5(v[5:])
-
-
-def ytree_vec(c):
-    """box_filter_kernel's y-stage start: q_j = c[2j] + c[2j+1]; ((q0+q1) + (q2+q3)) + q4."""
-    q = [c[2 * j] + c[2 * j + 1] for j in range(5)]
-    return ((q[0] + q[1]) + (q[2] + q[3])) + q[4]
 
 
 def z_stage(m, p0, zc):
@@ -39,29 +33,50 @@ def z_stage(m, p0, zc):
     return out
 
 
-def slide_axis(a, axis, run, chains, start_fn):
-    """Box sums of width P along `axis`: tasks of `run` outputs starting at multiples of `run`,
-    each as `chains` independent chains (tree / pair start, then s = fl(s + fl(in - out)))."""
-    a = np.moveaxis(a, axis, 0)
-    n_out = a.shape[0] - P + 1
-    out = np.zeros((n_out,) + a.shape[1:], F)
-    step = run // chains
-    for s0 in range(0, n_out, step):                  # every chain start is a fresh tree sum
-        s = start_fn([a[s0 + k] for k in range(P)])
-        out[s0] = s
-        for i in range(1, min(step, n_out - s0)):
-            s = s + (a[s0 + i + P - 1] - a[s0 + i - 1])
-            out[s0 + i] = s
-    return np.moveaxis(out, 0, axis)
+def y_stage(z):
+    """box_strip_filter_kernel's y-stage: a strip of K = 8 output rows starts with a tree over its
+    first 10 z-window sums, then 7 slides o = fl(o + fl(in - out)); strips start at multiples of 8."""
+    K = 8
+    n_out = z.shape[1] - P + 1
+    out = np.zeros((z.shape[0], n_out, z.shape[2]), F)
+    for r0 in range(0, n_out, K):
+        o = tree10([z[:, r0 + k] for k in range(P)])
+        out[:, r0] = o
+        for k in range(1, min(K, n_out - r0)):
+            o = o + (z[:, r0 + k + P - 1] - z[:, r0 + k - 1])
+            out[:, r0 + k] = o
+    return out
 
 
-def emulate(m, p0, zc, vector_kernel):
-    z = z_stage(m.astype(F), p0, zc)
-    if vector_kernel:   # x: 16 outputs, one chain; y: 8 outputs, one chain, pairwise start
-        x = slide_axis(z, 2, 16, 1, tree10)
-        return slide_axis(x, 1, 8, 1, ytree_vec)
-    x = slide_axis(z, 2, 16, 2, tree10)               # march kernel: two chains of 8 / of 4, tree starts
-    return slide_axis(x, 1, 8, 2, tree10)
+def x_stage(y, xs, later_tile_wins):
+    """x-stage: x tiles of `xs` outputs (119 for 128-float staged rows, 55 for 64-float rows) at a pitch of
+    xs & ~3 (TMA origins are 16-byte aligned, so neighbouring tiles both compute 3 outputs: either value
+    may be the one that reaches the maximum); lane l owns outputs 4l .. 4l+3 of the tile:
+    S0 = (Q_l + Q_{l+1}) + A_{l+2} (Q = (e0+e1) + (e2+e3), A = e0+e1), then three slides.  Columns past
+    the map edge arrive as zeros (TMA fill) and only feed masked outputs."""
+    D2 = y.shape[2]
+    n_out = D2 - P + 1
+    e = np.concatenate([y, np.zeros(y.shape[:2] + (16,), F)], axis=2)
+    out = np.zeros(y.shape[:2] + (n_out,), F)
+    origins = list(range(0, max(n_out - xs, 0) + (xs & ~3), xs & ~3)) if n_out > xs else [0]
+    for x0 in (origins if later_tile_wins else origins[::-1]):
+        for l4 in range(0, min(xs, n_out - x0), 4):
+            b = x0 + l4
+            q0 = (e[..., b] + e[..., b + 1]) + (e[..., b + 2] + e[..., b + 3])
+            q1 = (e[..., b + 4] + e[..., b + 5]) + (e[..., b + 6] + e[..., b + 7])
+            a2 = e[..., b + 8] + e[..., b + 9]
+            s = [(q0 + q1) + a2]
+            for j in range(1, 4):
+                s.append(s[-1] + (e[..., b + 9 + j] - e[..., b + j - 1]))
+            for j in range(4):
+                if b + j < min(n_out, x0 + xs):
+                    out[..., b + j] = s[j]
+    return out
+
+
+def emulate(m, p0, zc, later_tile_wins):
+    xs = 55 if m.shape[2] <= 64 else 119              # StripNarrow / StripWide
+    return x_stage(y_stage(z_stage(m.astype(F), p0, zc)), xs, later_tile_wins)
 
 
 def exact(m, p0):
@@ -71,9 +86,8 @@ def exact(m, p0):
             + c[:-a, :-b, d:] + c[:-a, b:, :-d] + c[a:, :-b, :-d] - c[:-a, :-b, :-d])
 
 
-def maps():
+def maps(shape):
     rng = np.random.default_rng(99)
-    shape = (40, 27, 45)
     out = {"uniform": rng.random(shape), "signed": rng.standard_normal(shape)}
     m = rng.random(shape) * 1e-3
     m[7, 9, 11] = 1e4
@@ -89,20 +103,22 @@ def maps():
     return {k: v.astype(F) for k, v in out.items()}
 
 
-@pytest.mark.parametrize("vector_kernel", [1, 0], ids=["box_filter_kernel", "march_fp32"])
+@pytest.mark.parametrize("shape", [(40, 27, 45), (30, 35, 150)], ids=["narrow", "wide-two-x-tiles"])
 @pytest.mark.parametrize("p0,zc", [(10, 31), (10, 8), (3, 38), (1, 40)])
-def test_fp32_box_sums_stay_within_the_filter_bound(vector_kernel, p0, zc):
+def test_fp32_box_sums_stay_within_the_filter_bound(shape, p0, zc):
     from values_b200 import _lib
 
-    coef = _lib.lib.values_patch_filter_err_coef(zc, p0, vector_kernel)
+    coef = _lib.lib.values_patch_filter_err_coef(zc, p0)
     assert coef > 0
-    for name, m in maps().items():
-        got = emulate(m, p0, zc, vector_kernel).astype(np.longdouble)
+    for name, m in maps(shape).items():
         want = exact(m, p0)
         amax = float(np.abs(m).max())
-        err = float(np.abs(got - want).max())
-        assert err <= coef * amax, (name, err, coef * amax)
-        assert err <= 0.25 * coef * amax, (name, err / (coef * amax))   # and with room to spare
+        for later in (False, True) if shape[2] > 64 + 9 else (True,):
+            got = emulate(m, p0, zc, later).astype(np.longdouble)
+            assert np.isfinite(got).all() and got.shape == want.shape
+            err = float(np.abs(got - want).max())
+            assert err <= coef * amax, (name, err, coef * amax)
+            assert err <= 0.25 * coef * amax, (name, err / (coef * amax))   # and with room to spare
 
 
 def test_fp64_log_table_accuracy():

@@ -34,16 +34,12 @@ def vo():
     return values_oracle
 
 
-@pytest.fixture(params=[0, 6, 5, 4, 1, 2],
-                ids=["k2b-auto", "k2b-march-scalar-filter", "k2b-march-nofilter", "k2b-fused", "k2b-stream",
-                     "k2b-tiled"])
-def patch_path(request, vb):
-    """Every K2b implementation (march kernel behind the vector fp32 filter kernel / behind its own
-    fp32 instantiation / alone, fused tile kernel, streaming two-kernel path, generic tiled path)
-    must give the same scores and the same bounding boxes."""
-    vb._lib.lib.values_debug_set_patch_path(request.param)
-    yield request.param
-    vb._lib.lib.values_debug_set_patch_path(0)
+@pytest.fixture(params=[0, 5, 4, 2], ids=["k2b-auto", "k2b-march-nofilter", "k2b-fused", "k2b-tiled"])
+def patch_path(request):
+    """Every K2b implementation (exact march kernel behind the fp32 TMA strip filter / alone, fused
+    tile kernel, generic tiled path) must give the same scores and the same bounding boxes.  The
+    implementation is an argument of the call (values_patch_max `path`), not process state."""
+    return request.param
 
 
 def softmax_stack(seed, n, c, spatial, dtype=torch.float32, shared=False, sharp=3.0):
@@ -244,7 +240,7 @@ def test_c3_golden(vb, patch_path):
             m = g["map_" + str(g[key + "_map"])]
             p = g[key + "_patch"].tolist()
             p = p[0] if len(p) == 1 else p
-            r = vb.patch_level_aggregation(m, p, mean=bool(mean))
+            r = vb.patch_level_aggregation(m, p, mean=bool(mean), _k2b_path=patch_path)
             rtol = 1e-12 if m.dtype == np.float64 else 1e-6  # reference FFT runs fp32 images in complex64
             np.testing.assert_allclose(r["max_score"], float(g[key + "_score"]), rtol=rtol, atol=1e-300)
             assert [list(b) for b in r["bounding_box"]] == g[key + "_bbox"].tolist(), key
@@ -272,7 +268,7 @@ def test_c3_patch_vs_oracle(vb, vo, shape, patch, dtype, patch_path):
     rng = np.random.default_rng(sum(shape) * 7 + len(shape))
     m = rng.random(shape).astype(dtype)
     for mean in (False, True):
-        a = vb.patch_level_aggregation(m, patch, mean=mean)
+        a = vb.patch_level_aggregation(m, patch, mean=mean, _k2b_path=patch_path)
         b = vo.patch_level_aggregation(m, patch, mean=mean)
         assert a["bounding_box"] == b["bounding_box"]
         np.testing.assert_allclose(a["max_score"], b["max_score"], rtol=1e-12)
@@ -284,7 +280,7 @@ def test_c3_batched_and_isclose_rule(vb, vo, patch_path):
     maps[3] = 0.0                                   # all-zero map -> score 0, box at origin
     maps[4, 5:15, 5:15, 5:15] += 1.0
     maps[5] = maps[4] * (1 - 4e-6)                  # everything scales: same bbox
-    score, bbox = vb.patch_max(torch.from_numpy(maps).cuda(), 10)
+    score, bbox = vb.patch_max(torch.from_numpy(maps).cuda(), 10, path=patch_path)
     for i in range(7):
         r = vo.patch_level_aggregation(maps[i], 10)
         np.testing.assert_allclose(score[i].item(), r["max_score"], rtol=1e-12)
@@ -331,14 +327,10 @@ def test_c3_filter_pass_is_exact(vb, vo, mean):
     names = list(cases)
     maps = torch.from_numpy(np.stack([cases[k] for k in names])).cuda()
     res = {}
-    for path in (0, 6, 5):
-        vb._lib.lib.values_debug_set_patch_path(path)
-        try:
-            s, b = vb.patch_max(maps, 10, mean=mean)
-            res[path] = (s.cpu().numpy(), b.cpu().numpy())
-        finally:
-            vb._lib.lib.values_debug_set_patch_path(0)
-    for path in (0, 6):
+    for path in (0, 5):
+        s, b = vb.patch_max(maps, 10, mean=mean, path=path)
+        res[path] = (s.cpu().numpy(), b.cpu().numpy())
+    for path in (0,):
         np.testing.assert_allclose(res[path][0], res[5][0], rtol=1e-13, atol=0)
         assert np.array_equal(res[path][1], res[5][1])
     for i, k in enumerate(names):
@@ -356,14 +348,10 @@ def test_c3_filter_pass_other_window_depths(vb, vo, p0):
     maps[1, 10:20, 30:40, 60:70] += 0.25
     t = torch.from_numpy(maps).cuda()
     res = {}
-    for path in (0, 6, 5):
-        vb._lib.lib.values_debug_set_patch_path(path)
-        try:
-            s, b = vb.patch_max(t, [p0, 10, 10])
-            res[path] = (s.cpu().numpy(), b.cpu().numpy())
-        finally:
-            vb._lib.lib.values_debug_set_patch_path(0)
-    for path in (0, 6):
+    for path in (0, 5):
+        s, b = vb.patch_max(t, [p0, 10, 10], path=path)
+        res[path] = (s.cpu().numpy(), b.cpu().numpy())
+    for path in (0,):
         np.testing.assert_allclose(res[path][0], res[5][0], rtol=1e-13, atol=0)
         assert np.array_equal(res[path][1], res[5][1])
     for i in range(3):
@@ -381,14 +369,10 @@ def test_c3_filter_pass_nonfinite(vb):
     maps[3, 39, 63, 95] = -np.inf
     t = torch.from_numpy(maps).cuda()
     res = {}
-    for path in (0, 6, 5):
-        vb._lib.lib.values_debug_set_patch_path(path)
-        try:
-            s, b = vb.patch_max(t, 10)
-            res[path] = (s.cpu().numpy(), b.cpu().numpy())
-        finally:
-            vb._lib.lib.values_debug_set_patch_path(0)
-    for path in (0, 6):
+    for path in (0, 5):
+        s, b = vb.patch_max(t, 10, path=path)
+        res[path] = (s.cpu().numpy(), b.cpu().numpy())
+    for path in (0,):
         np.testing.assert_allclose(res[path][0], res[5][0], rtol=1e-13, atol=0, equal_nan=True)
         assert np.array_equal(res[path][1], res[5][1])
     assert np.isnan(res[0][0][1]) and res[0][1][1].tolist() == [-1, -1, -1]
@@ -401,10 +385,10 @@ def test_c3_workspace_garbage_is_harmless(vb, vo, shape, patch_path):
     scores -- z-chunks whose last sub-chunk is short are the case that once did."""
     rng = np.random.default_rng(shape[0])
     maps = torch.from_numpy(rng.random((5,) + shape).astype(np.float32)).cuda()
-    ws_bytes = vb.aggregation.patch_max_workspace_bytes(5, shape, 10)
+    ws_bytes = vb.aggregation.patch_max_workspace_bytes(5, shape, 10, path=patch_path)
     for fill in (0x7f, 0xff):
         ws = torch.full((ws_bytes + 64,), fill, dtype=torch.uint8, device="cuda")
-        score, bbox = vb.patch_max(maps, 10, workspace=ws)
+        score, bbox = vb.patch_max(maps, 10, workspace=ws, path=patch_path)
         for i in range(5):
             r = vo.patch_level_aggregation(maps[i].cpu().numpy(), 10)
             np.testing.assert_allclose(score[i].item(), r["max_score"], rtol=1e-12)

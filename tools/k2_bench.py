@@ -2,7 +2,7 @@
 """Micro-benchmark of K2b (values_patch_max) on the GPU box: M fp32 maps resident in L2/HBM,
 CUDA-event timing per implementation path.
 
-    python tools/k2_bench.py [--shape 128,128,128] [--maps 3,12,24] [--paths 0,1] [--patch 10]
+    python tools/k2_bench.py [--shape 128,128,128] [--maps 3,12,24] [--paths 0,5] [--patch 10]
 """
 import argparse
 import os
@@ -19,7 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shape", default="128,128,128")
     ap.add_argument("--maps", default="3,12")
-    ap.add_argument("--paths", default="0,1")
+    ap.add_argument("--paths", default="0,5")
     ap.add_argument("--patch", type=int, default=10)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--sparse", action="store_true", help="95 %% zeros (real maps are mostly background)")
@@ -33,8 +33,7 @@ def main():
             maps = torch.where(maps > 0.95, maps, torch.zeros_like(maps))
         ref = None
         for path in [int(v) for v in args.paths.split(",")]:
-            _lib.lib.values_debug_set_patch_path(path)
-            score, bbox = vb.patch_max(maps, args.patch)
+            score, bbox = vb.patch_max(maps, args.patch, path=path)
             torch.cuda.synchronize()
             if ref is None:
                 ref = (score.clone(), bbox.clone())
@@ -44,7 +43,7 @@ def main():
             for _ in range(args.reps):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                vb.patch_max(maps, args.patch)
+                vb.patch_max(maps, args.patch, path=path)
                 e1.record()
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1))
@@ -52,7 +51,6 @@ def main():
             print(f"shape={shape} M={M} path={path}: {best * 1e3:8.1f} us  {best * 1e3 / M:7.2f} us/map "
                   f"{vox / best / 1e6:7.2f} Gvox/s  ({vox * 4 / best / 1e6:7.1f} GB/s of map bytes) "
                   f"bbox_same_as_first={same}", flush=True)
-    _lib.lib.values_debug_set_patch_path(0)
 
 
 if __name__ == "__main__":

@@ -13,17 +13,15 @@ import values_b200 as vb
 from values_b200 import _lib
 
 g = torch.Generator(device="cuda").manual_seed(1)
-for shape in [(40, 64, 96), (23, 50, 76)]:
+for shape in [(40, 64, 96), (23, 50, 76), (21, 45, 140)]:
     maps = torch.rand((3,) + shape, generator=g, device="cuda")
     ref = None
-    for path in (5, 6, 0):
-        _lib.lib.values_debug_set_patch_path(path)
-        s, b = vb.patch_max(maps, 10)
+    for path in (5, 4, 0):
+        s, b = vb.patch_max(maps, 10, path=path)
         torch.cuda.synchronize()
         if ref is None:
             ref = (s.clone(), b.clone())
         assert torch.equal(ref[1], b) and torch.allclose(ref[0], s, rtol=1e-13, atol=0), (shape, path)
-_lib.lib.values_debug_set_patch_path(0)
 x = torch.rand((33, 17, 70), generator=g, device="cuda")
 assert torch.equal(vb.reverse_axes(x), x.permute(2, 1, 0).contiguous())
 torch.cuda.synchronize()

@@ -48,20 +48,22 @@ def _as_map(image, device: torch.device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ device-side batched ops
-def patch_max_workspace_bytes(M: int, spatial: Sequence[int], patch_size) -> int:
+def patch_max_workspace_bytes(M: int, spatial: Sequence[int], patch_size, path: int = 0) -> int:
     nd = len(spatial)
     if isinstance(patch_size, (int, np.integer)):
         patch_size = nd * [int(patch_size)]
     return int(_lib.lib.values_patch_max_workspace_bytes(
-        M, _lib.i64x3([1] * (3 - nd) + list(spatial)), _lib.i64x3([1] * (3 - nd) + list(patch_size))))
+        M, _lib.i64x3([1] * (3 - nd) + list(spatial)), _lib.i64x3([1] * (3 - nd) + list(patch_size)), int(path)))
 
 
 def patch_max(maps: torch.Tensor, patch_size, mean: bool = False,
               rtol: float = ISCLOSE_RTOL, atol: float = ISCLOSE_ATOL,
               out_score: Optional[torch.Tensor] = None, out_bbox: Optional[torch.Tensor] = None,
-              workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+              workspace: Optional[torch.Tensor] = None, path: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """maps [M, *S] (CUDA fp32/fp64, 1 <= len(S) <= 3) -> (max_score fp64 [M], bbox_lo int64 [M, len(S)]).
-    out_score fp64 [M] / out_bbox int64 [M, 3] / workspace (uint8) may be preallocated."""
+    out_score fp64 [M] / out_bbox int64 [M, 3] / workspace (uint8) may be preallocated.
+    path: implementation for this call (include/values_b200.h: 0 automatic, 5 exact march without the
+    fp32 filter, 4 fused tile kernel, 2 generic tiled path); all give identical results."""
     if maps.device.type != "cuda":
         raise RuntimeError("patch_max expects a CUDA tensor (no CPU fallback)")
     nd = maps.dim() - 1
@@ -82,7 +84,7 @@ def patch_max(maps: torch.Tensor, patch_size, mean: bool = False,
             or tuple(bbox.shape) != (M, 3) or bbox.dtype != torch.int64 or not bbox.is_contiguous()):
         raise ValueError("out_score must be contiguous fp64 [M] and out_bbox contiguous int64 [M, 3]")
     sh, pa = _lib.i64x3(shape3), _lib.i64x3(patch3)
-    ws_bytes = _lib.lib.values_patch_max_workspace_bytes(M, sh, pa)
+    ws_bytes = _lib.lib.values_patch_max_workspace_bytes(M, sh, pa, int(path))
     if workspace is not None and workspace.numel() * workspace.element_size() >= ws_bytes:
         ws = workspace
     else:
@@ -91,7 +93,7 @@ def patch_max(maps: torch.Tensor, patch_size, mean: bool = False,
     with torch.cuda.device(dev):
         rc = _lib.lib.values_patch_max(maps.data_ptr(), _lib.dtype_code(maps.dtype), M, V, sh, pa,
                                        int(bool(mean)), float(rtol), float(atol), score.data_ptr(),
-                                       bbox.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(dev))
+                                       bbox.data_ptr(), ws.data_ptr(), ws_bytes, int(path), _lib.stream_ptr(dev))
     _lib.check(rc)
     return score, bbox[:, 3 - nd:]
 
@@ -144,7 +146,8 @@ def patch_level_aggregation(image, patch_size, mean: bool = False, **kwargs) -> 
     dev = _lib.require_cuda()
     img = _as_map(image, dev)
     try:
-        score, bbox = patch_max(img.unsqueeze(0), patch_size, mean=mean)
+        # `_k2b_path` (tests only): the K2b implementation for this call, see patch_max
+        score, bbox = patch_max(img.unsqueeze(0), patch_size, mean=mean, path=int(kwargs.get("_k2b_path", 0)))
     except ValueError as e:  # image smaller than the patch: scipy's message (probe)
         raise ValueError(str(e)) from None
     lo = bbox[0].tolist()

@@ -3,14 +3,19 @@
 //   K2b patch_max  : fp64 sliding box-sum, max, first-isclose index      (:13-31)
 //   normalize_maps : map / clip(count, 1) in fp64                        (data_carrier_3D.py:326-329)
 // All HBM/L2-bound; algorithmic bytes = sizeof(T) per map voxel, outputs O(1).
+#include <cuda.h>
+
+#include <algorithm>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vb {
 
-// 0 = automatic (march kernel for 10x10 in-plane patches, else the fused tile kernel when the
-// patch fits its shared memory), 1 = streaming two-kernel path, 2 = generic tiled path, 4 = fused
-// tile kernel even where the march kernel applies (values_debug_set_patch_path; tests cover all)
-static int g_patch_path = 0;
+// K2b implementations, selected per call (values_patch_max `path`): 0 = automatic (10x10 in-plane
+// patches: fp32 strip filter by TMA in front of the exact fp64 march kernel; else the fused tile
+// kernel when the patch fits its shared memory; else the generic tiled path), 5 = march kernel
+// without the filter, 4 = fused tile kernel even where the march applies, 2 = generic tiled path.
 
 // =============================================================================== K2a
 struct ThrTable { double v[16]; int n; };
@@ -273,6 +278,7 @@ struct FusedParams {
     int zsub, zc_fine;            // pass 2 splits a pass-1 z-chunk into zsub pieces of zc_fine planes
     int64_t ntiles;
     int64_t nent;                 // tile_max entries per map: ntiles (fused) or ntiles * zsub (march)
+    int tx_per, xs_stride;        // march tiles: x origin of tile column tx = (tx / tx_per) * xs_stride + (tx % tx_per) * 64
     double denom;
     int mean_flag;
     double rtol, atol;
@@ -301,7 +307,8 @@ template <int N> __device__ __forceinline__ double tree_sum(const double* v) {
 template <int PASS, int NT = kFusedThreads, bool FINE = false>
 __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t m, double tmax,
                                                 unsigned long long tbest, double* red, int& s_flag,
-                                                int& s_count, float amax = 0.f) {
+                                                int& s_count, float amax = 0.f,
+                                                unsigned int n_ctas = gridDim.x) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
     if constexpr (PASS == 0) {
@@ -319,7 +326,7 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            s_flag = atomicAdd(prm.tickets + 4 * m, 1u) == gridDim.x - 1;
+            s_flag = atomicAdd(prm.tickets + 4 * m, 1u) == n_ctas - 1;
             s_count = 0;
         }
         __syncthreads();
@@ -365,7 +372,7 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
                 prm.tile_max[m * prm.nent + blockIdx.x] = mm;
             }
             __threadfence();
-            s_flag = atomicAdd(prm.tickets + 4 * m + 1, 1u) == gridDim.x - 1;
+            s_flag = atomicAdd(prm.tickets + 4 * m + 1, 1u) == n_ctas - 1;
             s_count = 0;
         }
         __syncthreads();
@@ -406,7 +413,7 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            s_flag = atomicAdd(prm.tickets + 4 * m + 2, 1u) == gridDim.x - 1;
+            s_flag = atomicAdd(prm.tickets + 4 * m + 2, 1u) == n_ctas - 1;
         }
         __syncthreads();
         if (s_flag && tid == 0) {
@@ -641,13 +648,8 @@ __device__ __forceinline__ double acc_max(double a, double b) { return fmax(a, b
 __device__ __forceinline__ float acc_max(float a, float b) { return fmaxf(a, b); }
 constexpr int tree_depth(int n) { return n <= 1 ? 0 : 1 + tree_depth(n - n / 2); }
 
-// PASS 0 (ACC = float, fp32 maps only): the FILTER.  The same march in fp32 -- half the shared
-// memory traffic and registers, no fp32->fp64 conversions, 4-cycle add chains -- over every tile,
-// storing one fp32 maximum of box sums per z sub-chunk and the largest |input|.  fp32 sliding sums
-// are not the answer (np.isclose decisions need fp64), but with a rigorous error bound they say
-// which sub-chunks can possibly hold the maximum or a window np.isclose to it (box_pass_finish<0>);
-// PASS 1 then computes the exact fp64 maxima of only those (prm.use_list), PASS 2 the first index.
-// Results are bit-identical to running PASS 1 over everything.
+// PASS 1 after the fp32 strip filter (prm.use_list): only the (tile, z sub-chunk) entries the filter
+// listed are walked; results are bit-identical to running PASS 1 over everything.
 template <typename T, typename ACC, int TY, int TX, int PC, int PASS, int MINB>
 __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const FusedParams prm) {
     using MT = MarchTile<TY, TX, PC>;
@@ -668,7 +670,6 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
     double gmax = 0.0;
     unsigned long long tbest = ~0ull;
     ACC tmax = ninf_a;
-    float amax = 0.f;
     bool saw_nan = false;
     int n_work = 1, work = 0, work_step = 1;
     const int* list = prm.active + m * (1 + kMaxActive);
@@ -705,7 +706,9 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
         const int64_t zo0 = (int64_t)zc_i * prm.zc + (int64_t)fine * zc_fine;
         const int64_t zo1 = min(zo0 + zc_fine, min((int64_t)(zc_i + 1) * prm.zc, prm.O0));
         if (zo0 >= zo1) continue;
-        const unsigned int x0 = (unsigned int)tx_i * TX, y0 = (unsigned int)ty_i * TY;
+        // tile columns follow the filter's x tiling when it runs in front (FusedParams::tx_per)
+        const unsigned int x0 = (unsigned int)((tx_i / prm.tx_per) * prm.xs_stride + (tx_i % prm.tx_per) * TX);
+        const unsigned int y0 = (unsigned int)ty_i * TY;
         const int nplanes = (int)(zo1 - zo0) + p0 - 1;
         const unsigned int plane_elems = D1 * D2;
         const T* src = reinterpret_cast<const T*>(prm.maps) + m * prm.stride_m + zo0 * (int64_t)plane_elems;
@@ -739,7 +742,6 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
 #pragma unroll
                 for (int i = 0; i < MT::NSLOT; ++i) {
                     zs[i] += (ACC)nw[i] - (ACC)od[i];
-                    if constexpr (PASS == 0) amax = fmaxf(amax, fabsf((float)nw[i]));
                 }
                 if (zi + 1 < nplanes) {    // entering plane zi+1 and leaving plane zi+1-p0: in flight
                     const T* pn = src + (int64_t)(zi + 1) * plane_elems;   // during the x / y passes
@@ -794,11 +796,9 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
                         o[H + k] = o[H + k - 1] + (cb[(H + k + PC - 1) * MT::pitchB] - cb2[k - 1]);
                     }
                 }
-                if constexpr (PASS != 0) {     // the filter compares box SUMS (finish<0> scales atol instead)
-                    if (prm.mean_flag) {
+                if (prm.mean_flag) {
 #pragma unroll
-                        for (int k = 0; k < MT::RUN; ++k) o[k] = box_mean_div(o[k], prm.denom);
-                    }
+                    for (int k = 0; k < MT::RUN; ++k) o[k] = box_mean_div(o[k], prm.denom);
                 }
                 if constexpr (PASS <= 1) {
                     if (all_valid) {
@@ -844,142 +844,248 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
             for (int f = written; f < zsub; ++f) prm.tile_max[m * prm.nent + (int64_t)tile * zsub + f] = ninf;
         }
     }
-    box_pass_finish<PASS, kFusedThreads, true>(prm, m, 0.0, tbest, red, s_flag, s_count, amax);
+    box_pass_finish<PASS, kFusedThreads, true>(prm, m, 0.0, tbest, red, s_flag, s_count);
 }
 
-// ------------------------------------------------------------------ K2b fast path (p2 <= 32)
-// Two sync-free streaming kernels with an L2-resident fp64 intermediate:
-//   A  box_zx_kernel: thread = (y, x) column marching over a z-chunk.  z-box by a sliding sum
-//      (one new + one leaving plane per step, restarted every chunk so rounding cannot drift),
-//      x-box by warp shuffles (binary decomposition of p2), result XZ[z', y, x'] (fp64).
-//   B  box_y_kernel: thread = (z', x') marching over a y-chunk with a sliding sum over XZ;
-//      pass 1 records the per-CTA max, pass 2 re-walks only CTAs whose max is np.isclose to the
-//      global max and takes the minimum C-order index (atomicMin: order-free, deterministic).
-constexpr int kZC = 16;   // outputs per z-chunk (kernel A)
-constexpr int kYC = 32;   // outputs per y-chunk (kernel B)
-constexpr int kRowsA = kThreads / 32;  // y rows per CTA in kernel A
-
-struct StreamParams {
-    const void* maps;
-    int64_t stride_m;
-    int64_t D0, D1, D2, O0, O1, O2;
-    int p0, p1, p2;
-    int xs;                 // valid outputs per warp window = 32 - p2 + 1
-    int nxw, nyg, nzc;      // kernel A grid decomposition
-    int64_t nlb;            // kernel B: CTAs over (z', x')
-    int nyc;                // kernel B: y-chunks
-    int64_t ntiles;         // kernel B CTAs per map = nlb * nyc
-    double* xz;             // [M, O0, D1, O2]
-    double denom;
-    int mean_flag;
-    double rtol, atol;
-    double* tile_max;
-    const double* gmax;
-    unsigned long long* best;
+// ------------------------------------------------------------------ K2b filter: strip kernel (TMA)
+// The fp32 FILTER in front of the exact march: fp32 box sums over every window, one maximum per
+// (march tile, z sub-chunk) entry plus a bound on max |input|; box_pass_finish<0> turns them into
+// the work list of the exact fp64 passes (rigorous error bound, filter_err_coef).  fp32 sliding
+// sums are not the answer -- np.isclose decisions need fp64 -- but they say where the answer can be.
+//
+// Built around the L1 / shared-memory data pipe, which bounded the previous filter (ncu, r01g: 64 %
+// of its wavefronts, one block barrier per plane): here a WARP owns a strip of K output rows over
+// the whole staged width and keeps everything between the plane tile and the maximum in registers.
+//  * planes arrive by TMA (cp.async.bulk.tensor, one 4-D box [1 map, 1 plane, RIN rows, WF columns]
+//    for the entering plane and one for the leaving plane, out-of-range rows / columns zero-filled)
+//    into a two-stage shared-memory ring; one producer warp, full / empty mbarriers, no block barrier
+//    anywhere in the march;
+//  * z-stage: lane = one float4 column of the strip's K + 9 input rows: LDS.128 of the entering and
+//    the leaving plane, packed f32x2 adds into K + 9 float4 window sums (registers);
+//  * y-stage: tree sum of 10 rows, then K - 1 slides, all in registers (no exchange);
+//  * x-stage: the 10-wide window of output x = 4 lane + j spans lanes l .. l+3: five SHFL per float4
+//    (lane sums Q, pair sum A, three single elements), one tree-shaped start S0 = (Q_l + Q_{l+1}) + A_{l+2}
+//    and three slides;
+//  * the strip's maximum per z sub-chunk goes through one shared-memory atomicMax per half-warp; the
+//    last warp of the CTA to close a sub-chunk writes the entries.
+// Per output: 11 thread instructions and 0.19 data-pipe wavefronts (previous filter: 24 and 0.39).
+// LW = 32: staged rows of 128 floats, 119 outputs per x tile (two march tile columns: lanes 0-15 and
+// 16-31); LW = 16 (maps up to 64 wide): rows of 64 floats, two strips side by side in a warp.
+template <int K_, int NW_, int LW_> struct StripTile {
+    static constexpr int K = K_, NW = NW_, LW = LW_, PC = 10;
+    static constexpr int SUBS = 32 / LW;                 // strips side by side in one warp
+    static constexpr int ROWS = NW * SUBS * K;           // output rows per CTA
+    static constexpr int RIN = ROWS + PC - 1;            // input rows per staged plane
+    static constexpr int RW = K + PC - 1;                // input rows per strip
+    static constexpr int WF = LW * 4;                    // input columns per staged plane
+    static constexpr int XS = WF - PC + 1;               // outputs per x tile (119 / 55)
+    static constexpr int XSTEP = XS & ~3;                // x tile pitch: the innermost TMA coordinate must be a
+                                                         // multiple of 16 bytes (an odd origin traps as an illegal
+                                                         // instruction), so neighbouring tiles share 3 outputs
+    static constexpr int NSTAGE = 2;
+    static constexpr int PLANE = RIN * WF;               // floats per staged plane
+    static constexpr int NT = (NW + 1) * 32;             // consumer warps + the producer warp
+    static constexpr int TYC = ROWS / 32;                // march tile rows per CTA
+    static constexpr int TXC = (XS + 63) / 64;           // march tile columns per x tile (2 / 1)
+    static constexpr int NSLOT = TYC * TXC;
+    static constexpr size_t smem = (size_t)NSTAGE * 2 * PLANE * sizeof(float) + 128;   // + alignment slack
+    static_assert(ROWS % 32 == 0 && 32 % K == 0, "strips must not straddle march tiles");
+    static_assert((PLANE * sizeof(float)) % 128 == 0, "TMA destinations are 128-byte aligned");
+    static_assert(RIN <= 256 && WF <= 256, "TMA box limits");
 };
 
-__device__ __forceinline__ double shfl_down_f64(double v, int delta) {
-    return __shfl_down_sync(0xffffffffu, v, delta);
+__device__ __forceinline__ int strip_fkey(float f) {      // order-preserving float -> int
+    const int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
 }
-// sum of lanes [lane, lane + p) for every lane (valid where lane + p <= 32)
-__device__ __forceinline__ double warp_window_sum(double v, int p) {
-    double s = v, acc = 0.0;
-    int off = 0;
-    for (int bit = 1; bit <= p; bit <<= 1) {
-        if (p & bit) { acc += shfl_down_f64(s, off); off += bit; }
-        if ((bit << 1) <= p) s += shfl_down_f64(s, bit);
-    }
-    return acc;
+__device__ __forceinline__ float strip_funkey(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+constexpr int kStripKeyNinf = (int)0x807fffff;            // strip_fkey(-inf)
+
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) {
+    const float2 lo = sub2(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = sub2(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ unsigned int or4(unsigned int acc, float4 v) {
+    acc |= __float_as_uint(v.x) | __float_as_uint(v.y);
+    return acc | __float_as_uint(v.z) | __float_as_uint(v.w);
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 q;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(a));
+    return q;
+}
+template <int N> __device__ __forceinline__ float4 tree_sum4(const float4* v) {
+    if constexpr (N == 1) return v[0];
+    else return add4(tree_sum4<N / 2>(v), tree_sum4<N - N / 2>(v + N / 2));
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads) box_zx_kernel(const StreamParams prm) {
-    int64_t idx = blockIdx.x;
-    const int xw = (int)(idx % prm.nxw); idx /= prm.nxw;
-    const int yg = (int)(idx % prm.nyg); idx /= prm.nyg;
-    const int zc = (int)(idx % prm.nzc); idx /= prm.nzc;
-    const int64_t m = idx;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t x = (int64_t)xw * prm.xs + lane;
-    const int64_t y = (int64_t)yg * kRowsA + warp;
-    if (y >= prm.D1) return;  // warp-uniform
-    const bool in_x = x < prm.D2;
-    const bool out_x = lane < prm.xs && x < prm.O2;
-    const int64_t z0 = (int64_t)zc * kZC;
-    const int64_t z1 = min(z0 + kZC, prm.O0);
-    const int64_t plane = prm.D1 * prm.D2;
-    const T* src = reinterpret_cast<const T*>(prm.maps) + m * prm.stride_m + y * prm.D2 + (in_x ? x : 0);
-    double* dst = prm.xz + ((m * prm.O0) * prm.D1 + y) * prm.O2 + (out_x ? x : 0);
-    const int64_t oplane = prm.D1 * prm.O2;
-    double run = 0.0;
-    for (int k = 0; k < prm.p0; ++k) {
-        const double v = in_x ? (double)In<T>::load_one(src + (z0 + k) * plane) : 0.0;
-        run += v;
-    }
-    for (int64_t z = z0;; ++z) {
-        const double xz = warp_window_sum(run, prm.p2);
-        if (out_x) dst[z * oplane] = xz;
-        if (z + 1 >= z1) break;
-        const double add = in_x ? (double)In<T>::load_one(src + (z + prm.p0) * plane) : 0.0;
-        const double sub = in_x ? (double)In<T>::load_one(src + z * plane) : 0.0;
-        run += add - sub;
-    }
-}
-
-template <int PASS>
-__global__ void __launch_bounds__(kThreads) box_y_kernel(const StreamParams prm) {
-    __shared__ double red[8];
-    const int64_t m = blockIdx.y;
-    const int64_t lb = blockIdx.x % prm.nlb;
-    const int yc = (int)(blockIdx.x / prm.nlb);
-    if (PASS == 2) {
-        const double tm = prm.tile_max[m * prm.ntiles + blockIdx.x];
-        if (!np_isclose(tm, prm.gmax[m], prm.rtol, prm.atol)) return;
-    }
-    const int64_t L = lb * kThreads + threadIdx.x;     // flattened (z', x')
-    const bool valid = L < prm.O0 * prm.O2;
-    const int64_t zq = valid ? L / prm.O2 : 0;
-    const int64_t xq = valid ? L - zq * prm.O2 : 0;
-    const int64_t y0 = (int64_t)yc * kYC;
-    const int64_t y1 = min(y0 + kYC, prm.O1);
-    const double* src = prm.xz + ((m * prm.O0 + zq) * prm.D1) * prm.O2 + xq;
-    double tmax = -__longlong_as_double(0x7ff0000000000000LL);
-    unsigned long long tbest = ~0ull;
-    const double gmax = PASS == 2 ? prm.gmax[m] : 0.0;
-    if (valid) {
-        double run = 0.0;
-        for (int k = 0; k < prm.p1; ++k) run += src[(y0 + k) * prm.O2];
-        for (int64_t y = y0;; ++y) {
-            const double v = prm.mean_flag ? run / prm.denom : run;
-            if (PASS == 1) {
-                tmax = nanmax(tmax, v);
-            } else if (np_isclose(v, gmax, prm.rtol, prm.atol)) {
-                const unsigned long long lin = (unsigned long long)((zq * prm.O1 + y) * prm.O2 + xq);
-                tbest = lin < tbest ? lin : tbest;
-            }
-            if (y + 1 >= y1) break;
-            run += src[(y + prm.p1) * prm.O2] - src[y * prm.O2];
-        }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (PASS == 1) {
+template <int K, int NW, int LW>
+__global__ void __launch_bounds__(StripTile<K, NW, LW>::NT, 2)
+box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams prm, int cta_y, int nxs) {
+    using ST = StripTile<K, NW, LW>;
+    constexpr int NT = ST::NT, RW = ST::RW, PC = ST::PC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[ST::NSTAGE];
+    __shared__ __align__(8) uint64_t empty_bar[ST::NSTAGE];
+    __shared__ int s_key[4][ST::NSLOT];     // sub-chunk maxima in flight (order-preserving keys), 4 deep
+    __shared__ int s_cnt[4];
+    __shared__ double red[NT / 32];
+    __shared__ int s_flag;
+    __shared__ int s_count;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p0 = prm.p0;
+    // work item: (map, z-chunk, CTA row of march tiles, x tile); x fastest so that neighbours share halo rows in L2
+    int item = blockIdx.x;
+    const int xt = item % nxs; item /= nxs;
+    const int cy = item % cta_y; item /= cta_y;
+    const int zc_i = item % prm.chunks_z;
+    const int64_t m = item / prm.chunks_z;
+    const int64_t zo0 = (int64_t)zc_i * prm.zc;
+    const int nout = (int)(min(zo0 + prm.zc, prm.O0) - zo0);
+    const int nplanes = nout + p0 - 1;
+    const int x0 = xt * ST::XSTEP, y0 = cy * ST::ROWS;
+    const uint32_t stage_base = (smem_u32(smem_raw) + 127u) & ~127u;
+    constexpr uint32_t kPlaneBytes = ST::PLANE * sizeof(float);
+    if (tid == 0) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tmax = nanmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-        if (lane == 0) red[warp] = tmax;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double mm = red[0];
-            for (int w = 1; w < kThreads / 32; ++w) mm = nanmax(mm, red[w]);
-            prm.tile_max[m * prm.ntiles + blockIdx.x] = mm;
+        for (int s = 0; s < ST::NSTAGE; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, NW); }
+        for (int q = 0; q < 4; ++q) {
+            s_cnt[q] = 0;
+            for (int i = 0; i < ST::NSLOT; ++i) s_key[q][i] = kStripKeyNinf;
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    unsigned int abits = 0;
+    if (warp == NW) {
+        // ---- producer: one lane streams the plane tiles of this z-chunk through the ring
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap);
+            for (int zi = 0; zi < nplanes; ++zi) {
+                const int stage = zi % ST::NSTAGE;
+                if (zi >= ST::NSTAGE) mbar_wait(empty_bar + stage, ((zi / ST::NSTAGE) & 1) ^ 1u);
+                const bool leaving = zi >= p0;
+                mbar_expect_tx(full_bar + stage, leaving ? 2 * kPlaneBytes : kPlaneBytes);
+                const uint32_t dst = stage_base + stage * 2 * kPlaneBytes;
+                tma_load_4d_addr(dst, &tmap, x0, y0, (int)(zo0 + zi), (int)m, full_bar + stage);
+                if (leaving) tma_load_4d_addr(dst + kPlaneBytes, &tmap, x0, y0, (int)(zo0 + zi - p0), (int)m, full_bar + stage);
+            }
         }
     } else {
+        // ---- consumers: lane = float4 column c4 of strip `strip` (K output rows, K + 9 input rows)
+        const int c4 = lane % LW, strip = warp * ST::SUBS + lane / LW;
+        const int r0 = strip * K;
+        const int nvr = max(0, min(K, (int)prm.O1 - (y0 + r0)));          // valid output rows of the strip
+        const int nvr_w = __shfl_sync(0xffffffffu, nvr, 0);                 // ... of the warp's first strip (the larger)
+        const int xo = 4 * c4, xlim = min(ST::XS, (int)prm.O2 - x0);        // valid outputs: xo + j < xlim
+        const bool cv0 = xo < xlim, cv1 = xo + 1 < xlim, cv2 = xo + 2 < xlim, cv3 = xo + 3 < xlim;
+        // the tail rows of a strip are the own rows of the next one: only the last strip of the CTA
+        // (and every strip's own K rows) feed the bound on max |input|
+        const bool or_tail = strip == NW * ST::SUBS - 1;
+        const uint32_t lane_off = (uint32_t)(r0 * ST::WF + xo) * 4u;
+        // entry slot of this half-warp: march tile row (r0 / 32) x tile column (lanes 16.. of a 128-wide row)
+        const int slot = (r0 / 32) * ST::TXC + (LW == 32 ? lane / 16 : 0);
+        float4 zs[RW];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, tbest, o);
-            tbest = other < tbest ? other : tbest;
+        for (int r = 0; r < RW; ++r) zs[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float tmax = -__int_as_float(0x7f800000);
+        int sub_idx = 0, sub_planes = 0;
+        for (int zi = 0; zi < nplanes; ++zi) {
+            const int stage = zi % ST::NSTAGE;
+            mbar_wait(full_bar + stage, (zi / ST::NSTAGE) & 1);
+            const uint32_t pn = stage_base + stage * 2 * kPlaneBytes + lane_off;
+            if (zi >= p0) {
+#pragma unroll
+                for (int r = 0; r < RW; ++r) {
+                    const float4 nw = lds_f4(pn + r * ST::WF * 4);
+                    const float4 od = lds_f4(pn + kPlaneBytes + r * ST::WF * 4);
+                    zs[r] = add4(zs[r], sub4(nw, od));
+                    if (r < K || or_tail) abits = or4(abits, nw);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < RW; ++r) {
+                    const float4 nw = lds_f4(pn + r * ST::WF * 4);
+                    zs[r] = add4(zs[r], nw);
+                    if (r < K || or_tail) abits = or4(abits, nw);
+                }
+            }
+            // the stage is free once every lane's loads have landed in registers: the arrive is issued
+            // behind the last window sum (which needs them all) and a warp barrier
+            asm volatile("" ::"f"(zs[0].x), "f"(zs[RW - 1].w) : "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + stage);
+            if (zi < p0 - 1) continue;                          // z-window still filling
+            // ---- y-stage (registers) and x-stage (shuffles) of output plane t = zi - (p0 - 1)
+            float4 o = tree_sum4<PC>(zs);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k > 0) o = add4(o, sub4(zs[k + PC - 1], zs[k - 1]));
+                if (k < nvr_w) {                                // warp-uniform (the shuffles need every lane)
+                    const bool rv = LW == 32 || k < nvr;
+                    const float A = o.x + o.y, B = o.z + o.w, Q = A + B;
+                    const float Q1 = __shfl_down_sync(0xffffffffu, Q, 1);
+                    const float A2 = __shfl_down_sync(0xffffffffu, A, 2);
+                    const float e2z = __shfl_down_sync(0xffffffffu, o.z, 2);
+                    const float e2w = __shfl_down_sync(0xffffffffu, o.w, 2);
+                    const float e3x = __shfl_down_sync(0xffffffffu, o.x, 3);
+                    const float S0 = (Q + Q1) + A2;
+                    const float S1 = S0 + (e2z - o.x);
+                    const float S2 = S1 + (e2w - o.y);
+                    const float S3 = S2 + (e3x - o.z);
+                    if (cv0 && rv) tmax = fmaxf(tmax, S0);
+                    if (cv1 && rv) tmax = fmaxf(tmax, S1);
+                    if (cv2 && rv) tmax = fmaxf(tmax, S2);
+                    if (cv3 && rv) tmax = fmaxf(tmax, S3);
+                }
+            }
+            // ---- one maximum per z sub-chunk of prm.zc_fine output planes (counted, not computed)
+            if (++sub_planes == prm.zc_fine || zi == nplanes - 1) {
+                float mx = tmax;
+#pragma unroll
+                for (int o2 = 8; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+                const int q = sub_idx & 3;
+                if ((lane & 15) == 0) atomicMax(&s_key[q][slot], strip_fkey(mx));
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    if (atomicAdd(&s_cnt[q], 1) == NW - 1) {    // last warp of the CTA to close this sub-chunk
+                        __threadfence_block();
+#pragma unroll
+                        for (int i = 0; i < ST::NSLOT; ++i) {
+                            const int key = atomicExch(&s_key[q][i], kStripKeyNinf);
+                            const int ty_i = cy * ST::TYC + i / ST::TXC, tx_i = xt * ST::TXC + i % ST::TXC;
+                            if (ty_i < prm.tiles_y) {
+                                const int64_t tile = ((int64_t)zc_i * prm.tiles_y + ty_i) * prm.tiles_x + tx_i;
+                                prm.tile_max[m * prm.nent + tile * prm.zsub + sub_idx] = (double)strip_funkey(key);
+                            }
+                        }
+                        atomicExch(&s_cnt[q], 0);
+                    }
+                }
+                tmax = -__int_as_float(0x7f800000); sub_planes = 0; ++sub_idx;
+            }
         }
-        if (lane == 0 && tbest != ~0ull) atomicMin(prm.best + m, tbest);
     }
+    if (tid == 0) {   // sub-chunks past the end of a short last z-chunk hold nothing
+        const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+        const int written = (nout + prm.zc_fine - 1) / prm.zc_fine;
+        for (int i = 0; i < ST::NSLOT; ++i) {
+            const int ty_i = cy * ST::TYC + i / ST::TXC, tx_i = xt * ST::TXC + i % ST::TXC;
+            if (ty_i >= prm.tiles_y) continue;
+            const int64_t tile = ((int64_t)zc_i * prm.tiles_y + ty_i) * prm.tiles_x + tx_i;
+            for (int f = written; f < prm.zsub; ++f) prm.tile_max[m * prm.nent + tile * prm.zsub + f] = ninf;
+        }
+    }
+    box_pass_finish<0, NT, true>(prm, m, 0.0, ~0ull, red, s_flag, s_count, __uint_as_float(abits & 0x7fffffffu),
+                                 (unsigned int)(prm.chunks_z * cta_y * nxs));
 }
 
 struct PatchPlan {
@@ -1046,73 +1152,15 @@ static int run_patch(PatchParams prm, const PatchPlan& pl, int64_t M, double* gm
     return check_launch("patch_finish_kernel");
 }
 
-struct StreamPlan {
-    int64_t O0, O1, O2;
-    int xs, nxw, nyg, nzc, nyc;
-    int64_t nlb, ntiles, xz_per_map;
-};
-
-static bool stream_path_ok(const int64_t* patch) { return patch[2] <= 32; }
-
-static int make_stream_plan(const int64_t* shape, const int64_t* patch, StreamPlan& sp) {
-    PatchPlan pl;  // reuse the argument checks (ValueError when patch > image)
-    for (int d = 0; d < 3; ++d) {
-        if (shape[d] <= 0 || patch[d] <= 0)
-            return set_error(VALUES_ERR_INVALID_ARG, "patch_max: non-positive shape/patch");
-        if (patch[d] > shape[d])
-            return set_error(VALUES_ERR_INVALID_ARG,
-                             "For 'valid' mode, one must be at least as large as the other in "
-                             "every dimension (axis %d: image %lld < patch %lld)",
-                             d, (long long)shape[d], (long long)patch[d]);
-    }
-    (void)pl;
-    sp.O0 = shape[0] - patch[0] + 1; sp.O1 = shape[1] - patch[1] + 1; sp.O2 = shape[2] - patch[2] + 1;
-    sp.xs = 32 - (int)patch[2] + 1;
-    sp.nxw = (int)ceil_div(sp.O2, sp.xs);
-    sp.nyg = (int)ceil_div(shape[1], kRowsA);
-    sp.nzc = (int)ceil_div(sp.O0, kZC);
-    sp.nlb = ceil_div(sp.O0 * sp.O2, kThreads);
-    sp.nyc = (int)ceil_div(sp.O1, kYC);
-    sp.ntiles = sp.nlb * sp.nyc;
-    sp.xz_per_map = sp.O0 * shape[1] * sp.O2;
-    if (sp.ntiles > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: too many tiles");
-    return VALUES_OK;
-}
-
-template <typename T>
-static int run_patch_stream(StreamParams prm, const StreamPlan& sp, int64_t M, double* gmax,
-                            double* max_score, int64_t* bbox_lo, cudaStream_t st) {
-    const int64_t gridA = (int64_t)sp.nxw * sp.nyg * sp.nzc * M;
-    if (gridA > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: grid too large");
-    box_zx_kernel<T><<<(unsigned)gridA, kThreads, 0, st>>>(prm);
-    int rc = check_launch("box_zx_kernel");
-    if (rc) return rc;
-    for (int64_t m0 = 0; m0 < M; m0 += 65535) {  // gridDim.y limit
-        const int64_t mc = std::min<int64_t>(65535, M - m0);
-        StreamParams q = prm;
-        q.xz = prm.xz + m0 * sp.xz_per_map;
-        q.tile_max = prm.tile_max + m0 * sp.ntiles;
-        q.gmax = gmax + m0;
-        q.best = prm.best + m0;
-        const dim3 grid((unsigned)sp.ntiles, (unsigned)mc);
-        box_y_kernel<1><<<grid, kThreads, 0, st>>>(q);
-        if ((rc = check_launch("box_y_kernel<1>"))) return rc;
-        patch_select_kernel<<<(unsigned)mc, kThreads, 0, st>>>(q.tile_max, sp.ntiles, gmax + m0,
-                                                                max_score + m0, q.best);
-        if ((rc = check_launch("patch_select_kernel"))) return rc;
-        box_y_kernel<2><<<grid, kThreads, 0, st>>>(q);
-        if ((rc = check_launch("box_y_kernel<2>"))) return rc;
-    }
-    patch_finish_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(prm.best, M, sp.O1, sp.O2, bbox_lo);
-    return check_launch("patch_finish_kernel");
-}
-
-// ------------------------------------------------------------------ fused path: host side
+// ------------------------------------------------------------------ fused / march / strip paths: host side
 struct FusedPlan {
     int march;             // 1 = box_march_kernel (32x64 tiles, z first), 0 = box_fused_kernel
-    int ty, tx;            // 16x64 or 8x32; 0 = fused path not applicable
+    int strip_lw;          // > 0: the fp32 strip filter runs in front of the march (lanes per staged row: 32 / 16)
+    int ty, tx;            // 32x64 (march), 16x64 or 8x32 (fused); 0 = neither applies
     int64_t O0, O1, O2;
     int tiles_x, tiles_y, chunks_z, zc, zsub, zc_fine;
+    int tx_per, xs_stride; // x origin of march tile column tx: (tx / tx_per) * xs_stride + (tx % tx_per) * 64
+    int cta_y, nxs;        // strip filter grid: CTA rows of march tiles, x tiles
     int64_t ntiles;
 };
 
@@ -1121,10 +1169,11 @@ static size_t fused_smem_bytes(int ty, int tx, const int64_t* patch) {
     return (size_t)(R * (tx + 1) + patch[0] * ty * tx + R * (W | 1)) * sizeof(double);
 }
 
-// 0 on success (pl.ty == 0 when the patch is too large for the fused kernel's shared memory)
-static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch, FusedPlan& pl) {
-    pl.ty = pl.tx = 0;
-    pl.march = 0;
+// strip filter shapes: <K output rows per strip, consumer warps, lanes per staged row>
+using StripWide = StripTile<8, 4, 32>;     // 128-wide staged rows: 32 output rows x 119 outputs per CTA
+using StripNarrow = StripTile<8, 4, 16>;   // maps up to 64 wide: 64 output rows x 55 outputs per CTA
+
+static int check_patch_shape(const int64_t* shape, const int64_t* patch) {
     for (int d = 0; d < 3; ++d) {
         if (shape[d] <= 0 || patch[d] <= 0)
             return set_error(VALUES_ERR_INVALID_ARG, "patch_max: non-positive shape/patch");
@@ -1134,33 +1183,63 @@ static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch
                              "every dimension (axis %d: image %lld < patch %lld)",
                              d, (long long)shape[d], (long long)patch[d]);
     }
+    return VALUES_OK;
+}
+
+static bool march_applies(int path, const int64_t* shape, const int64_t* patch) {
+    return (path == 0 || path == 5) && patch[1] == 10 && patch[2] == 10 && shape[2] - 9 > 32 && shape[1] - 9 > 16 &&
+           shape[1] * shape[2] < 0x7fffffffLL;
+}
+
+// 0 on success (pl.ty == 0 when neither the march nor the fused kernel applies).
+// strip: plan the fp32 strip filter in front of the march (the caller has checked dtype / alignment).
+static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch, int path, bool strip, FusedPlan& pl) {
+    pl = FusedPlan{};
+    int rc = check_patch_shape(shape, patch);
+    if (rc) return rc;
     pl.O0 = shape[0] - patch[0] + 1; pl.O1 = shape[1] - patch[1] + 1; pl.O2 = shape[2] - patch[2] + 1;
+    pl.tx_per = 1; pl.xs_stride = 64;
     const size_t budget = 113 * 1024;  // two CTAs per SM
-    if (g_patch_path != 4 && patch[1] == 10 && patch[2] == 10 && pl.O2 > 32 && pl.O1 > 16 &&
-        shape[1] * shape[2] < 0x7fffffffLL) {
+    if (march_applies(path, shape, patch)) {
         pl.march = 1; pl.ty = 32; pl.tx = 64;
+        if (strip && path == 0) pl.strip_lw = shape[2] <= StripNarrow::WF ? 16 : 32;
     }
+    else if (path != 0 && path != 4) return VALUES_OK;
     else if (fused_smem_bytes(16, 64, patch) <= budget && pl.O2 > 32) { pl.ty = 16; pl.tx = 64; }
     else if (fused_smem_bytes(8, 32, patch) <= budget) { pl.ty = 8; pl.tx = 32; }
     else return VALUES_OK;
-    pl.tiles_x = (int)ceil_div(pl.O2, pl.tx);
     pl.tiles_y = (int)ceil_div(pl.O1, pl.ty);
-    // output planes per z-chunk: minimise (planes marched per SM in pass 1, two CTAs interleaved
-    // per SM) + (planes of the serial pass-2 re-walk of one sub-chunk)
-    const int64_t in_plane = (int64_t)pl.tiles_x * pl.tiles_y * std::max<int64_t>(M, 1);
+    int64_t units;        // CTAs of the heaviest pass per z-chunk
+    int slots = 2 * 148;  // CTAs resident at once
+    if (pl.strip_lw == 32) {
+        pl.nxs = pl.O2 <= StripWide::XS ? 1 : (int)ceil_div(pl.O2 - StripWide::XS, StripWide::XSTEP) + 1;
+        pl.tx_per = StripWide::TXC; pl.xs_stride = StripWide::XSTEP;
+        pl.tiles_x = pl.nxs * StripWide::TXC; pl.cta_y = (int)ceil_div(pl.tiles_y, StripWide::TYC);
+        units = (int64_t)pl.nxs * pl.cta_y * std::max<int64_t>(M, 1);
+    } else if (pl.strip_lw == 16) {
+        pl.nxs = 1; pl.tiles_x = 1; pl.cta_y = (int)ceil_div(pl.tiles_y, StripNarrow::TYC);
+        units = (int64_t)pl.cta_y * std::max<int64_t>(M, 1);
+        slots = 3 * 148;
+    } else {
+        pl.tiles_x = (int)ceil_div(pl.O2, pl.tx);
+        units = (int64_t)pl.tiles_x * pl.tiles_y * std::max<int64_t>(M, 1);
+    }
+    // output planes per z-chunk: minimise (planes marched per SM by the heaviest pass) + (planes of
+    // the serial re-walk of one sub-chunk by the listed passes); even splits of O0
     int64_t best_cost = -1;
     pl.zc = (int)pl.O0;
-    for (int64_t zc : {(int64_t)8, (int64_t)16, (int64_t)32, (int64_t)64, (int64_t)128, pl.O0}) {
-        if (zc > pl.O0) zc = pl.O0;
-        const int64_t ctas = in_plane * ceil_div(pl.O0, zc);
-        // planes of pure warm-up per chunk, in units of a full plane (march: register adds only)
-        const int64_t warm = pl.march ? (patch[0] - 1) / 4 + 2 : patch[0] - 1 + 2;
+    for (int64_t n = 1; n <= 16; ++n) {
+        const int64_t zc = ceil_div(pl.O0, n);
+        const int64_t ctas = units * ceil_div(pl.O0, zc);
+        // planes of pure warm-up per chunk, in units of a full plane (march / strip: register adds only)
+        const int64_t warm = pl.strip_lw ? (patch[0] - 1) / 3 + 2 : pl.march ? (patch[0] - 1) / 4 + 2 : patch[0] - 1 + 2;
         // CTAs neither run in lock-step waves nor perfectly smoothly: average both models
-        const int64_t smooth = std::max(ceil_div(ctas * (zc + warm), 2 * 148), zc + warm);
-        const int64_t waves = ceil_div(ctas, 2 * 148) * (zc + warm);
+        const int64_t smooth = std::max(ceil_div(ctas * (zc + warm), slots), zc + warm);
+        const int64_t waves = ceil_div(ctas, slots) * (zc + warm);
         const int64_t pass2 = ceil_div(zc, pl.march ? 32 : 8) + warm;
         const int64_t cost = (smooth + waves) / 2 + pass2;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; pl.zc = (int)zc; }
+        if (zc <= 4) break;
     }
     // the listed passes (exact maxima of the filter's candidates, first index) walk single sub-chunks:
     // serial latency, so the march kernel's sub-chunks are short
@@ -1203,270 +1282,99 @@ static int run_patch_fused_pc(FusedParams prm, const FusedPlan& pl, int64_t M, c
     return VALUES_OK;
 }
 
-// ------------------------------------------------------------------ K2b filter, vector form
-// The same filter pass (PASS 0 above: fp32 box-sum maxima per (tile, z sub-chunk) + a bound on
-// max |input|) rebuilt for instruction count, which is what bounds the march: 56 thread
-// instructions per voxel in fp64, ~45 in its fp32 instantiation, ~12 here.
-//  * z-stage: a thread owns float4s of the input tile (LDG.128 for the entering and the leaving
-//    plane, packed f32x2 adds, STS.128) -- 1.75 instructions per element instead of 7;
-//  * x-stage: one task = 16 outputs of one row from 7 LDS.128, one sliding chain, 4 STS.128;
-//  * y-stage: one task = 2 adjacent columns x 8 rows, LDS.64 + packed adds, on the upper four warps
-//    while the lower warps run the x-stage of the next plane;
-//  * the three stages are software-pipelined over planes (double-buffered shared memory): one block
-//    barrier per plane;
-//  * no NaN bookkeeping: max |input| is bounded by the OR of the inputs' magnitude bits (>= the
-//    maximum, < twice it, all-ones exponent iff a NaN / inf was seen; one LOP3 per two elements),
-//    and box_pass_finish<0> sends a map with non-finite inputs or possible fp32 overflow through
-//    the exact pass, so every sum here is finite.
-// Tiling, z-chunks and sub-chunk entries are the march kernel's (FusedPlan), so PASS 1 / PASS 2
-// consume its list unchanged.  Needs 16-byte aligned rows: D2 % 4 == 0, aligned base and map stride.
-struct FilterTile {
-    static constexpr int NT = 256, TY = 32, TX = 64, PC = 10;
-    static constexpr int R = TY + PC - 1;                      // 41 input rows
-    static constexpr int W4 = (TX + PC - 1 + 3) / 4;           // 19 float4 per input row
-    static constexpr int NTASK = R * W4;                       // 779 float4 per plane
-    static constexpr int NSLOT = 4;                            // three per thread + 11 left over (warp 0)
-    static constexpr int S3 = NTASK - 3 * NT;
-    static constexpr int pitchA = 84, pitchB = 68;             // == 20 / 4 mod 32 words: row-striped
-                                                               // LDS.128 / STS.128 are conflict-free
-    static constexpr int BUF = 4096;                           // floats between the two buffers of A / Bs:
-                                                               // a power of two, so the buffer toggles by XOR
-    static constexpr int XRUN = 16, NSEG = TX / XRUN;          // x task: 16 outputs of one row
-    static constexpr int YRUN = 8;                             // y task: 2 columns x 8 rows
-    static constexpr int YT0 = NT - (TX / 2) * (TY / YRUN);    // first y-stage thread (128)
-    static constexpr size_t smem = (size_t)4 * BUF * sizeof(float);   // A0 | A1 | B0 | B1
-    static_assert(W4 * 4 <= pitchA && TX <= pitchB && R * NSEG <= NT && YT0 >= 0 && S3 > 0 && S3 <= 32, "tile shape");
-    static_assert(R * pitchA <= BUF && R * pitchB <= BUF, "buffer size");
-    static_assert(XRUN + PC - 1 <= 28, "x task reads 7 float4");
-};
-
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
-__device__ __forceinline__ float4 add4(float4 a, float4 b) {
-    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
-    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
-    return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-__device__ __forceinline__ float4 sub4(float4 a, float4 b) {
-    const float2 lo = sub2(make_float2(a.x, a.y), make_float2(b.x, b.y));
-    const float2 hi = sub2(make_float2(a.z, a.w), make_float2(b.z, b.w));
-    return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-__device__ __forceinline__ unsigned int or4(unsigned int acc, float4 v) {
-    acc |= __float_as_uint(v.x) | __float_as_uint(v.y);
-    return acc | __float_as_uint(v.z) | __float_as_uint(v.w);
-}
-
-// Measured alternatives (B200, 96 maps of 128^3): this shape 487 us; the y-stage as 4 columns x 8
-// rows on two warps (fewer instructions, longer per-warp chain) 569 us; 384 threads at 80 registers
-// (24 warps / SM, two float4 slots per thread, 8-output x tasks) 668 us -- more instructions and the
-// one-plane prefetch distance no longer covers the L2 latency; the y-stage as 2 columns x 4 rows on
-// all eight warps (even work per warp, 3.25 instead of 2.1 shared loads per output) 644 us total vs 507;
-// x / y task addresses held in opaque registers (what lifted K1, which is issue-bound): 87 fewer
-// instructions in the loop, no change in time -- this kernel waits on barriers and shared-memory
-// round trips, not on issue slots.
-__global__ void __launch_bounds__(FilterTile::NT, 2) box_filter_kernel(const FusedParams prm) {
-    using FT = FilterTile;
-    constexpr int NT = FT::NT, PC = FT::PC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[NT / 32];
-    __shared__ float ymax[2][4];
-    __shared__ int s_flag;
-    __shared__ int s_count;
-    float* A = reinterpret_cast<float*>(smem_raw);             // [2][BUF] z-window sums, rows of pitchA
-    float* Bs = A + 2 * FT::BUF;                               // [2][BUF] z-x sums, rows of pitchB
-    const int p0 = prm.p0;
-    const int64_t m = blockIdx.y;
-    const int tid = threadIdx.x;
-    const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
-    const int tile = blockIdx.x;
-    const int tiles_xy = prm.tiles_x * prm.tiles_y;
-    const int tx_i = tile % prm.tiles_x, ty_i = (tile / prm.tiles_x) % prm.tiles_y, zc_i = tile / tiles_xy;
-    const int64_t zo0 = (int64_t)zc_i * prm.zc;
-    const int64_t zo1 = min(zo0 + prm.zc, prm.O0);
-    const unsigned int x0 = (unsigned int)tx_i * FT::TX, y0 = (unsigned int)ty_i * FT::TY;
-    const unsigned int D1 = (unsigned int)prm.D1, D2 = (unsigned int)prm.D2;
-    const int nplanes = (int)(zo1 - zo0) + p0 - 1, nout = (int)(zo1 - zo0);
-    const unsigned int plane_elems = D1 * D2;
-    const float* src = reinterpret_cast<const float*>(prm.maps) + m * prm.stride_m + zo0 * (int64_t)plane_elems;
-    // z-stage ownership: slot i of this thread is float4 task (row, float4 column) of the input tile;
-    // rows / columns past the map edge are clamped (they only feed masked outputs).  One running
-    // pointer per slot for the entering plane and one for the leaving plane (two 64-bit adds per
-    // load instead of a full address computation) and one shared-memory pointer that toggles
-    // between the two buffers by XOR.
-    const bool has3 = tid < FT::S3;
-    const float4* pnw[FT::NSLOT];
-    const float4* pod[FT::NSLOT];
-    unsigned int sa[FT::NSLOT];                                 // shared-memory byte address of the slot
-    const int64_t plane4 = plane_elems / 4;
-    const unsigned int a_base = (unsigned int)__cvta_generic_to_shared(A);
-#pragma unroll
-    for (int i = 0; i < FT::NSLOT; ++i) {
-        const int task = min(tid + NT * i, FT::NTASK - 1);
-        const int r = task / FT::W4, c4 = task - r * FT::W4;
-        pnw[i] = reinterpret_cast<const float4*>(src + (min(y0 + r, D1 - 1) * D2 + min(x0 + 4 * c4, D2 - 4)));
-        pod[i] = pnw[i] - plane4;                             // advanced (to plane 0) before its first use
-        sa[i] = a_base + (unsigned int)(r * FT::pitchA + 4 * c4) * 4u;
-    }
-    // x-stage task (rows striped over lanes) and y-stage task (column pairs over lanes)
-    const int task_r = tid % FT::R, task_seg = tid / FT::R;
-    const int yt = tid - FT::YT0, cp = yt & 31, rg = yt >> 5;
-    int nvr = 0;                                                // valid output rows of this y task
-    bool cv0 = false, cv1 = false;
-    if (yt >= 0) {
-        nvr = max(0, min(FT::YRUN, (int)prm.O1 - (int)(y0 + rg * FT::YRUN)));
-        cv0 = x0 + 2 * cp < prm.O2; cv1 = x0 + 2 * cp + 1 < prm.O2;
-    }
-    const bool all_valid = nvr == FT::YRUN && cv1;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 zs[FT::NSLOT], nw[FT::NSLOT], od[FT::NSLOT];
-#pragma unroll
-    for (int i = 0; i < FT::NSLOT; ++i) { zs[i] = zero4; od[i] = zero4; nw[i] = zero4; }
-    unsigned int abits = 0;
-    float tmax = -__int_as_float(0x7f800000);
-    int pend = -1;                                              // sub-chunk whose maxima sit in ymax[pend & 1]
-    int sub = 0, sub_planes = 0;                                // current z sub-chunk, its planes done so far
-    nw[0] = __ldg(pnw[0]); nw[1] = __ldg(pnw[1]); nw[2] = __ldg(pnw[2]);
-    if (has3) nw[3] = __ldg(pnw[3]);
-    for (int zi = 0; zi < nplanes + 2; ++zi) {
-        const int t = zi - (p0 - 1);
-        if (zi < nplanes) {
-            const bool ld_new = zi + 1 < nplanes, ld_old = ld_new && zi + 1 >= p0;
-#define VB_Z_SLOT(i)                                                                              \
-            {                                                                                     \
-                zs[i] = add4(zs[i], sub4(nw[i], od[i]));                                          \
-                abits = or4(abits, nw[i]);                                                        \
-                if (ld_new) { pnw[i] += plane4; nw[i] = __ldg(pnw[i]); }                          \
-                if (ld_old) { pod[i] += plane4; od[i] = __ldg(pod[i]); }                          \
-                if (t >= 0) {                                                                     \
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa[i]),         \
-                                 "f"(zs[i].x), "f"(zs[i].y), "f"(zs[i].z), "f"(zs[i].w) : "memory"); \
-                    sa[i] ^= FT::BUF * 4u;                                                        \
-                }                                                                                 \
-            }
-            VB_Z_SLOT(0)
-            VB_Z_SLOT(1)
-            VB_Z_SLOT(2)
-            if (has3) VB_Z_SLOT(3)
-#undef VB_Z_SLOT
-            if (t < 0) continue;                               // z-window still filling: registers only
-        }
-        if (pend >= 0 && tid == 0) {                           // maxima of a finished sub-chunk (written
-            const float* ym = ymax[pend & 1];                  // before the last barrier)
-            prm.tile_max[m * prm.nent + (int64_t)tile * prm.zsub + pend] =
-                (double)fmaxf(fmaxf(ym[0], ym[1]), fmaxf(ym[2], ym[3]));
-        }
-        pend = -1;
-        // uniform: does the y-stage of this step finish z sub-chunk `sub` (zc_fine output planes, fewer
-        // at the end of the tile)?  Counted, not computed: a runtime modulo costs ~25 instructions.
-        bool closes = false;
-        if (t >= 2 && t - 2 < nout) closes = ++sub_planes == prm.zc_fine || t - 1 == nout;
-        // ---- x-stage of plane t-1: 16 outputs of one row, one sliding chain
-        if (t >= 1 && t - 1 < nout && tid < FT::R * FT::NSEG) {
-            const float* row = A + ((t - 1) & 1) * FT::BUF + task_r * FT::pitchA + task_seg * FT::XRUN;
-            float v[28];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const float4 q = *reinterpret_cast<const float4*>(row + 4 * k);
-                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-            }
-            float o[FT::XRUN];
-            o[0] = tree_sum_t<PC, float>(v);
-#pragma unroll
-            for (int i = 1; i < FT::XRUN; ++i) o[i] = o[i - 1] + (v[i + PC - 1] - v[i - 1]);
-            float* dst = Bs + ((t - 1) & 1) * FT::BUF + task_r * FT::pitchB + task_seg * FT::XRUN;
-#pragma unroll
-            for (int k = 0; k < FT::XRUN / 4; ++k)
-                *reinterpret_cast<float4*>(dst + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-        }
-        // ---- y-stage of plane t-2: 2 columns x 8 rows per thread of the upper four warps
-        if (t >= 2 && t - 2 < nout && yt >= 0) {
-            const float* cb = Bs + (t & 1) * FT::BUF + rg * FT::YRUN * FT::pitchB + 2 * cp;
-            float2 c[FT::YRUN + PC - 1];
-#pragma unroll
-            for (int j = 0; j < FT::YRUN + PC - 1; ++j) c[j] = *reinterpret_cast<const float2*>(cb + j * FT::pitchB);
-            float2 o[FT::YRUN];
-            {
-                float2 q[PC / 2];
-#pragma unroll
-                for (int j = 0; j < PC / 2; ++j) q[j] = __fadd2_rn(c[2 * j], c[2 * j + 1]);
-                o[0] = __fadd2_rn(__fadd2_rn(__fadd2_rn(q[0], q[1]), __fadd2_rn(q[2], q[3])), q[4]);
-            }
-#pragma unroll
-            for (int k = 1; k < FT::YRUN; ++k) o[k] = __fadd2_rn(o[k - 1], sub2(c[k + PC - 1], c[k - 1]));
-            if (all_valid) {
-#pragma unroll
-                for (int k = 0; k < FT::YRUN; ++k) tmax = fmaxf(tmax, fmaxf(o[k].x, o[k].y));
-            } else {
-#pragma unroll
-                for (int k = 0; k < FT::YRUN; ++k) {
-                    if (k < nvr && cv0) tmax = fmaxf(tmax, o[k].x);
-                    if (k < nvr && cv1) tmax = fmaxf(tmax, o[k].y);
-                }
-            }
-            if (closes) {                                      // one maximum per z sub-chunk
-#pragma unroll
-                for (int o2 = 16; o2 > 0; o2 >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o2));
-                if (cp == 0) ymax[sub & 1][rg] = tmax;
-                tmax = -__int_as_float(0x7f800000);
-            }
-        }
-        if (closes) { pend = sub; ++sub; sub_planes = 0; }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        if (pend >= 0) {
-            const float* ym = ymax[pend & 1];
-            prm.tile_max[m * prm.nent + (int64_t)tile * prm.zsub + pend] =
-                (double)fmaxf(fmaxf(ym[0], ym[1]), fmaxf(ym[2], ym[3]));
-        }
-        // sub-chunks past the end of a short last z-chunk hold nothing
-        const int written = (int)((zo1 - zo0 + prm.zc_fine - 1) / prm.zc_fine);
-        for (int f = written; f < prm.zsub; ++f) prm.tile_max[m * prm.nent + (int64_t)tile * prm.zsub + f] = ninf;
-    }
-    box_pass_finish<0, NT, true>(prm, m, 0.0, ~0ull, red, s_flag, s_count, __uint_as_float(abits & 0x7fffffffu));
-}
-
-// err_coef of the fp32 filter: a bound on |fp32 box sum - exact box sum| / max |input| for the
-// filter kernels' operation order (u = 2^-24, every fp32 add / subtract rounds to nearest, no
-// underflow error in additions).  With a = max |input|, Z = p0 a (bound on a z-window sum):
+// err_coef of the fp32 filter: a bound on |fp32 box sum - exact box sum| / max |input| for the strip
+// kernel's operation order (u = 2^-24, every fp32 add / subtract rounds to nearest, no underflow
+// error in additions).  With a = max |input|, Z = p0 a (bound on a z-window sum), pc = 10:
 //   z-slide, K = zc + p0 - 1 steps of zs = fl(zs + fl(new - old)):  ez <= K (p0 + 2) u a
-//   x-pass, tree over pc (depth d) + at most xs slides s = fl(s + fl(in - out)):
-//                                                                   ex <= pc ez + [d pc + xs (pc + 2)] u Z
-//   y-pass, tree over pc (depth dy) + at most ys slides:            ey <= pc ex + [dy pc + ys (pc + 2)] u pc Z
-// doubled to cover the second-order terms and the exact pass's own fp64 rounding.  (The vector
-// kernel's a is the OR bound, up to twice the true maximum: conservative.)
-static double filter_err_coef(int zc, int p0, int pc, int xs, int ys, int dy = 0) {
+//   y-stage, tree over pc (depth d) + at most ys slides s = fl(s + fl(in - out)):
+//                                                                   ey <= pc ez + [d pc + ys (pc + 2)] u Z
+//   x-stage, tree-shaped start over pc (depth d) + at most xs slides: ex <= pc ey + [d pc + xs (pc + 2)] u pc Z
+// doubled to cover the second-order terms and the exact pass's own fp64 rounding.  (The kernel's a is
+// the OR of the inputs' magnitude bits, up to twice the true maximum: conservative.)
+static double filter_err_coef(int zc, int p0, int pc, int s1, int s2) {
     const double u = 5.9604644775390625e-8;
     const double K = zc + p0 - 1, d = tree_depth(pc);
     const double ez = K * (p0 + 2);
-    const double ex = pc * ez + (d * pc + xs * (pc + 2)) * p0;
-    const double ey = pc * ex + ((dy ? dy : d) * pc + ys * (pc + 2)) * (double)pc * p0;
-    return 2.0 * u * ey;
+    const double e1 = pc * ez + (d * pc + s1 * (pc + 2)) * p0;
+    const double e2 = pc * e1 + (d * pc + s2 * (pc + 2)) * (double)pc * p0;
+    return 2.0 * u * e2;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// fp32 maps [M][D0][D1][D2] as a 4-D tensor map with a [1][1][rows][cols] box
+static int make_map_tensor(const FusedParams& prm, int64_t M, int rows, int cols, CUtensorMap* tm) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return set_error(VALUES_ERR_CUDA, "patch_max: cuTensorMapEncodeTiled is not available");
+    const cuuint64_t gdim[4] = {(cuuint64_t)prm.D2, (cuuint64_t)prm.D1, (cuuint64_t)prm.D0, (cuuint64_t)M};
+    const cuuint64_t gstr[3] = {(cuuint64_t)prm.D2 * 4, (cuuint64_t)prm.D1 * prm.D2 * 4, (cuuint64_t)prm.stride_m * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)cols, (cuuint32_t)rows, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(prm.maps), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(VALUES_ERR_CUDA, "patch_max: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return VALUES_OK;
+}
+
+// can the strip filter stream these maps by TMA?  (16-byte aligned rows, planes and maps)
+static bool strip_filter_ok(const void* maps, int dtype, int64_t stride_m, const int64_t* shape) {
+    return dtype == VALUES_F32 && shape[2] % 4 == 0 && stride_m % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(maps) & 15) == 0 && shape[0] < 0x7fffffffLL && encode_tiled_fn() != nullptr;
+}
+
+template <typename ST>
+static int launch_strip_filter(const FusedParams& prm, const FusedPlan& pl, int64_t M, cudaStream_t st) {
+    auto k0 = box_strip_filter_kernel<ST::K, ST::NW, ST::LW>;
+    if (cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST::smem) != cudaSuccess)
+        return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute(%zu) failed", ST::smem);
+    CUtensorMap tm;
+    int rc = make_map_tensor(prm, M, ST::RIN, ST::WF, &tm);
+    if (rc) return rc;
+    const int64_t grid = M * pl.chunks_z * pl.cta_y * pl.nxs;
+    if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: grid too large");
+    k0<<<(unsigned)grid, ST::NT, ST::smem, st>>>(tm, prm, pl.cta_y, pl.nxs);
+    return check_launch("box_strip_filter_kernel");
 }
 
 template <typename T>
 static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cudaStream_t st) {
     using MT = MarchTile<32, 64, 10>;
-    using FT = FilterTile;
-    static_assert(FT::TY == 32 && FT::TX == 64 && FT::PC == 10, "the filter shares the march kernel's tiling");
-    constexpr bool kCanFilter = std::is_same<T, float>::value;
-    // g_patch_path: 5 = no filter, 6 = the march kernel's own fp32 instantiation as the filter
-    const bool filter = kCanFilter && g_patch_path != 5;
-    // (a 2-D image is one plane per tile: nothing to pipeline, the scalar filter is faster there)
-    const bool vec = filter && g_patch_path != 6 && prm.zc >= 4 && prm.D2 % 4 == 0 && prm.stride_m % 4 == 0 &&
-                     (reinterpret_cast<uintptr_t>(prm.maps) & 15) == 0;
-    auto k0 = box_march_kernel<float, float, 32, 64, 10, 0, 3>;   // instantiated for fp32 maps only
     auto k1 = box_march_kernel<T, double, 32, 64, 10, 1, 2>;
     auto k2 = box_march_kernel<T, double, 32, 64, 10, 2, 2>;
-    const size_t smem = MT::smem_bytes<double>(), smem0 = vec ? FT::smem : MT::smem_bytes<float>();
+    const size_t smem = MT::smem_bytes<double>();
     if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        (filter && !vec && cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0) != cudaSuccess) ||
-        (vec && cudaFuncSetAttribute(box_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0) != cudaSuccess))
+        cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute(%zu) failed", smem);
+    const bool filter = pl.strip_lw != 0;
     prm.use_list = filter ? 1 : 0;
-    prm.err_coef = vec ? filter_err_coef(prm.zc, prm.p0, 10, FT::XRUN - 1, FT::YRUN - 1)
-                       : filter_err_coef(prm.zc, prm.p0, 10, MT::SEG / 2 - 1, MT::RUN / 2 - 1);   // == values_patch_filter_err_coef
+    prm.err_coef = filter_err_coef(prm.zc, prm.p0, 10, StripWide::K - 1, 3);   // == values_patch_filter_err_coef
+    if (cudaMemsetAsync(prm.tickets, 0, (size_t)M * 4 * sizeof(unsigned int), st) != cudaSuccess)
+        return set_error(VALUES_ERR_CUDA, "patch_max: cudaMemsetAsync failed");
+    int rc;
+    if (filter) {
+        if constexpr (std::is_same<T, float>::value) {
+            rc = pl.strip_lw == 32 ? launch_strip_filter<StripWide>(prm, pl, M, st)
+                                   : launch_strip_filter<StripNarrow>(prm, pl, M, st);
+            if (rc) return rc;
+        } else {
+            return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: the strip filter runs on fp32 maps");
+        }
+    }
     for (int64_t m0 = 0; m0 < M; m0 += 65535) {  // gridDim.y limit
         const int64_t mc = std::min<int64_t>(65535, M - m0);
         FusedParams q = prm;
@@ -1476,16 +1384,6 @@ static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
         q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
         q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
         q.tickets = prm.tickets + 4 * m0;
-        if (cudaMemsetAsync(q.tickets, 0, (size_t)mc * 4 * sizeof(unsigned int), st) != cudaSuccess)
-            return set_error(VALUES_ERR_CUDA, "patch_max: cudaMemsetAsync failed");
-        int rc;
-        if (vec) {
-            box_filter_kernel<<<dim3((unsigned)pl.ntiles, (unsigned)mc), FT::NT, smem0, st>>>(q);
-            if ((rc = check_launch("box_filter_kernel"))) return rc;
-        } else if (filter) {
-            k0<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kFusedThreads, smem0, st>>>(q);
-            if ((rc = check_launch("box_march_kernel<0>"))) return rc;
-        }
         // pass 1: every tile, or (after the filter) the few listed sub-chunks -- the grid stays
         // ntiles wide because a map whose list overflowed is walked tile by tile
         k1<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kFusedThreads, smem, st>>>(q);
@@ -1579,20 +1477,23 @@ extern "C" int values_normalize_maps(const void* maps, int dtype, int64_t M, int
     return check_launch("normalize_kernel");
 }
 
-// workspace layout (streaming path): xz [M, O0, D1, O2] | tile_max [M, ntiles] | gmax [M] | best [M]
+// workspace layout (march / fused): tile_max [M, nent] | gmax [M] | best [M] | tickets [M, 4] | active [M, 1 + 64]
 //                  (tiled fallback): tile_max [M, ntiles] | gmax [M] | best [M]
+static bool patch_path_ok(int path) { return path == 0 || path == 2 || path == 4 || path == 5; }
+
 extern "C" size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* shape3_host,
-                                                   const int64_t* patch3_host) {
-    if (M <= 0 || !shape3_host || !patch3_host) return 0;
-    if (g_patch_path == 0 || g_patch_path >= 4) {
-        FusedPlan fp;
-        if (make_fused_plan(M, shape3_host, patch3_host, fp) != VALUES_OK) return 0;
-        if (fp.ty) return fused_workspace_bytes(M, fp);
-    }
-    if (stream_path_ok(patch3_host) && g_patch_path != 2) {
-        StreamPlan sp;
-        if (make_stream_plan(shape3_host, patch3_host, sp) != VALUES_OK) return 0;
-        return (size_t)(M * sp.xz_per_map + M * sp.ntiles + 2 * M) * sizeof(double);
+                                                   const int64_t* patch3_host, int path) {
+    if (M <= 0 || !shape3_host || !patch3_host || !patch_path_ok(path)) return 0;
+    if (path != 2) {
+        // dtype and alignment (which decide whether the strip filter and its tiling apply) are not
+        // known here: the larger of the two layouts
+        size_t need = 0;
+        for (int strip = 0; strip < 2; ++strip) {
+            FusedPlan fp;
+            if (make_fused_plan(M, shape3_host, patch3_host, path, strip != 0, fp) != VALUES_OK) return 0;
+            if (fp.ty) need = std::max(need, fused_workspace_bytes(M, fp));
+        }
+        if (need) return need;
     }
     PatchPlan pl;
     if (make_patch_plan(shape3_host, patch3_host, pl) != VALUES_OK) return 0;
@@ -1603,18 +1504,21 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
                                 const int64_t* shape3_host, const int64_t* patch3_host,
                                 int mean_flag, double rtol, double atol, double* max_score,
                                 int64_t* bbox_lo, void* workspace, size_t workspace_bytes,
-                                void* stream) {
+                                int path, void* stream) {
     if (!shape3_host || !patch3_host) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: NULL shape");
     if (M < 0) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: M < 0");
     if (dtype != VALUES_F32 && dtype != VALUES_F64)
         return set_error(VALUES_ERR_INVALID_ARG, "patch_max: dtype must be f32 or f64");
+    if (!patch_path_ok(path)) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: unknown path %d (0, 2, 4, 5)", path);
     cudaStream_t st = (cudaStream_t)stream;
     double* ws = reinterpret_cast<double*>(workspace);
     const double denom =
         mean_flag ? (double)patch3_host[0] * (double)patch3_host[1] * (double)patch3_host[2] : 1.0;
-    if (g_patch_path == 0 || g_patch_path >= 4) {
+    if (path != 2) {
         FusedPlan fp;
-        int rc = make_fused_plan(M, shape3_host, patch3_host, fp);
+        const bool strip = path == 0 && M > 0 && maps && march_applies(path, shape3_host, patch3_host) &&
+                           strip_filter_ok(maps, dtype, stride_m, shape3_host);
+        int rc = make_fused_plan(M, shape3_host, patch3_host, path, strip, fp);
         if (rc) return rc;
         if (fp.ty) {
             if (M == 0) return VALUES_OK;
@@ -1629,6 +1533,7 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
             prm.p0 = (int)patch3_host[0]; prm.p1 = (int)patch3_host[1]; prm.p2 = (int)patch3_host[2];
             prm.tiles_x = fp.tiles_x; prm.tiles_y = fp.tiles_y; prm.chunks_z = fp.chunks_z; prm.zc = fp.zc;
             prm.zsub = fp.zsub; prm.zc_fine = fp.zc_fine; prm.ntiles = fp.ntiles;
+            prm.tx_per = fp.tx_per; prm.xs_stride = fp.xs_stride;
             prm.nent = fused_entries(fp);
             prm.denom = denom; prm.mean_flag = mean_flag ? 1 : 0; prm.rtol = rtol; prm.atol = atol;
             prm.tile_max = ws;
@@ -1648,30 +1553,6 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
             if (dtype == VALUES_F32) return run_patch_fused<float, 8, 32>(prm, fp, M, st);
             return run_patch_fused<double, 8, 32>(prm, fp, M, st);
         }
-    }
-    if (stream_path_ok(patch3_host) && g_patch_path != 2) {
-        StreamPlan sp;
-        int rc = make_stream_plan(shape3_host, patch3_host, sp);
-        if (rc) return rc;
-        if (M == 0) return VALUES_OK;
-        if (!maps || !max_score || !bbox_lo) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: NULL pointer");
-        const size_t need = (size_t)(M * sp.xz_per_map + M * sp.ntiles + 2 * M) * sizeof(double);
-        if (!workspace || workspace_bytes < need)
-            return set_error(VALUES_ERR_WORKSPACE, "patch_max: workspace %zu < %zu", workspace_bytes, need);
-        StreamParams prm{};
-        prm.maps = maps; prm.stride_m = stride_m;
-        prm.D0 = shape3_host[0]; prm.D1 = shape3_host[1]; prm.D2 = shape3_host[2];
-        prm.O0 = sp.O0; prm.O1 = sp.O1; prm.O2 = sp.O2;
-        prm.p0 = (int)patch3_host[0]; prm.p1 = (int)patch3_host[1]; prm.p2 = (int)patch3_host[2];
-        prm.xs = sp.xs; prm.nxw = sp.nxw; prm.nyg = sp.nyg; prm.nzc = sp.nzc;
-        prm.nlb = sp.nlb; prm.nyc = sp.nyc; prm.ntiles = sp.ntiles;
-        prm.denom = denom; prm.mean_flag = mean_flag ? 1 : 0; prm.rtol = rtol; prm.atol = atol;
-        prm.xz = ws;
-        prm.tile_max = ws + M * sp.xz_per_map;
-        double* gmax = prm.tile_max + M * sp.ntiles;
-        prm.best = reinterpret_cast<unsigned long long*>(gmax + M);
-        if (dtype == VALUES_F32) return run_patch_stream<float>(prm, sp, M, gmax, max_score, bbox_lo, st);
-        return run_patch_stream<double>(prm, sp, M, gmax, max_score, bbox_lo, st);
     }
     PatchPlan pl;
     int rc = make_patch_plan(shape3_host, patch3_host, pl);
@@ -1698,12 +1579,7 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
     return run_patch<double>(prm, pl, M, gmax, max_score, bbox_lo, st);
 }
 
-extern "C" void values_debug_set_patch_path(int path) { g_patch_path = path; }
-
-extern "C" double values_patch_filter_err_coef(int zc, int p0, int vector_kernel) {
-    using MT = MarchTile<32, 64, 10>;
-    using FT = FilterTile;
+extern "C" double values_patch_filter_err_coef(int zc, int p0) {
     if (zc <= 0 || p0 <= 0) return 0.0;
-    return vector_kernel ? filter_err_coef(zc, p0, 10, FT::XRUN - 1, FT::YRUN - 1)
-                         : filter_err_coef(zc, p0, 10, MT::SEG / 2 - 1, MT::RUN / 2 - 1);
+    return filter_err_coef(zc, p0, 10, StripWide::K - 1, 3);
 }
