@@ -682,10 +682,12 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
         n_work = n_act < 0 ? (int)prm.nent : n_act;
         work = blockIdx.x; work_step = gridDim.x;
         listed = true;
-    } else if (PASS == 1 && prm.use_list && list[0] >= 0) {
-        n_work = list[0];
+    } else if (PASS == 1 && prm.use_list) {
+        // behind the filter the grid is a few CTAs per map: they share the listed entries, or -- when
+        // the list overflowed (constant maps) -- stride over every tile
         work = blockIdx.x; work_step = gridDim.x;
-        listed = true;
+        if (list[0] >= 0) { n_work = list[0]; listed = true; }
+        else n_work = (int)prm.ntiles;
     }
     const int zc_fine = listed ? prm.zc_fine : prm.zc;
     // z-slide ownership: column cx of the input tile, rows g, g + G, ...
@@ -698,7 +700,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
     const unsigned int D1 = (unsigned int)prm.D1, D2 = (unsigned int)prm.D2;
     for (; work < n_work; work += work_step) {
         int tile, fine;
-        if (!listed) { tile = blockIdx.x; fine = 0; }
+        if (!listed) { tile = prm.use_list ? work : blockIdx.x; fine = 0; }
         else { const int id = list[0] < 0 ? work : list[1 + work]; tile = id / zsub; fine = id - tile * zsub; }
         const int tx_i = tile % prm.tiles_x;
         const int ty_i = (tile / prm.tiles_x) % prm.tiles_y;
@@ -871,7 +873,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
 // Per output: 11 thread instructions and 0.19 data-pipe wavefronts (previous filter: 24 and 0.39).
 // LW = 32: staged rows of 128 floats, 119 outputs per x tile (two march tile columns: lanes 0-15 and
 // 16-31); LW = 16 (maps up to 64 wide): rows of 64 floats, two strips side by side in a warp.
-template <int K_, int NW_, int LW_> struct StripTile {
+template <int K_, int NW_, int LW_, int NSTAGE_ = 2, int MINB_ = 2> struct StripTile {
     static constexpr int K = K_, NW = NW_, LW = LW_, PC = 10;
     static constexpr int SUBS = 32 / LW;                 // strips side by side in one warp
     static constexpr int ROWS = NW * SUBS * K;           // output rows per CTA
@@ -882,7 +884,7 @@ template <int K_, int NW_, int LW_> struct StripTile {
     static constexpr int XSTEP = XS & ~3;                // x tile pitch: the innermost TMA coordinate must be a
                                                          // multiple of 16 bytes (an odd origin traps as an illegal
                                                          // instruction), so neighbouring tiles share 3 outputs
-    static constexpr int NSTAGE = 2;
+    static constexpr int NSTAGE = NSTAGE_, MINB = MINB_;
     static constexpr int PLANE = RIN * WF;               // floats per staged plane
     static constexpr int NT = (NW + 1) * 32;             // consumer warps + the producer warp
     static constexpr int TYC = ROWS / 32;                // march tile rows per CTA
@@ -926,10 +928,11 @@ template <int N> __device__ __forceinline__ float4 tree_sum4(const float4* v) {
     else return add4(tree_sum4<N / 2>(v), tree_sum4<N - N / 2>(v + N / 2));
 }
 
-template <int K, int NW, int LW>
-__global__ void __launch_bounds__(StripTile<K, NW, LW>::NT, 2)
-box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams prm, int cta_y, int nxs) {
-    using ST = StripTile<K, NW, LW>;
+template <typename ST>
+__global__ void __launch_bounds__(ST::NT, ST::MINB)
+box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams prm, int cta_y, int nxs, int ysteps,
+                        unsigned int ctas_per_map) {
+    constexpr int K = ST::K, NW = ST::NW, LW = ST::LW;
     constexpr int NT = ST::NT, RW = ST::RW, PC = ST::PC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[ST::NSTAGE];
@@ -941,15 +944,28 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
     __shared__ int s_count;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p0 = prm.p0;
-    // work item: (map, z-chunk, CTA row of march tiles, x tile); x fastest so that neighbours share halo rows in L2
+    // Two march directions.  z-march (ysteps == 0): work item = (map, z-chunk, CTA row of march tiles,
+    // x tile), x fastest so that neighbours share halo rows in L2; the ring streams the planes of the
+    // z-chunk.  y-march (single-plane maps, i.e. 2-D images; ysteps > 0): work item = (map, chunk of
+    // ysteps CTA rows, x tile) and the ring streams the CTA rows of the chunk top to bottom -- a
+    // one-plane tile would otherwise be load, compute, exit with nothing in flight.
+    const bool ym = ysteps > 0;
     int item = blockIdx.x;
     const int xt = item % nxs; item /= nxs;
-    const int cy = item % cta_y; item /= cta_y;
-    const int zc_i = item % prm.chunks_z;
-    const int64_t m = item / prm.chunks_z;
-    const int64_t zo0 = (int64_t)zc_i * prm.zc;
-    const int nout = (int)(min(zo0 + prm.zc, prm.O0) - zo0);
-    const int nplanes = nout + p0 - 1;
+    int cy, zc_i, nsteps, nout;
+    int64_t m, zo0;
+    if (ym) {
+        const int ychunks = (cta_y + ysteps - 1) / ysteps;
+        cy = (item % ychunks) * ysteps; m = item / ychunks;
+        zc_i = 0; zo0 = 0; nout = 1;
+        nsteps = min(ysteps, cta_y - cy);
+    } else {
+        cy = item % cta_y; item /= cta_y;
+        zc_i = item % prm.chunks_z; m = item / prm.chunks_z;
+        zo0 = (int64_t)zc_i * prm.zc;
+        nout = (int)(min(zo0 + prm.zc, prm.O0) - zo0);
+        nsteps = nout + p0 - 1;
+    }
     const int x0 = xt * ST::XSTEP, y0 = cy * ST::ROWS;
     const uint32_t stage_base = (smem_u32(smem_raw) + 127u) & ~127u;
     constexpr uint32_t kPlaneBytes = ST::PLANE * sizeof(float);
@@ -965,25 +981,35 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
     __syncthreads();
     unsigned int abits = 0;
     if (warp == NW) {
-        // ---- producer: one lane streams the plane tiles of this z-chunk through the ring
+        // ---- producer: one lane streams the plane tiles through the ring.  An entering plane is read
+        // again as the leaving plane p0 steps later: it is marked evict-last in L2 when it enters and
+        // evict-first when it leaves (ncu: 1.23 -> 0.93 GB of DRAM reads for 0.81 GB of maps).
         if (lane == 0) {
             tma_prefetch_desc(&tmap);
-            for (int zi = 0; zi < nplanes; ++zi) {
+            uint64_t pol_last, pol_first;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+            for (int zi = 0; zi < nsteps; ++zi) {
                 const int stage = zi % ST::NSTAGE;
                 if (zi >= ST::NSTAGE) mbar_wait(empty_bar + stage, ((zi / ST::NSTAGE) & 1) ^ 1u);
-                const bool leaving = zi >= p0;
-                mbar_expect_tx(full_bar + stage, leaving ? 2 * kPlaneBytes : kPlaneBytes);
                 const uint32_t dst = stage_base + stage * 2 * kPlaneBytes;
-                tma_load_4d_addr(dst, &tmap, x0, y0, (int)(zo0 + zi), (int)m, full_bar + stage);
-                if (leaving) tma_load_4d_addr(dst + kPlaneBytes, &tmap, x0, y0, (int)(zo0 + zi - p0), (int)m, full_bar + stage);
+                if (ym) {
+                    mbar_expect_tx(full_bar + stage, kPlaneBytes);
+                    tma_load_4d_addr(dst, &tmap, x0, y0 + zi * ST::ROWS, 0, (int)m, full_bar + stage);
+                } else {
+                    const bool leaving = zi >= p0;
+                    mbar_expect_tx(full_bar + stage, leaving ? 2 * kPlaneBytes : kPlaneBytes);
+                    tma_load_4d_addr_hint(dst, &tmap, x0, y0, (int)(zo0 + zi), (int)m, full_bar + stage, pol_last);
+                    if (leaving)
+                        tma_load_4d_addr_hint(dst + kPlaneBytes, &tmap, x0, y0, (int)(zo0 + zi - p0), (int)m,
+                                              full_bar + stage, pol_first);
+                }
             }
         }
     } else {
         // ---- consumers: lane = float4 column c4 of strip `strip` (K output rows, K + 9 input rows)
         const int c4 = lane % LW, strip = warp * ST::SUBS + lane / LW;
         const int r0 = strip * K;
-        const int nvr = max(0, min(K, (int)prm.O1 - (y0 + r0)));          // valid output rows of the strip
-        const int nvr_w = __shfl_sync(0xffffffffu, nvr, 0);                 // ... of the warp's first strip (the larger)
         const int xo = 4 * c4, xlim = min(ST::XS, (int)prm.O2 - x0);        // valid outputs: xo + j < xlim
         const bool cv0 = xo < xlim, cv1 = xo + 1 < xlim, cv2 = xo + 2 < xlim, cv3 = xo + 3 < xlim;
         // the tail rows of a strip are the own rows of the next one: only the last strip of the CTA
@@ -992,16 +1018,23 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
         const uint32_t lane_off = (uint32_t)(r0 * ST::WF + xo) * 4u;
         // entry slot of this half-warp: march tile row (r0 / 32) x tile column (lanes 16.. of a 128-wide row)
         const int slot = (r0 / 32) * ST::TXC + (LW == 32 ? lane / 16 : 0);
+        const float ninf_f = -__int_as_float(0x7f800000);
         float4 zs[RW];
 #pragma unroll
         for (int r = 0; r < RW; ++r) zs[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float tmax = -__int_as_float(0x7f800000);
-        int sub_idx = 0, sub_planes = 0;
-        for (int zi = 0; zi < nplanes; ++zi) {
+        float tm0 = ninf_f, tm1 = ninf_f, tm2 = ninf_f, tm3 = ninf_f;   // four independent max chains
+        int sub_idx = 0, sub_planes = 0, closes = 0;
+        for (int zi = 0; zi < nsteps; ++zi) {
             const int stage = zi % ST::NSTAGE;
             mbar_wait(full_bar + stage, (zi / ST::NSTAGE) & 1);
             const uint32_t pn = stage_base + stage * 2 * kPlaneBytes + lane_off;
-            if (zi >= p0) {
+            if (ym) {
+#pragma unroll
+                for (int r = 0; r < RW; ++r) {
+                    zs[r] = lds_f4(pn + r * ST::WF * 4);
+                    if (r < K || or_tail) abits = or4(abits, zs[r]);
+                }
+            } else if (zi >= p0) {
 #pragma unroll
                 for (int r = 0; r < RW; ++r) {
                     const float4 nw = lds_f4(pn + r * ST::WF * 4);
@@ -1022,8 +1055,11 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
             asm volatile("" ::"f"(zs[0].x), "f"(zs[RW - 1].w) : "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_bar + stage);
-            if (zi < p0 - 1) continue;                          // z-window still filling
-            // ---- y-stage (registers) and x-stage (shuffles) of output plane t = zi - (p0 - 1)
+            if (!ym && zi < p0 - 1) continue;                   // z-window still filling
+            // ---- y-stage (registers) and x-stage (shuffles) of this output plane / CTA row
+            const int cy_cur = ym ? cy + zi : cy;
+            const int nvr = max(0, min(K, (int)prm.O1 - (cy_cur * ST::ROWS + r0)));   // valid output rows of the strip
+            const int nvr_w = __shfl_sync(0xffffffffu, nvr, 0);         // ... of the warp's first strip (the larger)
             float4 o = tree_sum4<PC>(zs);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -1040,18 +1076,19 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
                     const float S1 = S0 + (e2z - o.x);
                     const float S2 = S1 + (e2w - o.y);
                     const float S3 = S2 + (e3x - o.z);
-                    if (cv0 && rv) tmax = fmaxf(tmax, S0);
-                    if (cv1 && rv) tmax = fmaxf(tmax, S1);
-                    if (cv2 && rv) tmax = fmaxf(tmax, S2);
-                    if (cv3 && rv) tmax = fmaxf(tmax, S3);
+                    if (cv0 && rv) tm0 = fmaxf(tm0, S0);
+                    if (cv1 && rv) tm1 = fmaxf(tm1, S1);
+                    if (cv2 && rv) tm2 = fmaxf(tm2, S2);
+                    if (cv3 && rv) tm3 = fmaxf(tm3, S3);
                 }
             }
-            // ---- one maximum per z sub-chunk of prm.zc_fine output planes (counted, not computed)
-            if (++sub_planes == prm.zc_fine || zi == nplanes - 1) {
-                float mx = tmax;
+            // ---- one maximum per z sub-chunk of prm.zc_fine output planes (counted, not computed); in the
+            // y-march every step closes the single entry of its own march tile row
+            if (ym || ++sub_planes == prm.zc_fine || zi == nsteps - 1) {
+                float mx = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3));
 #pragma unroll
                 for (int o2 = 8; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
-                const int q = sub_idx & 3;
+                const int q = closes & 3;
                 if ((lane & 15) == 0) atomicMax(&s_key[q][slot], strip_fkey(mx));
                 __syncwarp();
                 if (lane == 0) {
@@ -1061,7 +1098,7 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
 #pragma unroll
                         for (int i = 0; i < ST::NSLOT; ++i) {
                             const int key = atomicExch(&s_key[q][i], kStripKeyNinf);
-                            const int ty_i = cy * ST::TYC + i / ST::TXC, tx_i = xt * ST::TXC + i % ST::TXC;
+                            const int ty_i = cy_cur * ST::TYC + i / ST::TXC, tx_i = xt * ST::TXC + i % ST::TXC;
                             if (ty_i < prm.tiles_y) {
                                 const int64_t tile = ((int64_t)zc_i * prm.tiles_y + ty_i) * prm.tiles_x + tx_i;
                                 prm.tile_max[m * prm.nent + tile * prm.zsub + sub_idx] = (double)strip_funkey(key);
@@ -1070,11 +1107,12 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
                         atomicExch(&s_cnt[q], 0);
                     }
                 }
-                tmax = -__int_as_float(0x7f800000); sub_planes = 0; ++sub_idx;
+                tm0 = tm1 = tm2 = tm3 = ninf_f; sub_planes = 0; ++closes;
+                if (!ym) ++sub_idx;
             }
         }
     }
-    if (tid == 0) {   // sub-chunks past the end of a short last z-chunk hold nothing
+    if (tid == 0 && !ym) {   // sub-chunks past the end of a short last z-chunk hold nothing
         const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
         const int written = (nout + prm.zc_fine - 1) / prm.zc_fine;
         for (int i = 0; i < ST::NSLOT; ++i) {
@@ -1085,7 +1123,7 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
         }
     }
     box_pass_finish<0, NT, true>(prm, m, 0.0, ~0ull, red, s_flag, s_count, __uint_as_float(abits & 0x7fffffffu),
-                                 (unsigned int)(prm.chunks_z * cta_y * nxs));
+                                 ctas_per_map);
 }
 
 struct PatchPlan {
@@ -1161,6 +1199,7 @@ struct FusedPlan {
     int tiles_x, tiles_y, chunks_z, zc, zsub, zc_fine;
     int tx_per, xs_stride; // x origin of march tile column tx: (tx / tx_per) * xs_stride + (tx % tx_per) * 64
     int cta_y, nxs;        // strip filter grid: CTA rows of march tiles, x tiles
+    int ysteps;            // > 0: single-plane maps, the filter marches over ysteps CTA rows per CTA (y-march)
     int64_t ntiles;
 };
 
@@ -1216,6 +1255,11 @@ static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch
         pl.tx_per = StripWide::TXC; pl.xs_stride = StripWide::XSTEP;
         pl.tiles_x = pl.nxs * StripWide::TXC; pl.cta_y = (int)ceil_div(pl.tiles_y, StripWide::TYC);
         units = (int64_t)pl.nxs * pl.cta_y * std::max<int64_t>(M, 1);
+        if (shape[0] == 1) {   // 2-D image: y-march, about two waves of CTAs
+            const int64_t cols = (int64_t)pl.nxs * std::max<int64_t>(M, 1);
+            const int ychunks = (int)std::max<int64_t>(1, std::min<int64_t>(pl.cta_y, ceil_div(2 * slots, cols)));
+            pl.ysteps = (int)ceil_div(pl.cta_y, ychunks);
+        }
     } else if (pl.strip_lw == 16) {
         pl.nxs = 1; pl.tiles_x = 1; pl.cta_y = (int)ceil_div(pl.tiles_y, StripNarrow::TYC);
         units = (int64_t)pl.cta_y * std::max<int64_t>(M, 1);
@@ -1339,15 +1383,15 @@ static bool strip_filter_ok(const void* maps, int dtype, int64_t stride_m, const
 
 template <typename ST>
 static int launch_strip_filter(const FusedParams& prm, const FusedPlan& pl, int64_t M, cudaStream_t st) {
-    auto k0 = box_strip_filter_kernel<ST::K, ST::NW, ST::LW>;
+    auto k0 = box_strip_filter_kernel<ST>;
     if (cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST::smem) != cudaSuccess)
         return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute(%zu) failed", ST::smem);
     CUtensorMap tm;
     int rc = make_map_tensor(prm, M, ST::RIN, ST::WF, &tm);
     if (rc) return rc;
-    const int64_t grid = M * pl.chunks_z * pl.cta_y * pl.nxs;
-    if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: grid too large");
-    k0<<<(unsigned)grid, ST::NT, ST::smem, st>>>(tm, prm, pl.cta_y, pl.nxs);
+    const int64_t per_map = pl.ysteps ? ceil_div(pl.cta_y, pl.ysteps) * pl.nxs : (int64_t)pl.chunks_z * pl.cta_y * pl.nxs;
+    if (M * per_map > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "patch_max: grid too large");
+    k0<<<(unsigned)(M * per_map), ST::NT, ST::smem, st>>>(tm, prm, pl.cta_y, pl.nxs, pl.ysteps, (unsigned)per_map);
     return check_launch("box_strip_filter_kernel");
 }
 
@@ -1384,12 +1428,12 @@ static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
         q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
         q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
         q.tickets = prm.tickets + 4 * m0;
-        // pass 1: every tile, or (after the filter) the few listed sub-chunks -- the grid stays
-        // ntiles wide because a map whose list overflowed is walked tile by tile
-        k1<<<dim3((unsigned)pl.ntiles, (unsigned)mc), kFusedThreads, smem, st>>>(q);
-        if ((rc = check_launch("box_march_kernel<1>"))) return rc;
-        // pass 2: the work list normally holds one or two (tile, z sub-chunk) entries per map
+        // the work list normally holds one or two (tile, z sub-chunk) entries per map
         const unsigned g2 = (unsigned)std::min<int64_t>(prm.nent, mc >= 16 ? 8 : 32);
+        // pass 1: every tile, or (after the filter) the few listed sub-chunks
+        const unsigned g1 = filter ? (unsigned)std::min<int64_t>(pl.ntiles, g2) : (unsigned)pl.ntiles;
+        k1<<<dim3(g1, (unsigned)mc), kFusedThreads, smem, st>>>(q);
+        if ((rc = check_launch("box_march_kernel<1>"))) return rc;
         k2<<<dim3(g2, (unsigned)mc), kFusedThreads, smem, st>>>(q);
         if ((rc = check_launch("box_march_kernel<2>"))) return rc;
     }
