@@ -84,27 +84,6 @@ def load():
     if _loaded:
         return types.SimpleNamespace(**_loaded)
 
-
-def load_datamodules():
-    """The reference's two 3-D datamodules (unmodified), whose `get_val_test_data_samples` holds the
-    crop-index loop of the sliding-window path (lidc_idri_datamodule_3D.py:719-736,
-    toy_datamodule_3D.py:637-654).  Their batchgenerators / lightning imports are stubbed like the rest."""
-    load()
-    out = []
-    for name in ("uncertainty_modeling.lidc_idri_datamodule_3D", "uncertainty_modeling.toy_datamodule_3D"):
-        for _ in range(8):   # stub whatever further third-party sub-module the import asks for
-            try:
-                out.append(importlib.import_module(name))
-                break
-            except ModuleNotFoundError as e:
-                if not e.name or e.name.split(".")[0] not in {n.split(".")[0] for n in _STUBBED}:
-                    raise
-                mod = _Anything(e.name)
-                mod.__path__ = []
-                sys.modules[e.name] = mod
-        else:
-            raise RuntimeError(f"could not import {name}")
-    return out
     if not available():
         raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
     for name in _STUBBED:
@@ -148,3 +127,25 @@ def load_datamodules():
                      find_threshold=thr, ncc=ncc, ace=ace),
     )
     return types.SimpleNamespace(**_loaded)
+
+
+def load_datamodules():
+    """The reference's two 3-D datamodules (unmodified), whose `get_val_test_data_samples` holds the
+    crop-index loop of the sliding-window path (lidc_idri_datamodule_3D.py:719-736,
+    toy_datamodule_3D.py:637-654).  Their batchgenerators / lightning imports are stubbed like the rest."""
+    load()
+    out = []
+    for name in ("uncertainty_modeling.lidc_idri_datamodule_3D", "uncertainty_modeling.toy_datamodule_3D"):
+        for _ in range(8):   # stub whatever further third-party sub-module the import asks for
+            try:
+                out.append(importlib.import_module(name))
+                break
+            except ModuleNotFoundError as e:
+                if not e.name or e.name.split(".")[0] not in {n.split(".")[0] for n in _STUBBED}:
+                    raise
+                mod = _Anything(e.name)
+                mod.__path__ = []
+                sys.modules[e.name] = mod
+        else:
+            raise RuntimeError(f"could not import {name}")
+    return out

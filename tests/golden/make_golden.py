@@ -230,10 +230,48 @@ def formats_cases(ref, carrier):
     print("save_data_3d", len(recorded), "files")
 
 
+A5_CASES = [((20, 17, 33), 8, 0.5), ((64, 64, 64), 16, 1), ((70, 45, 33), 16, 0.75), ((40, 40, 40), 10, 0.25),
+            ((33, 20, 17), 8, 0.3), ((16, 16, 16), 16, 1), ((15, 40, 40), 16, 0.5), ((128, 128, 128), 64, 0.5),
+            ((256, 256, 256), 64, 0.5), ((256, 256, 256), 64, 1)]
+
+
+def patch_grid_cases():
+    import json
+
+    """SURVEY 8 row a5: the crop-index loop of the sliding-window path, produced by the reference's own
+    get_val_test_data_samples (lidc_idri_datamodule_3D.py:719-736; toy_datamodule_3D.py:637-654 must
+    agree) on temporary .npy volumes -> tests/golden/patch_grid.json."""
+    import tempfile
+    from pathlib import Path
+
+    lidc, toy = ref_loader.load_datamodules()
+    out = []
+    for shape, p, overlap in A5_CASES:
+        crops = {}
+        for mod, is_toy in ((lidc, False), (toy, True)):
+            with tempfile.TemporaryDirectory() as d:
+                sub = "Tr" if is_toy else ""
+                os.makedirs(Path(d) / f"images{sub}")
+                os.makedirs(Path(d) / f"labels{sub}")
+                np.save(Path(d) / f"images{sub}" / "vol.npy", np.zeros(shape, np.uint8))
+                samples = mod.get_val_test_data_samples(d, subject_ids=["vol.npy"], num_raters=1,
+                                                        patch_size=p, patch_overlap=overlap)
+                crops[is_toy] = [s["crop_idx"] for s in samples]
+        assert crops[False] == crops[True]
+        out.append({"shape": list(shape), "patch_size": p, "patch_overlap": overlap,
+                    "crops": [[list(ax) for ax in c] for c in crops[False]]})
+    with open(os.path.join(HERE, "patch_grid.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("patch_grid", len(out), "cases,", sum(len(c["crops"]) for c in out), "crops")
+
+
 def main():
     ref = ref_loader.load()
     if "--only-k4" in sys.argv:
         k4_cases(ref)
+        return
+    if "--only-a5" in sys.argv:
+        patch_grid_cases()
         return
     gen = torch.Generator().manual_seed(20261017)
 
@@ -313,6 +351,8 @@ def main():
     agg["thresholds"] = np.array([0.0, 0.5, 0.9, 2.0])
     np.savez_compressed(os.path.join(HERE, "c3_aggregations.npz"), **agg)
     print("c3_aggregations", len(agg), "arrays")
+
+    patch_grid_cases()
 
     # ---- stitching through the reference DataCarrier3D (C=2 hardcoded there)
     from oracle import values_oracle as vo

@@ -163,3 +163,19 @@ def test_k4_ncc_ace_golden(golden_dir):
     np.testing.assert_array_equal(tot, g["cs_total"])
     assert nz == int(g["cs_nonzero"]) and vo.calc_ace(g["cs_correct"], g["cs_conf"]) == float(g["cs_ace"])
     assert vo.compute_ncc(g["ncc32_a"], g["ncc32_b"]) == g["ncc32"]
+
+
+def test_a5_patch_grid_golden(golden_dir):
+    """the fixture holds the crop tuples the reference's own datamodule loop produced
+    (tests/golden/make_golden.py::patch_grid_cases); the oracle and the product's host-side
+    patch_grid (pure integer arithmetic, no device) must both reproduce them, in order."""
+    import json
+
+    from values_b200.stitching import patch_grid
+
+    cases = json.load(open(os.path.join(golden_dir, "patch_grid.json")))
+    assert len(cases) >= 8
+    for c in cases:
+        want = [tuple(tuple(ax) for ax in crop) for crop in c["crops"]]
+        assert vo.patch_grid(c["shape"], c["patch_size"], c["patch_overlap"]) == want
+        assert patch_grid(c["shape"], c["patch_size"], c["patch_overlap"]) == want

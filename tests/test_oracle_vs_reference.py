@@ -123,3 +123,36 @@ def test_patch_install_rebinds_and_restores_reference_names(ref):
         patch.uninstall(saved)
     after = (t3d.calculate_uncertainty, dc.DataCarrier3D, agg.patch_level_aggregation, dc.save, edl.ExperimentDataloader)
     assert all(a is b for a, b in zip(before, after))
+
+
+A5_CASES = [((20, 17, 33), 8, 0.5), ((64, 64, 64), 16, 1), ((70, 45, 33), 16, 0.75), ((40, 40, 40), 10, 0.25),
+            ((33, 20, 17), 8, 0.3), ((16, 16, 16), 16, 1), ((15, 40, 40), 16, 0.5), ((128, 128, 128), 64, 0.5)]
+
+
+def reference_crop_loop(module, shape, patch_size, overlap, tmp_path, toy):
+    """Run the reference's own get_val_test_data_samples (the crop-index loop of the sliding-window
+    path) on a temporary .npy volume and return its crop tuples."""
+    import os
+
+    sub = "Tr" if toy else ""
+    os.makedirs(tmp_path / f"images{sub}", exist_ok=True)
+    os.makedirs(tmp_path / f"labels{sub}", exist_ok=True)
+    np.save(tmp_path / f"images{sub}" / "vol.npy", np.zeros(shape, np.uint8))
+    np.save(tmp_path / f"labels{sub}" / ("vol_00.npy" if toy else "vol_00_mask.npy"), np.zeros(shape, np.uint8))
+    samples = module.get_val_test_data_samples(str(tmp_path), subject_ids=["vol.npy"], num_raters=1,
+                                               patch_size=patch_size, patch_overlap=overlap)
+    assert all(s["image_path"].endswith("vol.npy") and s["label_paths"] is not None for s in samples)
+    return [s["crop_idx"] for s in samples]
+
+
+@pytest.mark.parametrize("shape,patch_size,overlap", A5_CASES)
+def test_a5_patch_grid_is_the_reference_crop_loop(shape, patch_size, overlap, tmp_path):
+    """lidc_idri_datamodule_3D.py:719-736 and toy_datamodule_3D.py:637-654, run
+    unmodified, against the oracle's patch_grid (the product's patch_grid is compared with the
+    committed fixture tests/golden/patch_grid.json, which make_golden.py writes from this loop)."""
+    lidc, toy = ref_loader.load_datamodules()
+    want = reference_crop_loop(lidc, shape, patch_size, overlap, tmp_path / "lidc", toy=False)
+    assert want == reference_crop_loop(toy, shape, patch_size, overlap, tmp_path / "toy", toy=True)
+    assert want == vo.patch_grid(shape, patch_size, overlap)
+    if min(shape) < patch_size:
+        assert want == []

@@ -1255,10 +1255,14 @@ static int make_fused_plan(int64_t M, const int64_t* shape, const int64_t* patch
         pl.tx_per = StripWide::TXC; pl.xs_stride = StripWide::XSTEP;
         pl.tiles_x = pl.nxs * StripWide::TXC; pl.cta_y = (int)ceil_div(pl.tiles_y, StripWide::TYC);
         units = (int64_t)pl.nxs * pl.cta_y * std::max<int64_t>(M, 1);
-        if (shape[0] == 1) {   // 2-D image: y-march, about two waves of CTAs
+        if (shape[0] == 1) {   // 2-D image: y-march; chunks of CTA rows chosen by waves x (steps + ring fill)
             const int64_t cols = (int64_t)pl.nxs * std::max<int64_t>(M, 1);
-            const int ychunks = (int)std::max<int64_t>(1, std::min<int64_t>(pl.cta_y, ceil_div(2 * slots, cols)));
-            pl.ysteps = (int)ceil_div(pl.cta_y, ychunks);
+            int64_t best = -1;
+            for (int yc = 1; yc <= pl.cta_y; ++yc) {
+                const int64_t steps = ceil_div(pl.cta_y, yc);
+                const int64_t cost = ceil_div(cols * ceil_div(pl.cta_y, steps), slots) * (steps + 2);
+                if (best < 0 || cost < best) { best = cost; pl.ysteps = (int)steps; }
+            }
         }
     } else if (pl.strip_lw == 16) {
         pl.nxs = 1; pl.tiles_x = 1; pl.cta_y = (int)ceil_div(pl.tiles_y, StripNarrow::TYC);
