@@ -1484,7 +1484,11 @@ extern "C" int values_map_reduce(const void* maps, int dtype, int64_t M, int64_t
         return set_error(VALUES_ERR_WORKSPACE, "map_reduce: workspace %zu < %zu", workspace_bytes, need);
     ThrTable thr{};
     thr.n = thresholds_host ? n_thresholds : 0;
-    for (int i = 0; i < thr.n; ++i) thr.v[i] = thresholds_host[i];
+    // numpy compares an fp32 image with a Python-float threshold in fp32 (`image >= threshold`,
+    // aggregate_uncertainties.py:61-62), and so do K1's fused threshold sums: for fp32 maps the
+    // threshold is rounded to fp32 first (a voxel equal to fl32(0.7) counts for threshold 0.7)
+    for (int i = 0; i < thr.n; ++i)
+        thr.v[i] = dtype == VALUES_F32 ? (double)(float)thresholds_host[i] : thresholds_host[i];
     const int64_t bpm = ceil_div(V, kThreads * kReduceEPT);
     if (bpm * M > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "map_reduce: grid too large");
     const unsigned grid = (unsigned)(bpm * M);

@@ -39,6 +39,25 @@ class DataCarrier3D:
         # and `num_predictions` become weighted sums.  None = uniform, the reference's behaviour.
         self.patch_weight = patch_weight
 
+    @staticmethod
+    def load_image(sample: Dict) -> Dict:
+        """Drop-in for data_carrier_3D.py:59-97 (called by predict_cases, test_3D.py:369, 418): the
+        input dict of ONE crop of a 3-D `.npy` volume -- host-side file slicing, nothing for the GPU.
+        Keys: image_paths, label_paths, crop_idx, org_image_size, data [1, p,p,p], seg [R, 1, p,p,p] (int32)."""
+        (x0, x1), (y0, y1), (z0, z1) = sample["crop_idx"]
+        volume = np.load(sample["image_path"], mmap_mode="r")
+        out = {
+            "image_paths": [sample["image_path"]],
+            "label_paths": [sample["label_paths"]],
+            "crop_idx": [sample["crop_idx"]],
+            "org_image_size": [volume.shape],
+            "data": np.expand_dims(volume[x0:x1, y0:y1, z0:z1], 0),
+        }
+        if sample["label_paths"] is not None:
+            crops = [np.load(path, mmap_mode="r")[x0:x1, y0:y1, z0:z1] for path in sample["label_paths"]]
+            out["seg"] = np.expand_dims(np.array(crops, dtype=np.intc), 1)
+        return out
+
     def _dev(self) -> torch.device:
         if self.device is None:
             self.device = _lib.require_cuda()
@@ -209,6 +228,21 @@ class DataCarrier3D:
                     os.makedirs(unc_dir, exist_ok=True)
                     formats.save_from_device(norm[unc], os.path.join(unc_dir, name + ".nii.gz"), header)
 
+    def log_metrics(self) -> None:
+        """Drop-in for data_carrier_3D.py:373-391: `metrics.json` in the results directory, one entry
+        per image plus the mean of every metric over the images."""
+        import json
+        import os
+
+        per_image = {path: dict(value["metrics"]) for path, value in self.data.items()}
+        names = []
+        for scores in per_image.values():
+            names += [m for m in scores if m not in names]
+        per_image["mean"] = {m: np.asarray([s[m] for p, s in per_image.items() if p != "mean" and m in s]).mean()
+                             for m in names}
+        with open(os.path.join(self.save_dir, "metrics.json"), "w") as f:
+            json.dump(per_image, f, indent=2)
+
     def numpy_data(self) -> Dict[str, Dict]:
         """The reference's `.data` layout with numpy arrays (torch fp32 maps stay torch CPU
         tensors, as test_3D.py:533 stores them)."""
@@ -224,3 +258,39 @@ class DataCarrier3D:
                     e[name] = val
             out[key] = e
         return out
+
+
+def calculate_metrics(test_datacarrier) -> None:
+    """Drop-in for calculate_metrics (uncertainty_modeling/test_3D.py:537-575) on a device-resident
+    carrier: the mean softmax prediction and the rater labels are normalised on the GPU
+    (`normalize_maps`, the `/ clip(count, 1)` of :545-547, 553-566); GED / max-Dice come from
+    values_b200.segmetrics.calculate_ged; the SoftDice + NLL loss and Dice of the mean prediction
+    (calculate_test_metrics, test_3D.py:250-281 -- model quality, not on the hot path) are taken from
+    the reference module when it is imported, on the host as the reference does.  A reference
+    (numpy) DataCarrier3D is passed through to the reference's own function."""
+    import sys
+
+    from .segmetrics import calculate_ged
+
+    ref = sys.modules.get("uncertainty_modeling.test_3D") or sys.modules.get("test_3D")
+    if not isinstance(test_datacarrier, DataCarrier3D):
+        original = getattr(ref, "_values_b200_original_calculate_metrics", None) if ref else None
+        if original is None:
+            raise TypeError("calculate_metrics expects a values_b200.DataCarrier3D")
+        return original(test_datacarrier)
+    for key, value in test_datacarrier.data.items():
+        cnt = value["_count"]
+        size = tuple(cnt.shape)
+        n_pred, n_cls = value["softmax_pred"].shape[:2]
+        clip_min = 1.0 if test_datacarrier.patch_weight is None else 0.0
+        sm = normalize_maps(value["softmax_pred"].reshape((n_pred * n_cls,) + size), cnt, clip_min)
+        sm = sm.reshape((n_pred, n_cls) + size)
+        metrics_dict = {}
+        if ref is not None and hasattr(ref, "calculate_test_metrics"):
+            # :545-552 -- the reference averages RAW sums / count over samples, gt = raw label sums
+            mean_sm = torch.mean(sm, dim=0).unsqueeze(0).cpu()
+            metrics_dict.update(ref.calculate_test_metrics(mean_sm, value["seg"].cpu()))
+        if value["seg"].shape[0] > 1 or n_pred > 1:
+            gt = normalize_maps(value["seg"].to(torch.float64), cnt, clip_min).to(torch.int32)   # np.asarray(.., intc)
+            metrics_dict.update(calculate_ged(sm, gt))
+        value["metrics"] = metrics_dict

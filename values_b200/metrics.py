@@ -136,6 +136,19 @@ def calib_bins_fused(unc_map: torch.Tensor, pred_seg: torch.Tensor, reference_se
     ldt = pred_seg.dtype if pred_seg.dtype == reference_segs.dtype else torch.int64
     if ldt not in (torch.uint8, torch.int32, torch.int64):
         ldt = torch.int64
+    # gt_seg files are fp64 (label sum / count, data_carrier_3D.py:232-241) and the reference compares
+    # them with pred_seg and ignore_value in floating point (ace.py:108-117): a non-integral label
+    # (overlapping patches whose raters disagree) equals no class.  Such voxels get a label no
+    # prediction can take instead of being truncated to a class.
+    if reference_segs.is_floating_point():
+        frac = reference_segs != reference_segs.round()
+        reference_segs = reference_segs.round().to(torch.int64)
+        if bool(frac.any()):
+            ldt = torch.int64
+            reference_segs = torch.where(frac, torch.full_like(reference_segs, torch.iinfo(torch.int32).max),
+                                         reference_segs)
+    if pred_seg.is_floating_point():
+        pred_seg = pred_seg.round()
     pred_seg = pred_seg.to(ldt).contiguous()
     reference_segs = reference_segs.to(ldt).contiguous()
     dev = unc_map.device

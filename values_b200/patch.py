@@ -16,6 +16,7 @@ _PATCHES = {
         "calculate_one_minus_msr": uncertainty.calculate_one_minus_msr,
         "caculcate_uncertainty_multiple_pred": uncertainty.caculcate_uncertainty_multiple_pred,
         "calculate_ged": segmetrics.calculate_ged,
+        "calculate_metrics": data_carrier.calculate_metrics,
         "DataCarrier3D": data_carrier.DataCarrier3D,
     },
     "uncertainty_modeling.test_2D": {
@@ -23,6 +24,9 @@ _PATCHES = {
         "calculate_one_minus_msr": uncertainty.calculate_one_minus_msr,
     },
     "uncertainty_modeling.data_carrier_3D": {"DataCarrier3D": data_carrier.DataCarrier3D},
+    # lightning_experiment.py:23 binds the class at import time (`from data_carrier_3D import DataCarrier3D`)
+    # and instantiates it at :79; its test_step / on_test_end (:399, 405) only call concat_data / save_data
+    "uncertainty_modeling.lightning_experiment": {"DataCarrier3D": data_carrier.DataCarrier3D},
     "evaluation.uncertainty_aggregation.aggregate_uncertainties": {
         "patch_level_aggregation": aggregation.patch_level_aggregation,
         "image_level_aggregation": aggregation.image_level_aggregation,
@@ -75,13 +79,22 @@ def install(import_missing: bool = False, file_io: bool = False) -> dict:
                 mod = importlib.import_module(mod_name)
             except Exception:
                 mod = None
-        if mod is None:
-            continue
-        saved[mod_name] = {}
-        for name, fn in names.items():
-            if hasattr(mod, name):
-                saved[mod_name][name] = getattr(mod, name)
-                setattr(mod, name, fn)
+        # The reference runs with uncertainty_modeling/ itself on sys.path and imports its own files
+        # under their BARE names too (`from data_carrier_3D import ...`, lightning_experiment.py:23;
+        # `from loss_modules import ...`, `from main import set_seed`, test_3D.py:23-24): a module can
+        # therefore exist twice, as `uncertainty_modeling.x` and as `x`.  Both copies are rebound.
+        bare = sys.modules.get(mod_name.rpartition(".")[2]) if mod_name.startswith("uncertainty_modeling.") else None
+        for key, target in ((mod_name, mod), (mod_name.rpartition(".")[2], bare)):
+            if target is None or (key != mod_name and target is mod):
+                continue
+            saved[key] = {}
+            for name, fn in names.items():
+                if hasattr(target, name):
+                    original = getattr(target, name)
+                    saved[key][name] = original
+                    if name == "calculate_metrics":   # the numpy carrier of the reference still goes to its own code
+                        target._values_b200_original_calculate_metrics = original
+                    setattr(target, name, fn)
     return saved
 
 

@@ -76,6 +76,7 @@ class AsyncScoreGather:
         with torch.cuda.stream(self.stream):
             out = gather_scores(local, n_items, self.group)
         local.record_stream(self.stream)
+        out.record_stream(main)     # allocated on the side stream, read by the caller on the main one
         self._tables.append((local, out))
         if len(self._tables) > self.keep:
             self._tables.pop(0)
