@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VALUES_ABI_VERSION 5
+#define VALUES_ABI_VERSION 6
 
 typedef enum {
     VALUES_F32 = 0, VALUES_F64 = 1, VALUES_BF16 = 2,
@@ -57,9 +57,11 @@ int64_t values_launch_count(void);
  *                               volume-major layout [B, 3, V] that K2b consumes
  *   mean_argmax   uint8 [B, V]      or NULL
  *   sample_argmax uint8 [B, N, V]   or NULL
- *   scores  double [B, 3, 3] or NULL: per map (pe, ee, mi): {sum, sum over v>=thr, count v>=thr}
+ *   scores  double rows or NULL: per map (pe, ee, mi): {sum, sum over v>=thr, count v>=thr}
  *           = image_level_aggregation / threshold_aggregation numerators fused into the sweep
- *           (evaluation/uncertainty_aggregation/aggregate_uncertainties.py:34-37, 61-62).
+ *           (evaluation/uncertainty_aggregation/aggregate_uncertainties.py:34-37, 61-62); the row of
+ *           (volume b, map k) starts at scores[(3 b + k) * score_stride]: score_stride = 3 is a packed
+ *           [B, 3, 3] array, 7 writes columns 0..2 of a [B, 3, 7] score table in place.
  *   thresholds_host  3 doubles (pe, ee, mi) or NULL (then thr columns are 0).
  *   workspace: values_uncertainty_workspace_bytes(B, V, dtype) bytes when scores != NULL.
  */
@@ -68,8 +70,14 @@ int values_uncertainty_fused(const void* probs, int dtype, int64_t B, int64_t N,
                              int64_t V, int64_t stride_b, int64_t stride_n, int64_t stride_c,
                              float* pe, float* ee, float* mi, int64_t map_stride_b,
                              uint8_t* mean_argmax, uint8_t* sample_argmax, double* scores,
-                             const double* thresholds_host, void* workspace,
-                             size_t workspace_bytes, void* stream);
+                             int64_t score_stride, const double* thresholds_host, void* workspace,
+                             size_t workspace_bytes, int variant, int tiles_per_cta, void* stream);
+/* `variant` and `tiles_per_cta` choose the kernel for THIS call (no process-wide state); 0 / 0 is the
+ * automatic choice.  The alternatives exist so that tests and benchmarks can run two implementations
+ * of the same arithmetic against each other -- every variant gives bit-identical outputs:
+ * 1 = register-stream kernel instead of the bulk-copy (TMA) ring, 2 = ring with 4-row stages where
+ * 8-row stages are the default, 3 = 8-row stages x 3 at two CTAs per SM, 4 = (fp64 stacks) sample-outer
+ * kernel instead of the class-outer ring; tiles_per_cta 1..64 fixes the voxel tiles a CTA walks. */
 
 /* Replaces calculate_one_minus_msr(softmax_pred)  test_3D.py:521-525 and
  * ExperimentDataloader.get_max_softmax_pred  evaluation/experiment_dataloader.py:38-49.
@@ -97,14 +105,17 @@ int values_map_reduce(const void* maps, int dtype, int64_t M, int64_t V, int64_t
  * |sum - max| <= atol + rtol*|max| (np.isclose defaults rtol 1e-5, atol 1e-8).
  *   maps [M, shape[0], shape[1], shape[2]] (stride_m between maps; last axis contiguous);
  *   ndim in {1,2,3}: unused leading axes must have shape 1 and patch 1.
- *   max_score double [M]; bbox_lo int64 [M, 3] (leading unused axes report 0).
+ *   max_score double, map m at max_score[m * score_stride]; bbox_lo: the corner of map m at
+ *   bbox_lo[m * bbox_stride + 0..2], as int64 (bbox_dtype VALUES_I64) or as double (VALUES_F64, for
+ *   an fp64 score table written in place); leading unused axes report 0, (-1, -1, -1) on a NaN map.
  * Returns VALUES_ERR_INVALID_ARG if any patch > shape (the reference raises ValueError).
  */
 size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* shape3_host,
                                         const int64_t* patch3_host, int path);
 int values_patch_max(const void* maps, int dtype, int64_t M, int64_t stride_m,
                      const int64_t* shape3_host, const int64_t* patch3_host, int mean_flag,
-                     double rtol, double atol, double* max_score, int64_t* bbox_lo,
+                     double rtol, double atol, double* max_score, int64_t score_stride,
+                     void* bbox_lo, int bbox_dtype, int64_t bbox_stride,
                      void* workspace, size_t workspace_bytes, int path, void* stream);
 /* `path` selects the implementation for THIS call (no process-wide state): 0 automatic -- for
  * 10x10 in-plane patches (every reference config) an fp32 filter pass streams the maps by TMA
@@ -132,7 +143,8 @@ int values_stitch_accumulate(const void* patches, int patch_dtype, int64_t patch
                              const int32_t* crop_lo, int64_t n_sel, int64_t N, int64_t C,
                              const int64_t* patch3_host, const int64_t* vol3_host,
                              void* out_sum, int out_dtype, double* out_count, int accumulate,
-                             void* stream);
+                             int path, void* stream);
+/* `path`: 0 automatic (vector kernel when rows are 16-byte aligned), 1 scalar kernel; same results. */
 
 /* The same accumulator with a per-patch importance map (BASELINE.json north_star: "Gaussian-
  * weighted sliding-window patch stitching"; the reference itself accumulates with uniform weights,
@@ -144,7 +156,7 @@ int values_stitch_accumulate_weighted(const void* patches, int patch_dtype, int6
                                       const int32_t* crop_lo, const double* weight, int64_t n_sel,
                                       int64_t N, int64_t C, const int64_t* patch3_host,
                                       const int64_t* vol3_host, void* out_sum, int out_dtype,
-                                      double* out_count, int accumulate, void* stream);
+                                      double* out_count, int accumulate, int path, void* stream);
 
 /* Save-time normalisation (data_carrier_3D.py:215-217, 326-329):
  *   out[m, v] = (double) maps[m, v] / max(count[v], clip_min)   -> fp64 as written to NIfTI;
@@ -235,16 +247,10 @@ int values_confusion_counts(const void* labels_a, int64_t Na, int64_t stride_a, 
 int values_reverse_axes(const void* in, void* out, int elem_bytes, int64_t n0, int64_t n1,
                         int64_t n2, void* stream);
 
-/* Tuning hooks for benchmarks and tests (process-wide; 0 restores the automatic choice):
- * voxel tiles per CTA of the K1 stream kernel, and its batch / occupancy variant. */
-void values_debug_set_k1_iter(int iter);
-void values_debug_set_k1_variant(int variant);
 /* Pure host function: the error bound of K2b's fp32 filter pass, |fp32 box sum - exact box sum| <=
  * coef * max |input| for 10x10 in-plane patches, z-chunks of zc output planes and p0 planes per window.
  * tests/test_filter_bound.py checks it against an emulation of the kernel's operation order. */
 double values_patch_filter_err_coef(int zc, int p0);
-/* K3 implementation: 0 automatic (vector kernel when rows are 16-byte aligned), 1 scalar kernel. */
-void values_debug_set_stitch_path(int path);
 
 #ifdef __cplusplus
 }

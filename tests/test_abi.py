@@ -75,13 +75,13 @@ def test_invalid_arguments_are_rejected_before_any_launch():
     from values_b200 import _lib
 
     rc = _lib.lib.values_uncertainty_fused(None, _lib.F32, 1, 0, 2, 16, 0, 0, 0, None, None, None, 0,
-                                           None, None, None, None, None, 0, None)
+                                           None, None, None, 3, None, None, 0, 0, 0, None)
     assert rc == _lib.ERR_INVALID_ARG and b"bad sizes" in _lib.lib.values_last_error()
     rc = _lib.lib.values_uncertainty_fused(None, 7, 1, 2, 2, 16, 32, 16, 16, None, None, None, 0,
-                                           None, None, None, None, None, 0, None)
+                                           None, None, None, 3, None, None, 0, 0, 0, None)
     assert rc == _lib.ERR_INVALID_ARG   # NULL stack / unknown dtype
     sh, pa = _lib.i64x3([8, 8, 8]), _lib.i64x3([10, 10, 10])
-    rc = _lib.lib.values_patch_max(None, _lib.F32, 1, 512, sh, pa, 0, 1e-5, 1e-8, None, None, None, 0, 0, None)
+    rc = _lib.lib.values_patch_max(None, _lib.F32, 1, 512, sh, pa, 0, 1e-5, 1e-8, None, 1, None, _lib.I64, 3, None, 0, 0, None)
     assert rc == _lib.ERR_INVALID_ARG and b"valid" in _lib.lib.values_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc)

@@ -115,14 +115,16 @@ def test_c2_vs_oracle(vb, vo, n, c, spatial, dtype):
 
 
 @pytest.mark.parametrize("n,c,spatial,dtype", [
-    (16, 4, (64, 64, 40), torch.float32),   # RS = 8 (two sub-batches of 4); variants 13 / 14: RS = 4 / 8 x 3 stages
+    (16, 4, (64, 64, 40), torch.float32),   # RS = 8 (two sub-batches of 4); variants 2 / 3: RS = 4 / 8 x 3 stages
     (12, 3, (40, 64, 24), torch.float32),   # RS = 4
     (10, 20, (96, 132), torch.float32),     # RS = 5
     (6, 3, (50, 64), torch.float32),        # RS = 2, ragged last tile
     (7, 5, (40, 52), torch.float32),        # RS = 1
     (8, 4, (33, 64), torch.bfloat16),
     (16, 4, (24, 40, 26), torch.float64),   # fp64: class-outer ring kernel (per-sample accumulators) vs
-    (8, 2, (30, 50), torch.float64),        # the sample-outer kernel (variant 15)
+    (8, 2, (30, 50), torch.float64),        # the sample-outer kernel (variant 4)
+    (5, 2, (32, 32, 32), torch.float64),    # the reference's own 3-D case: 5-member ensemble, fp64
+    (10, 3, (40, 36), torch.float64),
 ])
 def test_k1_kernels_agree(vb, n, c, spatial, dtype):
     """The bulk-copy (TMA ring) kernel and the register-stream kernel share their arithmetic and
@@ -130,15 +132,12 @@ def test_k1_kernels_agree(vb, n, c, spatial, dtype):
     tiles-per-CTA setting."""
     x = softmax_stack(n * 7 + c, 3 * n, c, spatial).reshape(3, n, c, *spatial).to(dtype).cuda()
     outs = []
-    try:
-        for variant, it in [(0, 0), (0, 1), (0, 3), (8, 0), (8, 2), (13, 0), (14, 0), (15, 0)]:
-            vb._lib.lib.values_debug_set_k1_variant(variant)
-            vb._lib.lib.values_debug_set_k1_iter(it)
-            r = vb.uncertainty_fused(x, mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05))
-            outs.append((r.pred_entropy, r.expected_entropy, r.mutual_information, r.mean_argmax, r.scores))
-    finally:
-        vb._lib.lib.values_debug_set_k1_variant(0)
-        vb._lib.lib.values_debug_set_k1_iter(0)
+    # (variant, tiles per CTA): automatic ring, ring with fixed tiles per CTA, register-stream kernel,
+    # 4-row stages, 8-row stages x 3, sample-outer kernel (fp64) -- per-call arguments, no process state
+    for variant, it in [(0, 0), (0, 1), (0, 3), (1, 0), (1, 2), (2, 0), (3, 0), (4, 0)]:
+        r = vb.uncertainty_fused(x, mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05),
+                                 variant=variant, tiles_per_cta=it)
+        outs.append((r.pred_entropy, r.expected_entropy, r.mutual_information, r.mean_argmax, r.scores))
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert torch.equal(a, b)
@@ -425,12 +424,10 @@ def test_c3_map_reduce_vs_oracle(vb, vo):
 
 # --------------------------------------------------------------------------------- stitch
 @pytest.fixture(params=[0, 1], ids=["k3-auto", "k3-scalar"])
-def stitch_path(request, vb):
+def stitch_path(request):
     """The vector kernel (4 z voxels per thread, used when rows are 16-byte aligned) and the scalar
     kernel must both be bit-exact."""
-    vb._lib.lib.values_debug_set_stitch_path(request.param)
-    yield request.param
-    vb._lib.lib.values_debug_set_stitch_path(0)
+    return request.param
 
 
 def test_stitch_golden(vb, vo, stitch_path):
@@ -441,7 +438,7 @@ def test_stitch_golden(vb, vo, stitch_path):
     patches = torch.from_numpy(g["patches"])
     n_pred = patches.shape[0]
     # (a) drop-in DataCarrier3D.concat_data, batched like the reference's loop
-    carrier = vb.DataCarrier3D()
+    carrier = vb.DataCarrier3D(stitch_path=stitch_path)
     for pred_idx in range(n_pred):
         for s in range(0, len(crops), 5):
             idx = list(range(s, min(s + 5, len(crops))))
@@ -463,7 +460,7 @@ def test_stitch_golden(vb, vo, stitch_path):
     ref_layout = carrier.numpy_data()["vol_a.npy"]
     assert ref_layout["softmax_pred"].dtype == np.float64 and ref_layout["num_predictions"].shape == (2,) + shape
     # (b) all patches at once, written exactly once
-    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape)
+    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape, path=stitch_path)
     np.testing.assert_array_equal(total.cpu().numpy(), g["softmax_sum"])
     np.testing.assert_array_equal(cnt.cpu().numpy(), g["num_predictions"][0])
 
@@ -486,11 +483,11 @@ def test_stitch_vs_oracle(vb, vo, shape, p, overlap, dtype, stitch_path):
     for pi in range(n_pred):
         st.concat_data({"image_paths": ["v"] * len(crops), "org_image_size": [shape] * len(crops),
                         "crop_idx": crops}, patches[pi].double(), n_pred=n_pred, pred_idx=pi)
-    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape)
+    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape, path=stitch_path)
     np.testing.assert_array_equal(total.cpu().numpy(), st.data["v"]["softmax_pred"])
     np.testing.assert_array_equal(cnt.cpu().numpy(), st.data["v"]["num_predictions"][0])
     if dtype == torch.float32:
-        t32, _ = vb.stitch_volume(patches.cuda(), crops, shape, out_dtype=torch.float32)
+        t32, _ = vb.stitch_volume(patches.cuda(), crops, shape, out_dtype=torch.float32, path=stitch_path)
         np.testing.assert_allclose(t32.cpu().numpy(), st.data["v"]["softmax_pred"], rtol=1e-6)
 
 
@@ -502,7 +499,7 @@ def test_stitch_many_patches_chunked_list(vb, vo, stitch_path):
     st = vo.StitchOracle(n_classes=1)
     st.concat_data({"image_paths": ["v"] * len(crops), "org_image_size": [shape] * len(crops),
                     "crop_idx": crops}, patches[0], pred_idx=0)
-    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape)
+    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape, path=stitch_path)
     np.testing.assert_allclose(total.cpu().numpy(), st.data["v"]["softmax_pred"], rtol=1e-14)
     np.testing.assert_array_equal(cnt.cpu().numpy(), st.data["v"]["num_predictions"][0])
 
@@ -516,16 +513,16 @@ def test_stitch_gaussian_weighted(vb, vo, stitch_path):
     patches = torch.rand(2, len(crops), 2, p, p, p, generator=g, dtype=torch.float32)
     w = vb.gaussian_importance_map((p, p, p))
     np.testing.assert_array_equal(w.numpy(), vo.gaussian_importance_map((p, p, p)))
-    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape, weight=w.cuda())
+    total, cnt = vb.stitch_volume(patches.cuda(), crops, shape, weight=w.cuda(), path=stitch_path)
     ref_total, ref_cnt = vo.stitch_weighted(patches.numpy(), crops, shape, w.numpy())
     np.testing.assert_array_equal(total.cpu().numpy(), ref_total)
     np.testing.assert_array_equal(cnt.cpu().numpy(), ref_cnt)
     # uniform weight of ones == the reference's unweighted accumulator, bit for bit
-    t1, c1 = vb.stitch_volume(patches.cuda(), crops, shape, weight=torch.ones(p, p, p, dtype=torch.float64).cuda())
-    t0, c0 = vb.stitch_volume(patches.cuda(), crops, shape)
+    t1, c1 = vb.stitch_volume(patches.cuda(), crops, shape, weight=torch.ones(p, p, p, dtype=torch.float64).cuda(), path=stitch_path)
+    t0, c0 = vb.stitch_volume(patches.cuda(), crops, shape, path=stitch_path)
     assert torch.equal(t1, t0) and torch.equal(c1, c0)
     # carrier with a weight: normalised softmax = weighted mean, uncovered remainder stays 0
-    carrier = vb.DataCarrier3D(patch_weight=w)
+    carrier = vb.DataCarrier3D(patch_weight=w, stitch_path=stitch_path)
     for pred_idx in range(2):
         batch = {"image_paths": ["v"] * len(crops), "label_paths": [None] * len(crops),
                  "org_image_size": [shape] * len(crops), "crop_idx": crops, "data": None, "seg": None}

@@ -22,6 +22,8 @@ SHAPES = {
     "cfg2": (5, 2, (64, 64, 64), torch.float32, 512),
     "cfg3": (16, 2, (256, 256, 256), torch.float64, 2),
     "cfg5f64": (16, 4, (128, 128, 128), torch.float64, 8),
+    "cfg1": (5, 2, (64, 64, 64), torch.float64, 160),
+    "cfg3n8": (8, 2, (256, 256, 256), torch.float64, 2),
 }
 
 
@@ -46,21 +48,19 @@ def main():
     batch = args.batch or pool
     out = torch.empty((3, batch) + spatial, dtype=torch.float32, device=dev)
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
-    _lib.lib.values_debug_set_k1_variant(0)
     ref = vb.uncertainty_fused(x[:batch], mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05))
     ref = (ref.pred_entropy.clone(), ref.expected_entropy.clone(), ref.mutual_information.clone(),
            ref.mean_argmax.clone(), ref.scores.clone())
     for variant in [int(v) for v in args.variants.split(",")]:
         for it in [int(v) for v in args.iters.split(",")]:
-            _lib.lib.values_debug_set_k1_variant(variant)
-            _lib.lib.values_debug_set_k1_iter(it)
 
             def run():
                 for b0 in range(0, pool - batch + 1, batch):
                     vb.uncertainty_fused(x[b0:b0 + batch], mean_argmax=True, scores=bool(args.scores),
-                                         thresholds=(0.5, 0.4, 0.05), out_maps=out)
+                                         thresholds=(0.5, 0.4, 0.05), out_maps=out, variant=variant, tiles_per_cta=it)
 
-            chk = vb.uncertainty_fused(x[:batch], mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05))
+            chk = vb.uncertainty_fused(x[:batch], mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05),
+                                       variant=variant, tiles_per_cta=it)
             same = all(torch.equal(a, b) for a, b in zip(ref, (chk.pred_entropy, chk.expected_entropy,
                                                                chk.mutual_information, chk.mean_argmax, chk.scores)))
             run()
@@ -78,8 +78,6 @@ def main():
             print(f"{args.shape} variant={variant} iter={it} batch={batch}: {best / nvol * 1e3:8.1f} us/vol "
                   f"{nvol * V / best / 1e6:8.2f} Gvox/s {gbs:8.1f} GB/s = {gbs / peak:.3f} of measured peak  "
                   f"bit-identical to variant 0: {same}", flush=True)
-    _lib.lib.values_debug_set_k1_variant(0)
-    _lib.lib.values_debug_set_k1_iter(0)
 
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libvalues_b200.so")
 
 F32, F64, BF16, U8, I32, I64 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 5  # include/values_b200.h VALUES_ABI_VERSION
+ABI_VERSION = 6  # include/values_b200.h VALUES_ABI_VERSION
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 _LABEL_DTYPES = {torch.uint8: U8, torch.int32: I32, torch.int64: I64}
 
@@ -40,17 +40,17 @@ def _load() -> C.CDLL:
         "values_launch_count": (i64, []),
         "values_uncertainty_workspace_bytes": (sz, [i64, i64, C.c_int]),
         "values_uncertainty_fused": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, i64, i64, i64,
-                                               vp, vp, vp, i64, vp, vp, vp, pdbl, vp, sz, vp]),
+                                               vp, vp, vp, i64, vp, vp, vp, i64, pdbl, vp, sz, C.c_int, C.c_int, vp]),
         "values_one_minus_msr": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, i64, vp, vp]),
         "values_map_reduce_workspace_bytes": (sz, [i64, i64]),
         "values_map_reduce": (C.c_int, [vp, C.c_int, i64, i64, i64, pdbl, C.c_int, vp, vp, sz, vp]),
         "values_patch_max_workspace_bytes": (sz, [i64, pi64, pi64, C.c_int]),
         "values_patch_max": (C.c_int, [vp, C.c_int, i64, i64, pi64, pi64, C.c_int, dbl, dbl,
-                                       vp, vp, vp, sz, C.c_int, vp]),
+                                       vp, i64, vp, C.c_int, i64, vp, sz, C.c_int, vp]),
         "values_stitch_accumulate": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, i64, i64, i64,
-                                               pi64, pi64, vp, C.c_int, vp, C.c_int, vp]),
+                                               pi64, pi64, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
         "values_stitch_accumulate_weighted": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, vp, i64, i64, i64,
-                                                        pi64, pi64, vp, C.c_int, vp, C.c_int, vp]),
+                                                        pi64, pi64, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
         "values_normalize_maps": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, dbl, vp, vp]),
         "values_count_nonzero": (C.c_int, [vp, C.c_int, i64, vp, vp]),
         "values_radix_histogram": (C.c_int, [vp, C.c_int, i64, C.c_uint64, C.c_int, C.c_int, vp, vp]),
@@ -64,9 +64,6 @@ def _load() -> C.CDLL:
         "values_confusion_counts": (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, i64, C.c_int, vp, vp]),
         "values_reverse_axes": (C.c_int, [vp, vp, C.c_int, i64, i64, i64, vp]),
         "values_patch_filter_err_coef": (dbl, [C.c_int, C.c_int]),
-        "values_debug_set_k1_iter": (None, [C.c_int]),
-        "values_debug_set_k1_variant": (None, [C.c_int]),
-        "values_debug_set_stitch_path": (None, [C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
@@ -87,8 +84,6 @@ EXPORTED = [
     "values_min_key_above", "values_pair_moments_workspace_bytes", "values_pair_moments",
     "values_calib_bins_workspace_bytes", "values_calib_bins", "values_calib_bins_fused",
     "values_confusion_counts", "values_reverse_axes", "values_patch_filter_err_coef",
-    "values_debug_set_k1_iter", "values_debug_set_k1_variant",
-    "values_debug_set_stitch_path",
 ]
 
 

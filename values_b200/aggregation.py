@@ -60,8 +60,9 @@ def patch_max(maps: torch.Tensor, patch_size, mean: bool = False,
               rtol: float = ISCLOSE_RTOL, atol: float = ISCLOSE_ATOL,
               out_score: Optional[torch.Tensor] = None, out_bbox: Optional[torch.Tensor] = None,
               workspace: Optional[torch.Tensor] = None, path: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """maps [M, *S] (CUDA fp32/fp64, 1 <= len(S) <= 3) -> (max_score fp64 [M], bbox_lo int64 [M, len(S)]).
-    out_score fp64 [M] / out_bbox int64 [M, 3] / workspace (uint8) may be preallocated.
+    """maps [M, *S] (CUDA fp32/fp64, 1 <= len(S) <= 3) -> (max_score fp64 [M], bbox_lo [M, len(S)]).
+    out_score fp64 [M] (any stride) / out_bbox [M, 3] int64 or fp64 (rows evenly strided, e.g. columns
+    of an fp64 score table) / workspace (uint8) may be preallocated and are written in place.
     path: implementation for this call (include/values_b200.h: 0 automatic, 5 exact march without the
     fp32 filter, 4 fused tile kernel, 2 generic tiled path); all give identical results."""
     if maps.device.type != "cuda":
@@ -80,9 +81,10 @@ def patch_max(maps: torch.Tensor, patch_size, mean: bool = False,
     dev = maps.device
     score = out_score if out_score is not None else torch.empty(M, dtype=torch.float64, device=dev)
     bbox = out_bbox if out_bbox is not None else torch.empty((M, 3), dtype=torch.int64, device=dev)
-    if (tuple(score.shape) != (M,) or score.dtype != torch.float64 or not score.is_contiguous()
-            or tuple(bbox.shape) != (M, 3) or bbox.dtype != torch.int64 or not bbox.is_contiguous()):
-        raise ValueError("out_score must be contiguous fp64 [M] and out_bbox contiguous int64 [M, 3]")
+    if (tuple(score.shape) != (M,) or score.dtype != torch.float64 or (M > 1 and score.stride(0) < 1)
+            or tuple(bbox.shape) != (M, 3) or bbox.dtype not in (torch.int64, torch.float64)
+            or bbox.stride(1) != 1 or (M > 1 and bbox.stride(0) < 3)):
+        raise ValueError("out_score must be fp64 [M] and out_bbox int64 / fp64 [M, 3] with contiguous rows")
     sh, pa = _lib.i64x3(shape3), _lib.i64x3(patch3)
     ws_bytes = _lib.lib.values_patch_max_workspace_bytes(M, sh, pa, int(path))
     if workspace is not None and workspace.numel() * workspace.element_size() >= ws_bytes:
@@ -93,7 +95,10 @@ def patch_max(maps: torch.Tensor, patch_size, mean: bool = False,
     with torch.cuda.device(dev):
         rc = _lib.lib.values_patch_max(maps.data_ptr(), _lib.dtype_code(maps.dtype), M, V, sh, pa,
                                        int(bool(mean)), float(rtol), float(atol), score.data_ptr(),
-                                       bbox.data_ptr(), ws.data_ptr(), ws_bytes, int(path), _lib.stream_ptr(dev))
+                                       score.stride(0) if M > 1 else 1, bbox.data_ptr(),
+                                       _lib.I64 if bbox.dtype == torch.int64 else _lib.F64,
+                                       bbox.stride(0) if M > 1 else 3, ws.data_ptr(), ws_bytes, int(path),
+                                       _lib.stream_ptr(dev))
     _lib.check(rc)
     return score, bbox[:, 3 - nd:]
 

@@ -17,6 +17,33 @@ namespace vb {
 // kernel when the patch fits its shared memory; else the generic tiled path), 5 = march kernel
 // without the filter, 4 = fused tile kernel even where the march applies, 2 = generic tiled path.
 
+// Where K2b puts a map's result: max_score[m * score_stride]; the box corner (z, y, x) at
+// bbox[m * bbox_stride + 0..2] as int64 or -- for the fp64 score table [B, 3, 7] the pipeline hands
+// to its callers -- as doubles.  (-1, -1, -1) = no window is close to the maximum (NaN map: the
+// reference raises IndexError).
+struct PatchOut {
+    double* max_score; int64_t score_stride;
+    int64_t* bbox_i64; double* bbox_f64; int64_t bbox_stride;
+    __device__ __forceinline__ void put_score(int64_t m, double g) const { max_score[m * score_stride] = g; }
+    __device__ __forceinline__ void put_corner(int64_t m, unsigned long long best, int64_t O1, int64_t O2) const {
+        int64_t c[3] = {-1, -1, -1};
+        if (best != ~0ull) {
+            const int64_t lin = (int64_t)best;
+            c[2] = lin % O2; c[1] = (lin / O2) % O1; c[0] = lin / (O2 * O1);
+        }
+        for (int d = 0; d < 3; ++d) {
+            if (bbox_f64) bbox_f64[m * bbox_stride + d] = (double)c[d];
+            else bbox_i64[m * bbox_stride + d] = c[d];
+        }
+    }
+    PatchOut offset(int64_t m0) const {
+        PatchOut o = *this;
+        o.max_score += m0 * score_stride;
+        if (o.bbox_f64) o.bbox_f64 += m0 * bbox_stride; else o.bbox_i64 += m0 * bbox_stride;
+        return o;
+    }
+};
+
 // =============================================================================== K2a
 struct ThrTable { double v[16]; int n; };
 
@@ -213,7 +240,7 @@ __global__ void __launch_bounds__(kThreads) patch_kernel(const PatchParams prm) 
 __global__ void __launch_bounds__(kThreads) patch_select_kernel(const double* __restrict__ tile_max,
                                                                 int64_t ntiles,
                                                                 double* __restrict__ gmax,
-                                                                double* __restrict__ max_score,
+                                                                PatchOut out,
                                                                 unsigned long long* __restrict__ best) {
     __shared__ double red[8];
     const int64_t m = blockIdx.x;
@@ -227,24 +254,16 @@ __global__ void __launch_bounds__(kThreads) patch_select_kernel(const double* __
         double g = red[0];
         for (int w = 1; w < kThreads / 32; ++w) g = nanmax(g, red[w]);
         gmax[m] = g;
-        max_score[m] = g;
+        out.put_score(m, g);
         best[m] = ~0ull;
     }
 }
 
 __global__ void patch_finish_kernel(const unsigned long long* __restrict__ best, int64_t M,
-                                    int64_t O1, int64_t O2, int64_t* __restrict__ bbox_lo) {
+                                    int64_t O1, int64_t O2, PatchOut out) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
-    const unsigned long long b = best[m];
-    if (b == ~0ull) {  // no window is close to the max (NaN map): the reference raises IndexError
-        bbox_lo[3 * m] = bbox_lo[3 * m + 1] = bbox_lo[3 * m + 2] = -1;
-        return;
-    }
-    const int64_t lin = (int64_t)b;
-    bbox_lo[3 * m + 2] = lin % O2;
-    bbox_lo[3 * m + 1] = (lin / O2) % O1;
-    bbox_lo[3 * m] = lin / (O2 * O1);
+    out.put_corner(m, best[m], O1, O2);
 }
 
 // ------------------------------------------------------------------ K2b fused tile kernel
@@ -289,8 +308,7 @@ struct FusedParams {
     unsigned int* tickets;        // [M, 4]  filter / pass-1 / pass-2 arrival counters, max |input| bits
     int use_list;                 // pass 1 walks only the (tile, z sub-chunk) entries the fp32 filter listed
     double err_coef;              // fp32 filter: |fp32 box sum - true box sum| <= err_coef * max |input|
-    double* max_score;            // [M]
-    int64_t* bbox_lo;             // [M, 3]
+    PatchOut out;                 // max_score / box corner of every map
 };
 
 __device__ __noinline__ double box_mean_div(double s, double denom) { return s / denom; }  // mean=True only
@@ -399,7 +417,7 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
         if (tid == 0) {
             lst[0] = s_count > kMaxActive ? -1 : s_count;
             prm.gmax[m] = g;
-            prm.max_score[m] = g;
+            prm.out.put_score(m, g);
             prm.best[m] = ~0ull;
         }
     } else {
@@ -419,15 +437,7 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
         if (s_flag && tid == 0) {
             __threadfence();
             const unsigned long long b = atomicMin(prm.best + m, ~0ull);  // atomic read
-            int64_t* bb = prm.bbox_lo + 3 * m;
-            if (b == ~0ull) {  // no window is close to the max (NaN map): the reference raises IndexError
-                bb[0] = bb[1] = bb[2] = -1;
-            } else {
-                const int64_t lin = (int64_t)b;
-                bb[2] = lin % prm.O2;
-                bb[1] = (lin / prm.O2) % prm.O1;
-                bb[0] = lin / (prm.O2 * prm.O1);
-            }
+            prm.out.put_corner(m, b, prm.O1, prm.O2);
         }
     }
 }
@@ -1161,7 +1171,7 @@ static int make_patch_plan(const int64_t* shape, const int64_t* patch, PatchPlan
 
 template <typename T>
 static int run_patch(PatchParams prm, const PatchPlan& pl, int64_t M, double* gmax,
-                     double* max_score, int64_t* bbox_lo, cudaStream_t st) {
+                     const PatchOut& out, cudaStream_t st) {
     auto k1 = patch_kernel<T, 1>;
     auto k2 = patch_kernel<T, 2>;
     if (pl.smem > 48 * 1024) {
@@ -1181,12 +1191,12 @@ static int run_patch(PatchParams prm, const PatchPlan& pl, int64_t M, double* gm
         int rc = check_launch("patch_kernel<1>");
         if (rc) return rc;
         patch_select_kernel<<<(unsigned)mc, kThreads, 0, st>>>(q.tile_max, pl.ntiles, gmax + m0,
-                                                                max_score + m0, q.best);
+                                                                out.offset(m0), q.best);
         if ((rc = check_launch("patch_select_kernel"))) return rc;
         k2<<<grid, kThreads, pl.smem, st>>>(q);
         if ((rc = check_launch("patch_kernel<2>"))) return rc;
     }
-    patch_finish_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(prm.best, M, pl.O1, pl.O2, bbox_lo);
+    patch_finish_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(prm.best, M, pl.O1, pl.O2, out);
     return check_launch("patch_finish_kernel");
 }
 
@@ -1314,7 +1324,7 @@ static int run_patch_fused_pc(FusedParams prm, const FusedPlan& pl, int64_t M, c
         q.maps = reinterpret_cast<const T*>(prm.maps) + m0 * prm.stride_m;
         q.tile_max = prm.tile_max + m0 * prm.nent;
         q.best = prm.best + m0;
-        q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
+        q.out = prm.out.offset(m0);
         q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
         q.tickets = prm.tickets + 4 * m0;
         if (cudaMemsetAsync(q.tickets, 0, (size_t)mc * 4 * sizeof(unsigned int), st) != cudaSuccess)
@@ -1429,7 +1439,7 @@ static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
         q.maps = reinterpret_cast<const T*>(prm.maps) + m0 * prm.stride_m;
         q.tile_max = prm.tile_max + m0 * prm.nent;
         q.best = prm.best + m0;
-        q.max_score = prm.max_score + m0; q.bbox_lo = prm.bbox_lo + 3 * m0;
+        q.out = prm.out.offset(m0);
         q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
         q.tickets = prm.tickets + 4 * m0;
         // the work list normally holds one or two (tile, z sub-chunk) entries per map
@@ -1555,13 +1565,21 @@ extern "C" size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* sha
 extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t stride_m,
                                 const int64_t* shape3_host, const int64_t* patch3_host,
                                 int mean_flag, double rtol, double atol, double* max_score,
-                                int64_t* bbox_lo, void* workspace, size_t workspace_bytes,
-                                int path, void* stream) {
+                                int64_t score_stride, void* bbox_lo, int bbox_dtype, int64_t bbox_stride,
+                                void* workspace, size_t workspace_bytes, int path, void* stream) {
     if (!shape3_host || !patch3_host) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: NULL shape");
     if (M < 0) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: M < 0");
     if (dtype != VALUES_F32 && dtype != VALUES_F64)
         return set_error(VALUES_ERR_INVALID_ARG, "patch_max: dtype must be f32 or f64");
     if (!patch_path_ok(path)) return set_error(VALUES_ERR_INVALID_ARG, "patch_max: unknown path %d (0, 2, 4, 5)", path);
+    if (bbox_dtype != VALUES_I64 && bbox_dtype != VALUES_F64)
+        return set_error(VALUES_ERR_INVALID_ARG, "patch_max: bbox_dtype must be i64 or f64");
+    if (score_stride < 1 || bbox_stride < 3)
+        return set_error(VALUES_ERR_INVALID_ARG, "patch_max: score_stride >= 1 and bbox_stride >= 3");
+    PatchOut out{};
+    out.max_score = max_score; out.score_stride = score_stride; out.bbox_stride = bbox_stride;
+    if (bbox_dtype == VALUES_F64) out.bbox_f64 = reinterpret_cast<double*>(bbox_lo);
+    else out.bbox_i64 = reinterpret_cast<int64_t*>(bbox_lo);
     cudaStream_t st = (cudaStream_t)stream;
     double* ws = reinterpret_cast<double*>(workspace);
     const double denom =
@@ -1593,7 +1611,7 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
             prm.best = reinterpret_cast<unsigned long long*>(ws + M * prm.nent + M);
             prm.tickets = reinterpret_cast<unsigned int*>(ws + M * prm.nent + 2 * M);
             prm.active = reinterpret_cast<int*>(ws + M * prm.nent + 4 * M);
-            prm.max_score = max_score; prm.bbox_lo = bbox_lo;
+            prm.out = out;
             if (fp.march) {
                 if (dtype == VALUES_F32) return run_patch_march<float>(prm, fp, M, st);
                 return run_patch_march<double>(prm, fp, M, st);
@@ -1627,8 +1645,8 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
     prm.tile_max = ws;
     double* gmax = ws + M * pl.ntiles;
     prm.best = reinterpret_cast<unsigned long long*>(gmax + M);
-    if (dtype == VALUES_F32) return run_patch<float>(prm, pl, M, gmax, max_score, bbox_lo, st);
-    return run_patch<double>(prm, pl, M, gmax, max_score, bbox_lo, st);
+    if (dtype == VALUES_F32) return run_patch<float>(prm, pl, M, gmax, out, st);
+    return run_patch<double>(prm, pl, M, gmax, out, st);
 }
 
 extern "C" double values_patch_filter_err_coef(int zc, int p0) {

@@ -13,7 +13,6 @@ namespace vb {
 constexpr int kSZ = 64;  // tile extent along the contiguous axis (z)
 constexpr int kSY = 4;   // tile extent along axis 1 (y); kSZ*kSY == kThreads
 constexpr int kMaxList = 1024;  // overlapping patches kept per tile chunk
-static int g_stitch_path = 0;    // 0 = automatic, 1 = scalar kernel only (values_debug_set_stitch_path)
 
 struct StitchParams {
     const void* patches;
@@ -366,9 +365,10 @@ extern "C" int values_stitch_accumulate_weighted(const void* patches, int patch_
                                                  int64_t C, const int64_t* patch3_host,
                                                  const int64_t* vol3_host, void* out_sum,
                                                  int out_dtype, double* out_count, int accumulate,
-                                                 void* stream) {
+                                                 int path, void* stream) {
     if (!patches || !crop_lo || !patch3_host || !vol3_host || !out_sum)
         return set_error(VALUES_ERR_INVALID_ARG, "stitch: NULL pointer");
+    if (path != 0 && path != 1) return set_error(VALUES_ERR_INVALID_ARG, "stitch: unknown path %d (0, 1)", path);
     if (n_sel < 0 || N <= 0 || C <= 0)
         return set_error(VALUES_ERR_INVALID_ARG, "stitch: bad sizes");
     for (int d = 0; d < 3; ++d)
@@ -395,7 +395,7 @@ extern "C" int values_stitch_accumulate_weighted(const void* patches, int patch_
     // vector kernel: 4 consecutive z voxels per thread (16-byte loads / stores)
     const size_t pes = patch_dtype == VALUES_F64 ? 8 : (patch_dtype == VALUES_F32 ? 4 : 2);
     const size_t oes = out_dtype == VALUES_F64 ? 8 : 4;
-    const bool vec_ok = g_stitch_path != 1 && prm.Z % 4 == 0 && prm.p2 % 4 == 0 &&
+    const bool vec_ok = path != 1 && prm.Z % 4 == 0 && prm.p2 % 4 == 0 &&
                         (reinterpret_cast<uintptr_t>(patches) % (4 * pes)) == 0 &&
                         (patch_stride_n % 4) == 0 && (patch_stride_p % 4) == 0 &&
                         (reinterpret_cast<uintptr_t>(out_sum) % (4 * oes)) == 0 &&
@@ -403,7 +403,7 @@ extern "C" int values_stitch_accumulate_weighted(const void* patches, int patch_
                         (!weight || reinterpret_cast<uintptr_t>(weight) % 32 == 0);
     if (vec_ok) {
         // tile extent along z: short tiles keep the overlap list short (every thread walks all of it)
-        const int tzv = g_stitch_path == 32 ? 32 : (g_stitch_path == 64 ? 64 : 16);
+        constexpr int tzv = 16;
         prm.tiles_z = (int)ceil_div(prm.Z, tzv * 4);
         prm.tiles_y = (int)ceil_div(prm.Y, kThreads / tzv);
         const int64_t vtiles = (int64_t)prm.tiles_z * prm.tiles_y * ceil_div(prm.X, kXB);
@@ -411,8 +411,7 @@ extern "C" int values_stitch_accumulate_weighted(const void* patches, int patch_
         const dim3 vgrid((unsigned)vtiles, (unsigned)N);
 #define VB_STITCHV2(TP, TO, TZV) do { if (weight) stitch_vec_kernel<TP, TO, TZV, true><<<vgrid, kThreads, 0, st>>>(prm); \
         else stitch_vec_kernel<TP, TO, TZV, false><<<vgrid, kThreads, 0, st>>>(prm); } while (0)
-#define VB_STITCHV3(TP, TO) do { if (tzv == 16) VB_STITCHV2(TP, TO, 16); \
-        else if (tzv == 32) VB_STITCHV2(TP, TO, 32); else VB_STITCHV2(TP, TO, 64); } while (0)
+#define VB_STITCHV3(TP, TO) VB_STITCHV2(TP, TO, tzv)
         if (out_dtype == VALUES_F64) {
             if (patch_dtype == VALUES_F64) VB_STITCHV3(double, double);
             else if (patch_dtype == VALUES_F32) VB_STITCHV3(float, double);
@@ -457,11 +456,10 @@ extern "C" int values_stitch_accumulate(const void* patches, int patch_dtype,
                                         int64_t n_sel, int64_t N, int64_t C,
                                         const int64_t* patch3_host, const int64_t* vol3_host,
                                         void* out_sum, int out_dtype, double* out_count,
-                                        int accumulate, void* stream) {
+                                        int accumulate, int path, void* stream) {
     return values_stitch_accumulate_weighted(patches, patch_dtype, patch_stride_n, patch_stride_p,
                                              patch_index, crop_lo, nullptr, n_sel, N, C, patch3_host,
                                              vol3_host, out_sum, out_dtype, out_count, accumulate,
-                                             stream);
+                                             path, stream);
 }
 
-extern "C" void values_debug_set_stitch_path(int path) { vb::g_stitch_path = path; }

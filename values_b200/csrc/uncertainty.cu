@@ -13,8 +13,12 @@
 
 namespace vb {
 
-static int g_k1_iter_override = 0;
-static int g_k1_variant = 0;
+// Kernel choice per call (values_uncertainty_fused `variant`; 0 = automatic, the others exist so that
+// tests can run two implementations of the same arithmetic against each other -- every variant gives
+// bit-identical outputs): 1 = register-stream kernel instead of the bulk-copy ring, 2 = ring with
+// 4-row stages where 8-row stages are the default, 3 = 8-row stages x 3 at two CTAs per SM,
+// 4 = (fp64 stacks) sample-outer kernel instead of the class-outer ring.
+enum { K1_AUTO = 0, K1_STREAM = 1, K1_RING4 = 2, K1_RING8X3 = 3, K1_SAMPLE_OUTER = 4, K1_VARIANTS = 5 };
 
 struct K1Params {
     const void* probs;
@@ -26,7 +30,9 @@ struct K1Params {
     uint8_t* amax;
     uint8_t* samax;
     double* partials;  // [B, blocks_per_vol, 9] or nullptr
-    double* scores;    // [B, 9]: written by the last CTA of each volume
+    double* scores;    // row (b, map) at scores[(3 b + map) * score_stride + 0..2]: written by the last CTA of each volume
+    int64_t score_stride;
+    int variant, tiles_per_cta;   // per-call kernel choice (K1_*), tiles per CTA (0 = automatic)
     unsigned int* counters;  // [B] arrival tickets (zeroed before the launch)
     float thr_f[3];    // thresholds rounded to fp32: numpy compares an fp32 map in fp32
     int has_thr;
@@ -299,7 +305,7 @@ __device__ __forceinline__ void k1_write_partials(const K1Params& prm, double (&
     block_sum<9, BAR>(acc, red);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) prm.scores[b * 9 + k] = acc[k];
+        for (int k = 0; k < 9; ++k) prm.scores[(3 * b + k / 3) * prm.score_stride + k % 3] = acc[k];
     }
 }
 
@@ -715,7 +721,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k1_stream_kernel(const K1Param
 // fp32 entropy accumulator H[n], so each H_n still adds its classes in index order and EE is their
 // sequential fp32 sum -- the reference's order (test_3D.py:499-507) -- while the rows stream
 // class-outer through the ring like the fp32 path.  Bit-identical to the sample-outer k1_smem_kernel.
-template <typename T, int VEC, int MINB, int RS, int kTmaStages, bool EARLY, int NS = 0>
+template <typename T, int VEC, int MINB, int RS, int kTmaStages, int NS = 0>
 __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Params prm) {
     using A = typename In<T>::acc_t;
     using M = Math<T>;
@@ -818,10 +824,6 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                         const uint4 q = lds128(ring_tid + stage * kStageBytes + (h + u) * kRowBytes);
                         raw[u].w[0] = q.x; raw[u].w[1] = q.y; raw[u].w[2] = q.z; raw[u].w[3] = q.w;
                     }
-                    if (EARLY && h + SB == RS) {   // hand the slot back as soon as the warp has read it
-                        __syncwarp();
-                        if (is_lane0) mbar_arrive_addr(empty0 + stage * 8);
-                    }
                     if (active) {
 #pragma unroll
                         for (int u = 0; u < SB; ++u) {
@@ -838,15 +840,13 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                         }
                     }
                 }
-                if (!EARLY) {
-                    // The slot may only be handed back once the LDS above have RETURNED (an arrive
-                    // issued right after them races with the next bulk copy -- measured).  The
-                    // empty asm pins the arrive behind arithmetic that consumed every row of the
-                    // stage, and that arithmetic cannot issue before the loads complete.
-                    asm volatile("" ::"f"(NS > 0 ? H[n + RS - 1][0] : e[0]), "r"(bad) : "memory");
-                    __syncwarp();
-                    if (is_lane0) mbar_arrive_addr(empty0 + stage * 8);
-                }
+                // The slot may only be handed back once the LDS above have RETURNED (an arrive
+                // issued right after them races with the next bulk copy -- measured).  The
+                // empty asm pins the arrive behind arithmetic that consumed every row of the
+                // stage, and that arithmetic cannot issue before the loads complete.
+                asm volatile("" ::"f"(NS > 0 ? H[n + RS - 1][0] : e[0]), "r"(bad) : "memory");
+                __syncwarp();
+                if (is_lane0) mbar_arrive_addr(empty0 + stage * 8);
                 if (++stage == kTmaStages) { stage = 0; phase ^= 1u; }
             };
             if constexpr (NS > 0) {
@@ -1034,7 +1034,7 @@ static int choose_iter(int64_t total_tiles, int minb, int64_t rows) {
 template <typename T, int VEC, int U, int MINB, bool FULL>
 static int launch_stream(K1Params& prm, int64_t B, cudaStream_t st) {
     const int64_t tiles = ceil_div(ceil_div(prm.V, VEC), kThreads);
-    prm.iter = g_k1_iter_override > 0 ? g_k1_iter_override : choose_iter(tiles * B, MINB, prm.N * prm.C);
+    prm.iter = prm.tiles_per_cta > 0 ? prm.tiles_per_cta : choose_iter(tiles * B, MINB, prm.N * prm.C);
     prm.blocks_per_vol = ceil_div(tiles, prm.iter);
     const int64_t grid = prm.blocks_per_vol * B;
     if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
@@ -1042,14 +1042,14 @@ static int launch_stream(K1Params& prm, int64_t B, cudaStream_t st) {
     return check_launch("k1_stream_kernel");
 }
 
-template <typename T, int VEC, int MINB, int RS, int STAGES, bool EARLY = false, int NS = 0>
+template <typename T, int VEC, int MINB, int RS, int STAGES, int NS = 0>
 static int launch_tma(K1Params& prm, int64_t B, cudaStream_t st) {
     const int64_t tiles = ceil_div(ceil_div(prm.V, VEC), kThreads);
-    prm.iter = g_k1_iter_override > 0 ? g_k1_iter_override : choose_iter(tiles * B, MINB, prm.N * prm.C);
+    prm.iter = prm.tiles_per_cta > 0 ? prm.tiles_per_cta : choose_iter(tiles * B, MINB, prm.N * prm.C);
     prm.blocks_per_vol = ceil_div(tiles, prm.iter);
     const int64_t grid = prm.blocks_per_vol * B;
     if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
-    auto kern = k1_tma_kernel<T, VEC, MINB, RS, STAGES, EARLY, NS>;
+    auto kern = k1_tma_kernel<T, VEC, MINB, RS, STAGES, NS>;
     const size_t smem = (size_t)STAGES * RS * kThreads * 16;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return set_error(VALUES_ERR_CUDA, "cudaFuncSetAttribute(k1_tma_kernel) failed");
@@ -1069,48 +1069,34 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, cudaStream_t st) 
         // 8, 16; N = 5k: the reference's 5-member ensembles and N = 10)
         // Occupancy beats register comfort here (measured on B200, profiles/r01b_k1_variants.txt):
         // 3 CTAs/SM with a few cold-path spills reaches 0.84 of the HBM peak, 2 CTAs/SM 0.66.
-        const int v = g_k1_variant;
+        const int v = prm.variant;
         if constexpr (sizeof(T) != 8) {
             // default: bulk-copy ring, RS samples per stage (one mbarrier round trip per stage)
-            if (v == 0) {
+            if (v != K1_STREAM) {
                 // N = 8k (MC-dropout / TTA 8, 16): 8 rows per stage, consumed 4 at a time -- half the
                 // mbarrier round trips and loop overhead per element (K1 is issue-bound, not HBM-bound:
                 // 70 % issue slots); measured on cfg5 0.90 -> 0.94 of the HBM peak at 24 volumes per
                 // launch, equal at 8, outputs bit-identical
-                if (prm.N % 8 == 0) return launch_tma<T, NV, 3, 8, 2>(prm, B, st);
+                if (prm.N % 8 == 0 && v == K1_RING8X3) return launch_tma<T, NV, 2, 8, 3>(prm, B, st);
+                if (prm.N % 8 == 0 && v != K1_RING4) return launch_tma<T, NV, 3, 8, 2>(prm, B, st);
                 if (prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4>(prm, B, st);
                 if (prm.N % 5 == 0) return launch_tma<T, NV, 3, 5, 3>(prm, B, st);
                 if (prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8>(prm, B, st);
                 return launch_tma<T, NV, 3, 1, 8>(prm, B, st);
             }
-            if (v == 5) return launch_tma<T, NV, 3, 1, 8>(prm, B, st);
-            if (v == 13 && prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4>(prm, B, st);   // 4 rows per stage, 4 stages
-            if (v == 14 && prm.N % 8 == 0) return launch_tma<T, NV, 2, 8, 3>(prm, B, st);
-            if (v == 7 && prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4, true>(prm, B, st);  // racy on purpose (test)
-            if (v == 10 && prm.N % 5 == 0) return launch_tma<T, NV, 2, 5, 4>(prm, B, st);
-            if (v == 11 && prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8>(prm, B, st);
-            if (v == 12 && prm.N % 5 == 0) return launch_tma<T, NV, 3, 5, 3>(prm, B, st);
         }
-        if (prm.N % 4 == 0 && v != 9) {
-            if (v == 1) return launch_stream<T, NV, 4, 2, true>(prm, B, st);
-            if (v == 2) return launch_stream<T, NV, 2, 3, true>(prm, B, st);
-            if (v == 3) return launch_stream<T, NV, 4, 4, true>(prm, B, st);
-            if (v == 4) return launch_stream<T, NV, 2, 4, true>(prm, B, st);
-            return launch_stream<T, NV, 4, 3, true>(prm, B, st);
-        }
-        if (prm.N % 5 == 0 && v != 9) {
-            if (v == 1) return launch_stream<T, NV, 5, 2, true>(prm, B, st);
-            return launch_stream<T, NV, 5, 3, true>(prm, B, st);
-        }
-        if (v == 1) return launch_stream<T, NV, 4, 2, false>(prm, B, st);
+        if (prm.N % 4 == 0) return launch_stream<T, NV, 4, 3, true>(prm, B, st);
+        if (prm.N % 5 == 0) return launch_stream<T, NV, 5, 3, true>(prm, B, st);
         return launch_stream<T, NV, 4, 3, false>(prm, B, st);
     }
     if constexpr (sizeof(T) == 8) {
-        // fp64 stacks with the TTA / MC-dropout sample counts: class-outer ring kernel with one fp32
-        // accumulator per sample (variant 15 keeps the sample-outer kernel, for the bit-identity test)
-        if (prm.need_ent && !prm.samax && aligned && g_k1_variant != 15) {
-            if (prm.N == 16) return launch_tma<T, NV, 2, 4, 4, false, 16>(prm, B, st);
-            if (prm.N == 8) return launch_tma<T, NV, 2, 4, 4, false, 8>(prm, B, st);
+        // fp64 stacks with the sample counts of the reference's configs (5-member ensembles, N = 10
+        // MC dropout, TTA 8 / 16): class-outer ring kernel with one fp32 accumulator per sample
+        if (prm.need_ent && !prm.samax && aligned && prm.variant != K1_SAMPLE_OUTER) {
+            if (prm.N == 16) return launch_tma<T, NV, 2, 4, 4, 16>(prm, B, st);
+            if (prm.N == 8) return launch_tma<T, NV, 2, 4, 4, 8>(prm, B, st);
+            if (prm.N == 10) return launch_tma<T, NV, 2, 5, 3, 10>(prm, B, st);
+            if (prm.N == 5) return launch_tma<T, NV, 2, 5, 3, 5>(prm, B, st);
         }
     }
     // per-sample arg-max / arg-max only: sample-outer kernel with class sums in shared memory
@@ -1150,9 +1136,10 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
                                         int64_t C, int64_t V, int64_t stride_b, int64_t stride_n,
                                         int64_t stride_c, float* pe, float* ee, float* mi,
                                         int64_t map_stride_b, uint8_t* mean_argmax,
-                                        uint8_t* sample_argmax, double* scores,
+                                        uint8_t* sample_argmax, double* scores, int64_t score_stride,
                                         const double* thresholds_host, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+                                        size_t workspace_bytes, int variant, int tiles_per_cta,
+                                        void* stream) {
     if (B < 0 || N <= 0 || C <= 0 || V < 0)
         return set_error(VALUES_ERR_INVALID_ARG, "bad sizes B=%lld N=%lld C=%lld V=%lld",
                          (long long)B, (long long)N, (long long)C, (long long)V);
@@ -1162,10 +1149,13 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
         return set_error(VALUES_ERR_UNSUPPORTED, "uint8 arg-max needs C <= 256");
     if (stride_b < 0 || stride_n < 0 || stride_c < 0)
         return set_error(VALUES_ERR_INVALID_ARG, "negative strides");
+    if (variant < 0 || variant >= K1_VARIANTS || tiles_per_cta < 0 || tiles_per_cta > 64)
+        return set_error(VALUES_ERR_INVALID_ARG, "unknown variant %d / tiles_per_cta %d", variant, tiles_per_cta);
     if (B == 0 || V == 0) return VALUES_OK;
     cudaStream_t st = (cudaStream_t)stream;
     K1Params prm{};
     prm.probs = probs;
+    prm.variant = variant; prm.tiles_per_cta = tiles_per_cta;
     prm.N = N; prm.C = C; prm.V = V; prm.sb = stride_b; prm.sn = stride_n; prm.sc = stride_c;
     prm.pe = pe; prm.ee = ee; prm.mi = mi; prm.amax = mean_argmax; prm.samax = sample_argmax;
     prm.need_ent = (pe || ee || mi || scores) ? 1 : 0;
@@ -1181,7 +1171,8 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
             return set_error(VALUES_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
         prm.partials = reinterpret_cast<double*>(workspace);
         prm.counters = reinterpret_cast<unsigned int*>(prm.partials + B * k1_blocks_per_vol_upper(V) * 9);
-        prm.scores = scores;
+        if (score_stride < 3) return set_error(VALUES_ERR_INVALID_ARG, "score_stride < 3");
+        prm.scores = scores; prm.score_stride = score_stride;
         if (cudaMemsetAsync(prm.counters, 0, (size_t)B * sizeof(unsigned int), st) != cudaSuccess)
             return set_error(VALUES_ERR_CUDA, "cudaMemsetAsync(counters) failed");
     }
@@ -1202,8 +1193,6 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
 }
 
 // Test/benchmark hook: force the number of voxel tiles per CTA (0 = automatic).
-extern "C" void values_debug_set_k1_iter(int iter) { g_k1_iter_override = iter; }
-extern "C" void values_debug_set_k1_variant(int variant) { g_k1_variant = variant; }
 
 extern "C" int values_one_minus_msr(const void* probs, int dtype, int64_t B, int64_t C, int64_t V,
                                     int64_t stride_b, int64_t stride_c, void* out, void* stream) {

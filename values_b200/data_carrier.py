@@ -30,7 +30,7 @@ from .uncertainty import MAP_KEYS, uncertainty_fused
 
 class DataCarrier3D:
     def __init__(self, device: Optional[torch.device] = None, accum_dtype: torch.dtype = torch.float64,
-                 patch_weight: Optional[torch.Tensor] = None):
+                 patch_weight: Optional[torch.Tensor] = None, stitch_path: int = 0):
         self.data: Dict[str, Dict] = {}
         self.save_dir = None
         self.device = device
@@ -38,6 +38,7 @@ class DataCarrier3D:
         # opt-in importance map [p, p, p] (e.g. stitching.gaussian_importance_map): softmax sums
         # and `num_predictions` become weighted sums.  None = uniform, the reference's behaviour.
         self.patch_weight = patch_weight
+        self.stitch_path = stitch_path   # K3 implementation for this carrier's calls (tests; 0 = automatic)
 
     @staticmethod
     def load_image(sample: Dict) -> Dict:
@@ -105,10 +106,11 @@ class DataCarrier3D:
             pidx = torch.tensor(idxs, dtype=torch.int32, device=dev)
             stitch_accumulate(sp.unsqueeze(0), crop_lo, entry["softmax_pred"][pred_idx:pred_idx + 1],
                               entry["_count"] if pred_idx == 0 else None, patch_index=pidx, accumulate=True,
-                              weight=self.patch_weight)
+                              weight=self.patch_weight, path=self.stitch_path)
             if sg is not None:
                 stitch_accumulate(sg.unsqueeze(0), crop_lo, entry["sigma"][pred_idx:pred_idx + 1],
-                                  None, patch_index=pidx, accumulate=True, weight=self.patch_weight)
+                                  None, patch_index=pidx, accumulate=True, weight=self.patch_weight,
+                                  path=self.stitch_path)
             if pred_idx == 0:  # image / label slabs (:138-153): bookkeeping, plain torch slicing
                 for i in idxs:
                     (x0, x1), (y0, y1), (z0, z1) = batch["crop_idx"][i]

@@ -107,8 +107,8 @@ class PipelineResult:
 
 class UncertaintyPipeline:
     """K1 -> K2b over chunks of volumes with every buffer preallocated and reused: per chunk
-    the host issues two C-ABI calls (one K1 launch + a 4-byte memset, two K2b launches) and
-    nothing else; the score table is assembled once per run.  Never synchronises the host.
+    the host issues two C-ABI calls (one K1 launch + a 4-byte memset, three K2b launches) and
+    nothing else; both write their columns of the run's score table in place.  Never synchronises the host.
     With cfg.overlap the K2b launches and the assembly go to a side stream and run() returns with the
     main stream free for the next run's K1."""
 
@@ -164,20 +164,17 @@ class UncertaintyPipeline:
         else:
             maps_buf = self._buf("maps", (cb, 3) + spatial, torch.float32, dev)
             maps_buf2 = self._buf("maps2", (cb, 3) + spatial, torch.float32, dev) if overlap else maps_buf
-        if overlap:   # per-run outputs: the side stream may still be reading the previous run's
-            k1_scores = torch.empty((B, 3, 3), dtype=torch.float64, device=dev)
-        else:
-            k1_scores = self._buf("k1_scores", (B, 3, 3), torch.float64, dev)
+        # the score table of this run: K1 writes columns 0..2 of every row in place, K2b columns 3..6
+        # (max, corner as doubles) -- nothing is assembled afterwards.  Columns of unused leading axes
+        # (2-D images) and of a skipped patch level stay 0.
+        scores = torch.zeros((B, 3, N_COLS), dtype=torch.float64, device=dev)
+        k1_scores = scores[:, :, :3]
+        flat = scores.view(B * 3, N_COLS)
         am = torch.empty((B,) + spatial, dtype=torch.uint8, device=dev) if mean_argmax else None
         k1_ws_bytes = _lib.lib.values_uncertainty_workspace_bytes(cb, V, _lib.dtype_code(probs.dtype))
         k1_ws = self._buf("k1_ws", (max(k1_ws_bytes, 8),), torch.uint8, dev)
         if patch is not None:
-            if overlap:
-                ps = torch.empty((B * 3,), dtype=torch.float64, device=dev)
-                bb = torch.empty((B * 3, 3), dtype=torch.int64, device=dev)
-            else:
-                ps = self._buf("patch_score", (B * 3,), torch.float64, dev)
-                bb = self._buf("patch_bbox", (B * 3, 3), torch.int64, dev)
+            ps, bb = flat[:, COL_PATCH_MAX], flat[:, COL_BBOX:COL_BBOX + 3]
             k2_ws = self._buf("k2_ws", (max(patch_max_workspace_bytes(cb * 3, spatial, patch), 8),),
                               torch.uint8, dev)   # one workspace: K2b launches are serialised on one stream
         for ci, b0 in enumerate(range(0, B, cb)):
@@ -216,25 +213,12 @@ class UncertaintyPipeline:
                     st["done"][slot] = torch.cuda.Event()
                     st["done"][slot].record(side)
 
-        def assemble():
-            scores = torch.zeros((B, 3, N_COLS), dtype=torch.float64, device=dev)
-            scores[:, :, :3] = k1_scores
-            if patch is not None:
-                scores[:, :, COL_PATCH_MAX] = ps.view(B, 3)
-                scores[:, :, COL_BBOX + 3 - nd:COL_BBOX + 3] = bb.view(B, 3, 3)[:, :, 3 - nd:]
-            return scores
-
         ready = None
-        if overlap:   # the table is put together behind the last K2b, on the side stream
-            with torch.cuda.stream(side):
-                scores = assemble()
-                ready = torch.cuda.Event()
-                ready.record(side)
-            for t in (k1_scores, ps, bb) + ((maps_all,) if keep_maps else ()):
-                t.record_stream(side)     # allocated on the main stream, last read on the side stream
-            scores.record_stream(main)    # allocated on the side stream, read by the caller on main
-        else:
-            scores = assemble()
+        if overlap:   # the table is complete behind the last K2b, on the side stream
+            ready = torch.cuda.Event()
+            ready.record(side)
+            for t in (scores,) + ((maps_all,) if keep_maps else ()):
+                t.record_stream(side)     # allocated on the main stream, last written on the side stream
         return PipelineResult(_scores=scores, ready=ready, maps=maps_all.permute(1, 0, *range(2, 2 + nd)) if keep_maps else None,
                               mean_argmax=am, ssn=ssn, patch_size=patch,
                               thresholds=cfg.thresholds, threshold_mean=cfg.threshold_mean)

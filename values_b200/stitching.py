@@ -44,6 +44,7 @@ def stitch_accumulate(
     patch_index: Optional[torch.Tensor] = None,  # int32 [n_sel] or None (identity)
     accumulate: bool = True,
     weight: Optional[torch.Tensor] = None,     # fp64 [p0, p1, p2] importance map (None = uniform)
+    path: int = 0,                             # 0 automatic, 1 scalar kernel (tests; same results)
 ) -> None:
     if patches.device.type != "cuda":
         raise RuntimeError("stitch_accumulate expects CUDA tensors (no CPU fallback)")
@@ -76,7 +77,7 @@ def stitch_accumulate(
             patches.data_ptr(), _lib.dtype_code(patches.dtype), patches.stride()[0],
             patches.stride()[1], _lib.ptr(patch_index), crop_lo.data_ptr(), _lib.ptr(weight), n_sel, N, Cn,
             _lib.i64x3(patches.shape[3:]), _lib.i64x3(out_sum.shape[2:]), out_sum.data_ptr(),
-            _lib.dtype_code(out_sum.dtype), _lib.ptr(out_count), int(accumulate),
+            _lib.dtype_code(out_sum.dtype), _lib.ptr(out_count), int(accumulate), int(path),
             _lib.stream_ptr(dev))
     _lib.check(rc)
 
@@ -100,7 +101,7 @@ def gaussian_importance_map(patch_shape: Sequence[int], sigma_scale: float = 0.1
 
 def stitch_volume(patches: torch.Tensor, crops, vol_shape: Sequence[int],
                   out_dtype: torch.dtype = torch.float64,
-                  weight: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                  weight: Optional[torch.Tensor] = None, path: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """All patches of one volume at once: patches [N, P, C, p,p,p] + P crops ->
     (raw sum [N, C, X, Y, Z], count fp64 [X, Y, Z]); every output voxel is written exactly
     once (uncovered voxels are 0, as in the reference).  With `weight` [p,p,p] the sum is
@@ -110,5 +111,5 @@ def stitch_volume(patches: torch.Tensor, crops, vol_shape: Sequence[int],
     N, _, Cn = patches.shape[:3]
     out = torch.empty((N, Cn) + tuple(vol_shape), dtype=out_dtype, device=dev)
     cnt = torch.empty(tuple(vol_shape), dtype=torch.float64, device=dev)
-    stitch_accumulate(patches, crop_lo, out, cnt, accumulate=False, weight=weight)
+    stitch_accumulate(patches, crop_lo, out, cnt, accumulate=False, weight=weight, path=path)
     return out, cnt

@@ -81,6 +81,8 @@ def uncertainty_fused(
     out_scores: Optional[torch.Tensor] = None,
     out_argmax: Optional[torch.Tensor] = None,
     workspace: Optional[torch.Tensor] = None,
+    variant: int = 0,
+    tiles_per_cta: int = 0,
 ) -> FusedResult:
     """One HBM sweep over `probs` [B, N, C, *S] (CUDA; B/N/C axes may be strided views, e.g.
     a permuted [N, B, C, H, W] stack as test_2D.py:317 builds it).
@@ -89,8 +91,9 @@ def uncertainty_fused(
     out_maps:   optional preallocated fp32 buffer to write the maps into: [3, B, *S] (pe, ee, mi
                 planes, map-major) or, with volume_major=True, [B, 3, *S] -- the layout K2b
                 consumes as 3B consecutive maps.
-    out_scores / out_argmax / workspace: optional preallocated outputs ([B, 3, 3] fp64,
-                [B, *S] uint8, uint8 scratch) so that a pipeline can run without allocating.
+    out_scores / out_argmax / workspace: optional preallocated outputs ([B, 3, 3] fp64 -- or a
+                [B, 3, W >= 3] fp64 row-strided view such as table[:, :, :3] of a score table, written in
+                place --, [B, *S] uint8, uint8 scratch) so that a pipeline can run without allocating.
     """
     if probs.dim() < 3:
         raise ValueError("probs must be [B, N, C, *spatial]")
@@ -125,15 +128,17 @@ def uncertainty_fused(
     am = out_argmax if mean_argmax else None
     sam = torch.empty((B, N) + spatial, dtype=torch.uint8, device=dev) if sample_argmax else None
     sc_out = ws = None
-    ws_bytes = 0
+    ws_bytes, score_stride = 0, 3
     thr = None
     if scores:
         if out_scores is None:
             out_scores = torch.empty((B, 3, 3), dtype=torch.float64, device=dev)
         elif tuple(out_scores.shape) != (B, 3, 3) or out_scores.dtype != torch.float64 \
-                or not out_scores.is_contiguous():
-            raise ValueError("out_scores must be a contiguous fp64 [B, 3, 3] tensor")
+                or out_scores.stride(2) != 1 or out_scores.stride(1) < 3 \
+                or (B > 1 and out_scores.stride(0) != 3 * out_scores.stride(1)):
+            raise ValueError("out_scores must be an fp64 [B, 3, 3] tensor, rows contiguous and evenly strided")
         sc_out = out_scores
+        score_stride = out_scores.stride(1)
         ws_bytes = _lib.lib.values_uncertainty_workspace_bytes(B, V, _lib.dtype_code(probs.dtype))
         if workspace is not None and workspace.numel() * workspace.element_size() >= ws_bytes:
             ws = workspace
@@ -147,7 +152,8 @@ def uncertainty_fused(
         rc = _lib.lib.values_uncertainty_fused(
             probs.data_ptr(), _lib.dtype_code(probs.dtype), B, N, C, V, sb, sn, sc,
             _lib.ptr(pe), _lib.ptr(ee), _lib.ptr(mi), map_stride_b, _lib.ptr(am), _lib.ptr(sam),
-            _lib.ptr(sc_out), thr, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+            _lib.ptr(sc_out), score_stride, thr, _lib.ptr(ws), ws_bytes, int(variant), int(tiles_per_cta),
+            _lib.stream_ptr(dev))
     _lib.check(rc)
     return FusedResult(pe, ee, mi, am, sam, sc_out)
 
