@@ -144,7 +144,8 @@ int values_stitch_accumulate(const void* patches, int patch_dtype, int64_t patch
                              const int64_t* patch3_host, const int64_t* vol3_host,
                              void* out_sum, int out_dtype, double* out_count, int accumulate,
                              int path, void* stream);
-/* `path`: 0 automatic (vector kernel when rows are 16-byte aligned), 1 scalar kernel; same results. */
+/* `path`: 0 automatic (output boxes fed by tensor-map copies when the rows are 16-byte aligned, else the
+ * register-staged vector kernel, else the scalar kernel), 1 scalar kernel, 2 vector kernel; same results. */
 
 /* The same accumulator with a per-patch importance map (BASELINE.json north_star: "Gaussian-
  * weighted sliding-window patch stitching"; the reference itself accumulates with uniform weights,

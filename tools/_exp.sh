@@ -1,5 +1,10 @@
-for cfg in 0 3 4; do for pol in 0 512; do
-VALUES_K2B_CFG=$cfg VALUES_K2B_POL=$pol ncu --metrics gpu__time_duration.sum --clock-control none -k regex:box_strip --csv python tools/k2_bench.py --shape 128,128,128 --maps 96 --paths 0 --reps 1 2>&1 | grep box_strip | tail -1 | awk -F, -v p=$pol -v c=$cfg '{print "CFG=" c " POL=" p, $NF}'
-done; 
-echo -n "CFG=$cfg "; VALUES_K2B_CFG=$cfg python tools/k2_bench.py --shape 128,128,128 --maps 96 --paths 0 2>&1 | tail -1 | cut -c1-100
-done
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_counts.py tests/test_configs.py tests/test_gpu_formats.py tests/test_gpu_patch.py -q -m gpu -x 2>&1 | tail -6
+python tools/k1_bench.py --shape cfg3n8 --variants 0,4 2>&1 | tail -2
+python tools/k1_bench.py --shape cfg1 --variants 0,4 2>&1 | tail -2
+python tools/k1_bench.py --shape cfg5f64 --variants 0 2>&1 | tail -1
+python tools/k34_bench.py --reps 5 2>&1 | head -12
+echo "== racecheck with the all-lanes-arrive build"
+VALUES_B200_LIB=values_b200/lib_sanitize/libvalues_b200.so timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_k1_k3.py 2>&1 | tail -6
+VALUES_B200_LIB=values_b200/lib_sanitize/libvalues_b200.so timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_k2.py 2>&1 | tail -4
+echo "== memcheck, product build"
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_k1_k3.py 2>&1 | tail -4

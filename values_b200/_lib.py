@@ -11,7 +11,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libvalues_b200.so")
+# VALUES_B200_LIB: an alternative build of the same library (the compute-sanitizer build, values_b200/build.py)
+LIB_PATH = os.environ.get("VALUES_B200_LIB") or os.path.join(_PKG, "lib", "libvalues_b200.so")
 
 F32, F64, BF16, U8, I32, I64 = 0, 1, 2, 3, 4, 5
 ABI_VERSION = 6  # include/values_b200.h VALUES_ABI_VERSION

@@ -18,7 +18,8 @@ LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvalues_b200.so")
 OBJ_DIR = os.path.join(PKG, "build")
 SOURCES = ["api.cu", "uncertainty.cu", "aggregate.cu", "stitch.cu", "stats.cu", "formats.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "values_b200.h")]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tma_host.cuh"), os.path.join(CSRC, "log64_table.inc"),
+           os.path.join(ROOT, "include", "values_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -40,8 +41,16 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu for sm_100a and link the shared library.  Returns its path."""
+def build(force: bool = False, verbose: bool = False, sanitize: bool = False) -> str:
+    """Compile every .cu for sm_100a and link the shared library.  Returns its path.
+    sanitize=True builds values_b200/lib_sanitize/libvalues_b200.so with -DVALUES_ALL_LANES_ARRIVE (every
+    lane of a consumer warp arrives on the ring's empty barrier itself, see csrc/common.cuh) for
+    compute-sanitizer racecheck runs; VALUES_B200_LIB=<path> makes values_b200._lib load it."""
+    global LIB_DIR, LIB_PATH, OBJ_DIR, NVCC_FLAGS
+    if sanitize:
+        LIB_DIR, OBJ_DIR = os.path.join(PKG, "lib_sanitize"), os.path.join(PKG, "build_sanitize")
+        LIB_PATH = os.path.join(LIB_DIR, "libvalues_b200.so")
+        NVCC_FLAGS = NVCC_FLAGS + ["-DVALUES_ALL_LANES_ARRIVE"]
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
@@ -69,4 +78,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, sanitize="--sanitize" in sys.argv))

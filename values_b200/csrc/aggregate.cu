@@ -3,12 +3,11 @@
 //   K2b patch_max  : fp64 sliding box-sum, max, first-isclose index      (:13-31)
 //   normalize_maps : map / clip(count, 1) in fp64                        (data_carrier_3D.py:326-329)
 // All HBM/L2-bound; algorithmic bytes = sizeof(T) per map voxel, outputs O(1).
-#include <cuda.h>
-
 #include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace vb {
 
@@ -981,7 +980,7 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
     constexpr uint32_t kPlaneBytes = ST::PLANE * sizeof(float);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < ST::NSTAGE; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, NW); }
+        for (int s = 0; s < ST::NSTAGE; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, NW * kArriveLanes); }
         for (int q = 0; q < 4; ++q) {
             s_cnt[q] = 0;
             for (int i = 0; i < ST::NSLOT; ++i) s_key[q][i] = kStripKeyNinf;
@@ -1064,7 +1063,7 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
             // behind the last window sum (which needs them all) and a warp barrier
             asm volatile("" ::"f"(zs[0].x), "f"(zs[RW - 1].w) : "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar + stage);
+            if (arrives(lane)) mbar_arrive(empty_bar + stage);
             if (!ym && zi < p0 - 1) continue;                   // z-window still filling
             // ---- y-stage (registers) and x-stage (shuffles) of this output plane / CTA row
             const int cy_cur = ym ? cy + zi : cy;
@@ -1356,22 +1355,6 @@ static double filter_err_coef(int zc, int p0, int pc, int s1, int s2) {
     const double e1 = pc * ez + (d * pc + s1 * (pc + 2)) * p0;
     const double e2 = pc * e1 + (d * pc + s2 * (pc + 2)) * (double)pc * p0;
     return 2.0 * u * e2;
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link against libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            f = nullptr;
-        return reinterpret_cast<EncodeTiledFn>(f);
-    }();
-    return fn;
 }
 
 // fp32 maps [M][D0][D1][D2] as a 4-D tensor map with a [1][1][rows][cols] box

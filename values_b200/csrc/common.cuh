@@ -110,6 +110,19 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* smem /* [K * 8
     }
 }
 
+// Ring hand-back.  A consumer warp hands a stage back to the copy engine with ONE arrive, by lane 0,
+// after a warp barrier that orders every lane's shared-memory reads before it (__syncwarp guarantees
+// memory ordering among the participating threads).  compute-sanitizer's racecheck does not connect
+// the other 31 lanes' reads to lane 0's arrive and reports the next copy into the stage as a hazard;
+// building with -DVALUES_ALL_LANES_ARRIVE makes every lane arrive itself (barrier count x 32; slower),
+// which is the build the sanitizer logs under profiles/ were taken with.
+#ifdef VALUES_ALL_LANES_ARRIVE
+constexpr int kArriveLanes = 32;
+#else
+constexpr int kArriveLanes = 1;
+#endif
+__device__ __forceinline__ bool arrives(int lane) { return kArriveLanes == 32 || lane == 0; }
+
 // ------------------------------------------------------------------ async copies (TMA engine) + mbarriers
 // Producer / consumer rings: the producer arms a stage's "full" barrier with the byte count and
 // issues cp.async.bulk[.tensor] copies that complete on it; consumer warps wait on "full", read
@@ -162,6 +175,10 @@ __device__ __forceinline__ void tma_load_4d_addr(uint32_t dst, const void* tmap,
 __device__ __forceinline__ void tma_load_4d_addr_hint(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar, uint64_t pol) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
                  ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_addr(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"

@@ -7,6 +7,7 @@
 // and writes each output voxel exactly once.  No atomics, bit-reproducible.
 // Algorithmic bytes: every patch element read once + every output element written once.
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace vb {
 
@@ -354,6 +355,269 @@ __global__ void __launch_bounds__(kThreads, 3) stitch_vec_kernel(const StitchPar
     }
 }
 
+// ------------------------------------------------------------------ K3 box kernel (TMA ring)
+// The same output-stationary scheme with the patch data arriving through the copy engine: a CTA owns
+// an output box of kBX x kBY x kBZ voxels of one sample; for every class and every patch that
+// overlaps the box (list order = the reference's summation order) ONE cp.async.bulk.tensor copy
+// brings the box-shaped window of that patch into a shared-memory ring -- the part of the window
+// that lies outside the patch arrives as zeros -- while the eight consumer warps add the previous
+// window into their fp64 accumulators (four float4 groups of voxels per thread, conflict-free
+// LDS.128).  kStages windows (16 KB each for fp32 patches) are in flight per CTA regardless of how
+// far the arithmetic has got, which is what the register-staged vector kernel lacked (ncu r01e:
+// long-scoreboard bound, 32 B in flight per thread).  Every output voxel is still written exactly
+// once and sums are bit-identical to the other kernels.
+// A patch whose z origin is not a multiple of the 16-byte copy granularity cannot be fetched this
+// way (the innermost tensor coordinate must be 16-byte aligned); the consumers read such a patch
+// straight from global memory, element by element, in its place in the list.
+constexpr int kBX = 8, kBY = 16, kBZ = 32;             // output box of a CTA
+constexpr int kBoxVox = kBX * kBY * kBZ;               // 4096 voxels = 1024 groups of 4 = 4 groups per thread
+constexpr int kGroups = kBoxVox / 4 / kThreads;
+constexpr int kBoxList = 256;                           // overlapping patches kept per chunk (4 KB: two CTAs per SM)
+
+template <typename TP> struct StitchRing {
+    static constexpr int kBytes = kBoxVox * (int)sizeof(TP);          // one window
+    static constexpr int kStages = sizeof(TP) == 8 ? 3 : 6;
+    static constexpr int kAlign = sizeof(TP) == 2 ? 8 : 4;            // elements: 16-byte copies and whole groups of 4
+    static constexpr size_t smem = (size_t)kStages * kBytes + 128;
+};
+
+// four consecutive elements from shared memory, widened to fp64
+template <typename TP> __device__ __forceinline__ void lds_group(uint32_t addr, double (&o)[4]);
+template <> __device__ __forceinline__ void lds_group<float>(uint32_t addr, double (&o)[4]) {
+    const uint4 r = lds128(addr);
+    Raw4<float>::widen(r, o);
+}
+template <> __device__ __forceinline__ void lds_group<__nv_bfloat16>(uint32_t addr, double (&o)[4]) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+    Raw4<__nv_bfloat16>::widen(r, o);
+}
+template <> __device__ __forceinline__ void lds_group<double>(uint32_t addr, double (&o)[4]) {
+    Raw4<double>::type r;
+    r.a = lds128(addr); r.b = lds128(addr + 16);
+    Raw4<double>::widen(r, o);
+}
+
+template <typename TP, typename TO, bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads + 32, 2)
+stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams prm, int rows_per_sample) {
+    using SR = StitchRing<TP>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[SR::kStages];
+    __shared__ __align__(8) uint64_t empty_bar[SR::kStages];
+    __shared__ int4 s_list[kBoxList];           // {cx, cy, cz, patch index} of the overlapping patches
+    __shared__ int s_warp_cnt[kThreads / 32];
+    __shared__ int s_total;
+
+    int tile = blockIdx.x;
+    const int tz = tile % prm.tiles_z; tile /= prm.tiles_z;
+    const int ty = tile % prm.tiles_y; tile /= prm.tiles_y;
+    const int x_lo = tile * kBX, y_lo = ty * kBY, z_lo = tz * kBZ;
+    const int x_hi = (int)min((int64_t)x_lo + kBX, prm.X);
+    const int64_t n = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp == kThreads / 32;
+    const int64_t vol = prm.X * prm.Y * prm.Z;
+    const int64_t pvol = (int64_t)prm.p0 * prm.p1 * prm.p2;
+    TO* out = reinterpret_cast<TO*>(prm.out_sum) + n * prm.C * vol;
+    const TP* pin = reinterpret_cast<const TP*>(prm.patches) + n * prm.stride_n;
+    const uint32_t ring = (smem_u32(smem_raw) + 127u) & ~127u;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SR::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, kThreads / 32 * kArriveLanes); }
+        mbar_fence_init();
+    }
+    // this thread's voxel groups: group g = tid + kThreads * i -> (x, y, z) inside the box
+    int gx[kGroups], gy[kGroups], gz[kGroups];
+    bool gin[kGroups];
+#pragma unroll
+    for (int i = 0; i < kGroups; ++i) {
+        const int g = (tid & (kThreads - 1)) + kThreads * i, row = g / (kBZ / 4);
+        gx[i] = x_lo + row / kBY; gy[i] = y_lo + row % kBY; gz[i] = z_lo + (g % (kBZ / 4)) * 4;
+        gin[i] = !producer && gx[i] < prm.X && gy[i] < prm.Y && gz[i] < prm.Z;   // Z % 4 == 0: whole groups
+    }
+    unsigned int it = 0;        // windows that went through the ring so far (producer and consumers count alike)
+    for (int64_t base = 0; base < prm.n_sel; base += kBoxList) {
+        // ---- ordered compaction of the patches overlapping this CTA's box (chunk of kBoxList)
+        const int64_t chunk = min((int64_t)kBoxList, prm.n_sel - base);
+        if (tid == 0) s_total = 0;
+        __syncthreads();
+        for (int64_t off = 0; off < chunk; off += kThreads) {
+            const int64_t i = base + off + tid;
+            bool hit = false;
+            int4 e = make_int4(0, 0, 0, 0);
+            if (!producer && off + tid < chunk) {
+                e.x = prm.crop_lo[3 * i]; e.y = prm.crop_lo[3 * i + 1]; e.z = prm.crop_lo[3 * i + 2];
+                e.w = prm.patch_index ? prm.patch_index[i] : (int)i;
+                hit = x_lo < e.x + prm.p0 && x_hi > e.x && y_lo < e.y + prm.p1 && y_lo + kBY > e.y &&
+                      z_lo < e.z + prm.p2 && z_lo + kBZ > e.z;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0 && !producer) s_warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int before = s_total;
+            for (int w = 0; w < warp && w < kThreads / 32; ++w) before += s_warp_cnt[w];
+            if (hit) s_list[before + __popc(bal & ((1u << lane) - 1u))] = e;
+            __syncthreads();
+            if (tid == 0) {
+                int t = s_total;
+                for (int w = 0; w < kThreads / 32; ++w) t += s_warp_cnt[w];
+                s_total = t;
+            }
+            __syncthreads();
+        }
+        const int total = s_total;
+        const bool readback = base > 0 || prm.accumulate;
+        if (producer) {
+            // ---- one lane streams the windows: classes outer, listed patches inner
+            if (lane == 0) {
+                for (int c = 0; c < (int)prm.C; ++c) {
+                    for (int k = 0; k < total; ++k) {
+                        const int4 e = s_list[k];
+                        if (e.z % SR::kAlign) continue;                     // read directly by the consumers
+                        const int stage = it % SR::kStages;
+                        if (it >= SR::kStages) mbar_wait(empty_bar + stage, ((it / SR::kStages) & 1) ^ 1u);
+                        mbar_expect_tx(full_bar + stage, SR::kBytes);
+                        tma_load_5d_addr(ring + stage * SR::kBytes, &tmap, z_lo - e.z, y_lo - e.y, x_lo - e.x, c,
+                                         (int)(n * rows_per_sample + e.w), full_bar + stage);
+                        ++it;
+                    }
+                }
+            }
+        } else {
+            // pass c < C: class c; pass C (sample 0 only): the count -- same walk, no data
+            const int passes = (int)prm.C + ((n == 0 && prm.out_count) ? 1 : 0);
+            for (int c = 0; c < passes; ++c) {
+                const bool count_pass = c == (int)prm.C;
+                double acc[kGroups][4];
+#pragma unroll
+                for (int i = 0; i < kGroups; ++i) {
+                    const int64_t vox = ((int64_t)gx[i] * prm.Y + gy[i]) * prm.Z + gz[i];
+                    if (readback && gin[i]) {
+                        if (count_pass) read4(prm.out_count + vox, acc[i]);
+                        else read4(out + c * vol + vox, acc[i]);
+                    } else {
+                        acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0;
+                    }
+                }
+                for (int k = 0; k < total; ++k) {
+                    const int4 e = s_list[k];
+                    const bool aligned = e.z % SR::kAlign == 0;
+                    int stage = 0;
+                    if (aligned && !count_pass) {
+                        stage = it % SR::kStages;
+                        mbar_wait(full_bar + stage, (it / SR::kStages) & 1);
+                        ++it;
+                    }
+#pragma unroll
+                    for (int i = 0; i < kGroups; ++i) {
+                        const int lx = gx[i] - e.x, ly = gy[i] - e.y, lz = gz[i] - e.z;
+                        const bool in_xy = gin[i] && lx >= 0 && lx < prm.p0 && ly >= 0 && ly < prm.p1;
+                        const int64_t local = ((int64_t)lx * prm.p1 + ly) * prm.p2 + lz;
+                        if (aligned) {
+                            const bool in = in_xy && lz >= 0 && lz < prm.p2;         // whole group in or out
+                            double v[4] = {1.0, 1.0, 1.0, 1.0};
+                            if (!count_pass) lds_group<TP>(ring + stage * SR::kBytes + ((tid & (kThreads - 1)) + kThreads * i) * 4 * (int)sizeof(TP), v);
+                            if (in) {
+                                if (WEIGHTED) {
+                                    double w[4];
+                                    Raw4<double>::widen(Raw4<double>::load(prm.weight + local), w);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q)
+                                        acc[i][q] = count_pass ? acc[i][q] + w[q] : __dadd_rn(acc[i][q], __dmul_rn(w[q], v[q]));
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) acc[i][q] += v[q];
+                                }
+                            }
+                        } else if (in_xy) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (lz + q < 0 || lz + q >= prm.p2) continue;
+                                const double w = WEIGHTED ? __ldg(prm.weight + local + q) : 1.0;
+                                const double v = count_pass ? 1.0 : (double)In<TP>::load_one(pin + (int64_t)e.w * prm.stride_p + c * pvol + local + q);
+                                acc[i][q] = !WEIGHTED ? acc[i][q] + v : count_pass ? acc[i][q] + w : __dadd_rn(acc[i][q], __dmul_rn(w, v));
+                            }
+                        }
+                    }
+                    if (aligned && !count_pass) {
+                        // hand the slot back once the loads above have returned: the arrive sits behind
+                        // arithmetic that consumed them (the same ordering as K1's ring) and a warp barrier
+                        asm volatile("" ::"d"(acc[0][0]), "d"(acc[kGroups - 1][3]) : "memory");
+                        __syncwarp();
+                        if (arrives(lane)) mbar_arrive(empty_bar + stage);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kGroups; ++i) {
+                    if (!gin[i]) continue;
+                    const int64_t vox = ((int64_t)gx[i] * prm.Y + gy[i]) * prm.Z + gz[i];
+                    if (count_pass) store4<double>(prm.out_count + vox, acc[i]);
+                    else store4<TO>(out + c * vol + vox, acc[i]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// patches [rows = (sample, patch)][C][p0][p1][p2] as a 5-D tensor map with a [1][1][kBX][kBY][kBZ] box
+template <typename TP>
+static int make_patch_tensor(const StitchParams& prm, CUtensorMap* tm) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return set_error(VALUES_ERR_CUDA, "stitch: cuTensorMapEncodeTiled is not available");
+    const cuuint64_t es = sizeof(TP);
+    const cuuint64_t pvol = (cuuint64_t)prm.p0 * prm.p1 * prm.p2;
+    // the number of (sample, patch) rows behind the pointer is not known here: any index the caller's
+    // patch_index / sample count can produce is inside the declared extent
+    const cuuint64_t gdim[5] = {(cuuint64_t)prm.p2, (cuuint64_t)prm.p1, (cuuint64_t)prm.p0, (cuuint64_t)prm.C, 0x7fffffffull};
+    const cuuint64_t gstr[4] = {(cuuint64_t)prm.p2 * es, (cuuint64_t)prm.p1 * prm.p2 * es, pvol * es,
+                                (cuuint64_t)prm.stride_p * es};
+    const cuuint32_t box[5] = {kBZ, kBY, kBX, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapDataType dt = sizeof(TP) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
+                                 : sizeof(TP) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUresult r = enc(tm, dt, 5, const_cast<void*>(prm.patches), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(VALUES_ERR_CUDA, "stitch: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return VALUES_OK;
+}
+
+template <typename TP, typename TO>
+static int launch_stitch_box(StitchParams prm, cudaStream_t st) {
+    using SR = StitchRing<TP>;
+    CUtensorMap tm;
+    int rc = make_patch_tensor<TP>(prm, &tm);
+    if (rc) return rc;
+    prm.tiles_z = (int)ceil_div(prm.Z, kBZ);
+    prm.tiles_y = (int)ceil_div(prm.Y, kBY);
+    const int64_t tiles = (int64_t)prm.tiles_z * prm.tiles_y * ceil_div(prm.X, kBX);
+    if (tiles > 0x7fffffffLL || prm.N > 65535) return set_error(VALUES_ERR_UNSUPPORTED, "stitch: volume too large");
+    const int rows_per_sample = prm.N > 1 ? (int)(prm.stride_n / prm.stride_p) : 0;
+    const dim3 grid((unsigned)tiles, (unsigned)prm.N);
+    auto launch = [&](auto kern) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SR::smem) != cudaSuccess)
+            return set_error(VALUES_ERR_CUDA, "stitch: cudaFuncSetAttribute(%zu) failed", SR::smem);
+        kern<<<grid, kThreads + 32, SR::smem, st>>>(tm, prm, rows_per_sample);
+        return check_launch("stitch_box_kernel");
+    };
+    return prm.weight ? launch(stitch_box_kernel<TP, TO, true>) : launch(stitch_box_kernel<TP, TO, false>);
+}
+
+// can the box kernel fetch these patches by tensor-map copies?
+static bool stitch_box_ok(const StitchParams& prm, int patch_dtype, int out_dtype, size_t pes, size_t oes) {
+    const int al = pes == 2 ? 8 : 4;
+    const bool rows_mergeable = prm.N == 1 || (prm.stride_p > 0 && prm.stride_n % prm.stride_p == 0 &&
+                                               prm.stride_n / prm.stride_p < 0x7fffffffLL / 65536);
+    return prm.Z % 4 == 0 && prm.p2 % al == 0 && rows_mergeable && (prm.stride_p * (int64_t)pes) % 16 == 0 &&
+           (prm.stride_p * (int64_t)pes) < (1LL << 40) && (reinterpret_cast<uintptr_t>(prm.patches) % 16) == 0 &&
+           (reinterpret_cast<uintptr_t>(prm.out_sum) % (4 * oes)) == 0 &&
+           (!prm.out_count || reinterpret_cast<uintptr_t>(prm.out_count) % 32 == 0) &&
+           (!prm.weight || reinterpret_cast<uintptr_t>(prm.weight) % 32 == 0) &&
+           prm.X < 0x7fffffffLL && prm.Y < 0x7fffffffLL && prm.Z < 0x7fffffffLL && prm.C < 0x7fffffffLL &&
+           (patch_dtype != VALUES_F64 || out_dtype == VALUES_F64) && encode_tiled_fn() != nullptr;
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -368,7 +632,7 @@ extern "C" int values_stitch_accumulate_weighted(const void* patches, int patch_
                                                  int path, void* stream) {
     if (!patches || !crop_lo || !patch3_host || !vol3_host || !out_sum)
         return set_error(VALUES_ERR_INVALID_ARG, "stitch: NULL pointer");
-    if (path != 0 && path != 1) return set_error(VALUES_ERR_INVALID_ARG, "stitch: unknown path %d (0, 1)", path);
+    if (path < 0 || path > 2) return set_error(VALUES_ERR_INVALID_ARG, "stitch: unknown path %d (0, 1, 2)", path);
     if (n_sel < 0 || N <= 0 || C <= 0)
         return set_error(VALUES_ERR_INVALID_ARG, "stitch: bad sizes");
     for (int d = 0; d < 3; ++d)
@@ -395,6 +659,21 @@ extern "C" int values_stitch_accumulate_weighted(const void* patches, int patch_
     // vector kernel: 4 consecutive z voxels per thread (16-byte loads / stores)
     const size_t pes = patch_dtype == VALUES_F64 ? 8 : (patch_dtype == VALUES_F32 ? 4 : 2);
     const size_t oes = out_dtype == VALUES_F64 ? 8 : 4;
+    if (path == 0 && stitch_box_ok(prm, patch_dtype, out_dtype, pes, oes)) {
+        // default: output boxes fed by tensor-map copies through a shared-memory ring
+        if (out_dtype == VALUES_F64) {
+            if (patch_dtype == VALUES_F64) return launch_stitch_box<double, double>(prm, st);
+            if (patch_dtype == VALUES_F32) return launch_stitch_box<float, double>(prm, st);
+            if (patch_dtype == VALUES_BF16) return launch_stitch_box<__nv_bfloat16, double>(prm, st);
+            return set_error(VALUES_ERR_INVALID_ARG, "stitch: unknown patch dtype");
+        }
+        if (out_dtype == VALUES_F32) {
+            if (patch_dtype == VALUES_F32) return launch_stitch_box<float, float>(prm, st);
+            if (patch_dtype == VALUES_BF16) return launch_stitch_box<__nv_bfloat16, float>(prm, st);
+            return set_error(VALUES_ERR_INVALID_ARG, "stitch: f32 output needs f32/bf16 patches");
+        }
+        return set_error(VALUES_ERR_INVALID_ARG, "stitch: out dtype must be f64 or f32");
+    }
     const bool vec_ok = path != 1 && prm.Z % 4 == 0 && prm.p2 % 4 == 0 &&
                         (reinterpret_cast<uintptr_t>(patches) % (4 * pes)) == 0 &&
                         (patch_stride_n % 4) == 0 && (patch_stride_p % 4) == 0 &&

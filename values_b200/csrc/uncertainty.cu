@@ -86,96 +86,44 @@ __device__ __forceinline__ float fast_logf(float p) {
 // The reference computes p*log(p) in the INPUT dtype and adds it into an fp32 accumulator
 // (test_3D.py:490-506); for fp64 stacks (its 3D path) CUDA's log(double) -- ~1 ulp, every special
 // case handled inline -- was what bounded the kernel (0.28 of the HBM peak).  The terms only have
-// to survive the rounding into fp32, so a table-driven log with <= 3e-14 relative error does:
-//   p = m * 2^k, m in [sqrt(2)/2, sqrt(2));  interval i = top 7 mantissa bits of m (129 intervals);
-//   r = fma(m, inv_i, -1) with inv_i ~ 1/centre_i rounded to 10 bits (|r| <= 2^-7; the two intervals
-//   around 1 use inv = 1, so r = m - 1 exactly and log keeps its relative accuracy near p = 1);
-//   log(p) = k*ln2 + (-log(inv_i)) + log1p(r),  log1p by its series to r^7.
+// to survive the rounding into fp32, so a table-driven log with <= 5e-15 relative error does:
+//   p = m * 2^k, m in [~sqrt(2)/2, ~sqrt(2)): the split point has a zero low word, so k, the table
+//   index and the mantissa rebias are 32-bit integer operations on the HIGH word of p alone;
+//   interval i = top 9 mantissa bits of m (513 intervals); r = fma(m, inv_i, -1) with inv_i ~ 1/centre_i
+//   rounded to 12 bits (|r| <= 2^-9; the two intervals around 1 use inv = 1, so r = m - 1 exactly and
+//   the log keeps its relative accuracy near p = 1);
+//   log(p) = k*ln2 + (-log(inv_i)) + log1p(r),  log1p by its series to r^5.
 // Checked against a 120-bit reference over 5e5 values from 1e-300 to 8 incl. 1 +- 1e-15
-// (tools/check_log64.py): max relative error 2.3e-14, i.e. a term changes its fp32 rounding
-// about once in 2e6.  Zero, negative, NaN, inf and subnormal inputs take log().
-__device__ const double2 kLog64Tab[129] = {
-    {0x1.6900000000000p+0, -0x1.5ff3070a793d4p-2}, {0x1.6700000000000p+0, -0x1.5a42ab0f4cfe2p-2},
-    {0x1.6500000000000p+0, -0x1.548a2c3add263p-2}, {0x1.6300000000000p+0, -0x1.4ec973260026ap-2},
-    {0x1.6180000000000p+0, -0x1.4a7373cecf997p-2}, {0x1.5f80000000000p+0, -0x1.44a41b463c47cp-2},
-    {0x1.5d80000000000p+0, -0x1.3ecc460ef5f50p-2}, {0x1.5b80000000000p+0, -0x1.38ebdb38ed321p-2},
-    {0x1.5a00000000000p+0, -0x1.347dd9a987d55p-2}, {0x1.5800000000000p+0, -0x1.2e8e2bae11d31p-2},
-    {0x1.5600000000000p+0, -0x1.2895a13de86a3p-2}, {0x1.5480000000000p+0, -0x1.241558bfd1404p-2},
-    {0x1.5280000000000p+0, -0x1.1e0d0c33716bep-2}, {0x1.5100000000000p+0, -0x1.1980d2dd4236fp-2},
-    {0x1.4f00000000000p+0, -0x1.136870293a8b0p-2}, {0x1.4d80000000000p+0, -0x1.0ed005f657da4p-2},
-    {0x1.4c00000000000p+0, -0x1.0a324e27390e3p-2}, {0x1.4a00000000000p+0, -0x1.0402594b4d041p-2},
-    {0x1.4880000000000p+0, -0x1.feb0233e607ccp-3}, {0x1.4700000000000p+0, -0x1.f550a564b7b37p-3},
-    {0x1.4500000000000p+0, -0x1.e8c0252aa5a60p-3}, {0x1.4380000000000p+0, -0x1.df46c0c722d2fp-3},
-    {0x1.4200000000000p+0, -0x1.d5c216b4fbb91p-3}, {0x1.4080000000000p+0, -0x1.cc320c0176502p-3},
-    {0x1.3f00000000000p+0, -0x1.c2968558c18c1p-3}, {0x1.3d80000000000p+0, -0x1.b8ef670420c3bp-3},
-    {0x1.3c00000000000p+0, -0x1.af3c94e80bff3p-3}, {0x1.3a80000000000p+0, -0x1.a57df28244dcdp-3},
-    {0x1.3900000000000p+0, -0x1.9bb362e7dfb83p-3}, {0x1.3780000000000p+0, -0x1.91dcc8c340bdep-3},
-    {0x1.3600000000000p+0, -0x1.87fa06520c911p-3}, {0x1.3480000000000p+0, -0x1.7e0afd630c274p-3},
-    {0x1.3300000000000p+0, -0x1.740f8f54037a5p-3}, {0x1.3180000000000p+0, -0x1.6a079d0f7aad2p-3},
-    {0x1.3000000000000p+0, -0x1.5ff3070a793d4p-3}, {0x1.2e80000000000p+0, -0x1.55d1ad4232d6fp-3},
-    {0x1.2d80000000000p+0, -0x1.4f099f4a230b2p-3}, {0x1.2c00000000000p+0, -0x1.44d2b6ccb7d1ep-3},
-    {0x1.2a80000000000p+0, -0x1.3a8eb2d31a376p-3}, {0x1.2900000000000p+0, -0x1.303d718e47fd3p-3},
-    {0x1.2800000000000p+0, -0x1.29552f81ff523p-3}, {0x1.2680000000000p+0, -0x1.1eed90e2dc2c3p-3},
-    {0x1.2500000000000p+0, -0x1.14785846742acp-3}, {0x1.2400000000000p+0, -0x1.0d77e7cd08e59p-3},
-    {0x1.2280000000000p+0, -0x1.02ebb42bf3d4bp-3}, {0x1.2180000000000p+0, -0x1.f7b79fec37ddfp-4},
-    {0x1.2000000000000p+0, -0x1.e27076e2af2e6p-4}, {0x1.1f00000000000p+0, -0x1.d4313d66cb35dp-4},
-    {0x1.1d80000000000p+0, -0x1.beba818146765p-4}, {0x1.1c80000000000p+0, -0x1.b05b49bee43fep-4},
-    {0x1.1b00000000000p+0, -0x1.9ab42462033adp-4}, {0x1.1a00000000000p+0, -0x1.8c345d6319b21p-4},
-    {0x1.1880000000000p+0, -0x1.765bf23a6be13p-4}, {0x1.1780000000000p+0, -0x1.67bb0726ec0fcp-4},
-    {0x1.1680000000000p+0, -0x1.590cafdf01c28p-4}, {0x1.1500000000000p+0, -0x1.42edcbea646f0p-4},
-    {0x1.1400000000000p+0, -0x1.341d7961bd1d1p-4}, {0x1.1300000000000p+0, -0x1.253f62f0a1417p-4},
-    {0x1.1180000000000p+0, -0x1.0ed839b5526fep-4}, {0x1.1080000000000p+0, -0x1.ffae9119b9303p-5},
-    {0x1.0f80000000000p+0, -0x1.e19070c276016p-5}, {0x1.0e80000000000p+0, -0x1.c355dd0921f2dp-5},
-    {0x1.0d00000000000p+0, -0x1.95c830ec8e3ebp-5}, {0x1.0c00000000000p+0, -0x1.77458f632dcfcp-5},
-    {0x1.0b00000000000p+0, -0x1.58a5bafc8e4d5p-5}, {0x1.0a00000000000p+0, -0x1.39e87b9febd60p-5},
-    {0x1.0900000000000p+0, -0x1.1b0d98923d980p-5}, {0x1.0780000000000p+0, -0x1.d91a66c543cc4p-6},
-    {0x1.0680000000000p+0, -0x1.9ace7551cc514p-6}, {0x1.0580000000000p+0, -0x1.5c45a51b8d389p-6},
-    {0x1.0480000000000p+0, -0x1.1d7f7eb9eebe7p-6}, {0x1.0380000000000p+0, -0x1.bcf712c74384cp-7},
-    {0x1.0280000000000p+0, -0x1.3e7295d25a7d9p-7}, {0x1.0180000000000p+0, -0x1.7ee11ebd82e94p-8},
-    {0x1.0000000000000p+0, 0x0.0p+0}, {0x1.0000000000000p+0, 0x0.0p+0},
-    {0x1.fa00000000000p-1, 0x1.82448a388a2aap-7}, {0x1.f600000000000p-1, 0x1.432a925980cc1p-6},
-    {0x1.f280000000000p-1, 0x1.b5cc258b718e6p-6}, {0x1.ee80000000000p-1, 0x1.1ce5a62bc353ap-5},
-    {0x1.eb00000000000p-1, 0x1.5715c4c03ceefp-5}, {0x1.e780000000000p-1, 0x1.91b073efd7314p-5},
-    {0x1.e380000000000p-1, 0x1.d52ed6405d86fp-5}, {0x1.e000000000000p-1, 0x1.08598b59e3a07p-4},
-    {0x1.dc80000000000p-1, 0x1.26536c3d8c369p-4}, {0x1.d900000000000p-1, 0x1.4485e03dbdfadp-4},
-    {0x1.d600000000000p-1, 0x1.5e95a4d9791cbp-4}, {0x1.d280000000000p-1, 0x1.7d33687c293c9p-4},
-    {0x1.cf00000000000p-1, 0x1.9c0c32d4d2548p-4}, {0x1.cc00000000000p-1, 0x1.b6ac88dad5b1cp-4},
-    {0x1.c880000000000p-1, 0x1.d5f55659210e2p-4}, {0x1.c580000000000p-1, 0x1.f0f70cdd992e3p-4},
-    {0x1.c280000000000p-1, 0x1.06135354d4b18p-3}, {0x1.bf80000000000p-1, 0x1.13c2605c398c3p-3},
-    {0x1.bc80000000000p-1, 0x1.2188fd9807263p-3}, {0x1.b980000000000p-1, 0x1.2f677cbbc0a96p-3},
-    {0x1.b680000000000p-1, 0x1.3d5e3126bc27fp-3}, {0x1.b380000000000p-1, 0x1.4b6d6fefe22a4p-3},
-    {0x1.b080000000000p-1, 0x1.59958ff1d52f1p-3}, {0x1.ad80000000000p-1, 0x1.67d6e9d785771p-3},
-    {0x1.ab00000000000p-1, 0x1.73cb9074fd14dp-3}, {0x1.a800000000000p-1, 0x1.823c16551a3c2p-3},
-    {0x1.a580000000000p-1, 0x1.8e588ebac2dbfp-3}, {0x1.a300000000000p-1, 0x1.9a8778debaa38p-3},
-    {0x1.a000000000000p-1, 0x1.a93ed3c8ad9e3p-3}, {0x1.9d80000000000p-1, 0x1.b5971a213acdbp-3},
-    {0x1.9b00000000000p-1, 0x1.c2028ab17f9b4p-3}, {0x1.9880000000000p-1, 0x1.ce816157f1988p-3},
-    {0x1.9600000000000p-1, 0x1.db13db0d48940p-3}, {0x1.9380000000000p-1, 0x1.e7ba35eb77e2ap-3},
-    {0x1.9100000000000p-1, 0x1.f474b134df229p-3}, {0x1.8e80000000000p-1, 0x1.00a1c6adda473p-2},
-    {0x1.8c00000000000p-1, 0x1.07138604d5862p-2}, {0x1.8980000000000p-1, 0x1.0d8fb813eb1efp-2},
-    {0x1.8780000000000p-1, 0x1.12c77cd00713bp-2}, {0x1.8500000000000p-1, 0x1.1956d3b9bc2fap-2},
-    {0x1.8280000000000p-1, 0x1.1ff0fe7cf47a7p-2}, {0x1.8080000000000p-1, 0x1.25410494e56c7p-2},
-    {0x1.7e00000000000p-1, 0x1.2bef07cdc9354p-2}, {0x1.7c00000000000p-1, 0x1.314f1e1d35ce4p-2},
-    {0x1.7980000000000p-1, 0x1.3811728564cb2p-2}, {0x1.7780000000000p-1, 0x1.3d81fb5946dbap-2},
-    {0x1.7580000000000p-1, 0x1.42f9f3ff62642p-2}, {0x1.7380000000000p-1, 0x1.487970e958770p-2},
-    {0x1.7100000000000p-1, 0x1.4f637ebba9810p-2}, {0x1.6f00000000000p-1, 0x1.54f431b7be1a9p-2},
-    {0x1.6d00000000000p-1, 0x1.5a8cadbbedfa1p-2}, {0x1.6b00000000000p-1, 0x1.602d08af091ecp-2},
-    {0x1.6900000000000p-1, 0x1.65d558d4ce00bp-2},
+// (tools/check_log64.py, which also writes log64_table.inc): max relative error 4.7e-15, i.e. a term
+// changes its fp32 rounding about once in 1e7.
+__device__ const double2 kLog64Tab[513] = {
+#include "log64_table.inc"
 };
-__device__ __forceinline__ double fast_log_f64(double p) {
-    const long long bits = __double_as_longlong(p);
-    if (bits < 0x0010000000000000LL || bits >= 0x7ff0000000000000LL) return log(p);   // also negatives (sign bit)
-    const long long k = (bits - 0x3FE6A09E667F3BCDLL) >> 52;
-    const long long mb = bits - (k << 52);
-    const double2 t = __ldg(&kLog64Tab[(int)(mb >> 45) - 0x1FF35]);
-    const double r = fma(__longlong_as_double(mb), t.x, -1.0);
-    double q = 1.0 / 7.0;
-    q = fma(q, r, -1.0 / 6.0);
-    q = fma(q, r, 0.2);
+constexpr unsigned int kLog64Lo = 0x3FE6A09Eu;     // high word of the split point
+constexpr int kLog64Base = 0x7FCD4;                // kLog64Lo >> 11: table index of the first interval
+
+// exponent, rebiased mantissa and table index from the high word (any bit pattern gives an index inside the table)
+__device__ __forceinline__ void log64_split(int hi, int& k, int& mhi, int& idx) {
+    k = (int)((unsigned int)hi - kLog64Lo) >> 20;
+    mhi = (int)((unsigned int)hi - ((unsigned int)k << 20));
+    idx = (mhi >> 11) - kLog64Base;
+}
+__device__ __forceinline__ double log64_finish(int k, double m, double2 t) {
+    const double r = fma(m, t.x, -1.0);
+    double q = 0.2;
     q = fma(q, r, -0.25);
     q = fma(q, r, 1.0 / 3.0);
     q = fma(q, r, -0.5);
     const double l1p = fma(r * r, q, r);
     return fma((double)k, 0.6931471805599453, t.y + l1p);
+}
+// any input: zero, negative, NaN, inf and subnormal values take log()
+__device__ __forceinline__ double fast_log_f64(double p) {
+    const int hi = __double2hiint(p);
+    if ((unsigned int)(hi - 0x00100000) >= 0x7fe00000u) return log(p);
+    int k, mhi, idx;
+    log64_split(hi, k, mhi, idx);
+    return log64_finish(k, __hiloint2double(mhi, __double2loint(p)), __ldg(&kLog64Tab[idx]));
 }
 
 // acc += p*log(p), NaN terms skipped (test_3D.py:490-494, 500-504).  A term is NaN exactly when
@@ -187,6 +135,23 @@ __device__ __forceinline__ void accum_term(float& acc, float p) {
 __device__ __forceinline__ void accum_term(float& acc, double p) {
     const double t = p * fast_log_f64(p);
     acc = (t == t) ? (float)((double)acc + t) : acc;  // add in fp64, round into fp32
+}
+
+// The N x C entropy terms of the fp64 ring kernel: no special-case branch per element.  The table-driven
+// log gives a FINITE value for every bit pattern (log64_split keeps the index inside the table), so for
+// finite p >= +0 the term p * log(p) is the reference's contribution (exactly 0 for p = 0, below any fp32
+// rounding for subnormals).  Inputs the NaN-skip rule treats differently -- negative, -0, inf, NaN -- are
+// detected from the unsigned maximum of the high words and the voxel's entropy is then recomputed by
+// k1_entropy_exact_samples (cold).  `tab` = shared-memory address of the table copy.
+__device__ __forceinline__ void accum_term_fast(float& acc, double p, unsigned int& hi_max, uint32_t tab) {
+    const int hi = __double2hiint(p);
+    hi_max = max(hi_max, (unsigned int)hi);
+    int k, mhi, idx;
+    log64_split(hi, k, mhi, idx);
+    double2 t;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(tab + (uint32_t)idx * 16u));
+    const double lg = log64_finish(k, __hiloint2double(mhi, __double2loint(p)), t);
+    acc = (float)((double)acc + p * lg);   // add in fp64, round into fp32 (test_3D.py:500-506 on an fp64 stack)
 }
 
 template <typename A>
@@ -551,6 +516,34 @@ __device__ __noinline__ void k1_entropy_exact(const T* base, int N, int C, int64
     for (int j = 0; j < VEC; ++j) E_out[j] = E[j];
 }
 
+// Cold path of the fp64 ring kernel: the reference's own order -- one fp32 accumulator per sample,
+// classes in index order, exact NaN-skip select, the samples' entropies added in index order.
+template <typename T, int VEC>
+__device__ __noinline__ void k1_entropy_exact_samples(const T* base, int N, int C, int64_t sn, int64_t sc,
+                                                      float* E_out) {
+    using A = typename In<T>::acc_t;
+    float E[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) E[j] = 0.f;
+    for (int n = 0; n < N; ++n) {
+        float h[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) h[j] = 0.f;
+        for (int c = 0; c < C; ++c) {
+            Raw<T, VEC> r;
+            load_raw<T, VEC>(base + c * sc + n * sn, r);
+            A p[VEC];
+            unpack(r, p);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) accum_term(h[j], p[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) E[j] += h[j];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) E_out[j] = E[j];
+}
+
 // S += p, packed two at a time for fp32
 template <int VEC> __device__ __forceinline__ void add_rows(float (&S)[VEC], const float (&p)[VEC]) {
     if constexpr (VEC % 2 == 0) {
@@ -730,14 +723,18 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
     constexpr int kStageBytes = RS * kRowBytes;
     extern __shared__ __align__(128) unsigned char ring[];            // [kTmaStages][RS][kRowBytes]
     __shared__ __align__(8) uint64_t full_bar[kTmaStages], empty_bar[kTmaStages];
+    __shared__ __align__(16) double2 s_log_tab[NS > 0 ? 513 : 1];     // fp64 stacks: the log table, 8 KB
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x / prm.blocks_per_vol;
     const int64_t blk = blockIdx.x - b * prm.blocks_per_vol;
     const int N = (int)prm.N, C = (int)prm.C;
     const int64_t snb = prm.sn * (int64_t)sizeof(T), scb = prm.sc * (int64_t)sizeof(T);
+    if constexpr (NS > 0) {
+        for (int i = tid; i < 513; i += kThreads + 32) s_log_tab[i] = kLog64Tab[i];
+    }
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kTmaStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, kThreads / 32); }
+        for (int s = 0; s < kTmaStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, kThreads / 32 * kArriveLanes); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -780,8 +777,9 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
     // issue-bound.
     uint32_t ring_tid = smem_u32(ring) + (uint32_t)tid * 16u;
     uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
-    int is_lane0 = lane == 0;
-    asm volatile("" : "+r"(ring_tid), "+r"(full0), "+r"(empty0), "+r"(is_lane0));
+    int is_lane0 = arrives(lane);
+    uint32_t log_tab = smem_u32(s_log_tab);
+    asm volatile("" : "+r"(ring_tid), "+r"(full0), "+r"(empty0), "+r"(is_lane0), "+r"(log_tab));
     double psum[6];
     int pcnt[3];
 #pragma unroll
@@ -800,6 +798,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
         float e[VEC], E[VEC], PE[VEC], Sacc[VEC];
         int idx[VEC];
         uint32_t bad = 0;
+        unsigned int hi_max = 0;                    // fp64 stacks: largest high word seen (negative / inf / NaN inputs)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             S[j] = (A)0; e[j] = 0.f; E[j] = 0.f; PE[j] = 0.f; idx[j] = 0; best[j] = (A)0; Sacc[j] = 0.f;
@@ -833,7 +832,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                             add_rows<VEC>(S, p);
                             if constexpr (NS > 0) {
 #pragma unroll
-                                for (int j = 0; j < VEC; ++j) accum_term(H[n + h + u][j], p[j]);
+                                for (int j = 0; j < VEC; ++j) accum_term_fast(H[n + h + u][j], p[j], hi_max, log_tab);
                             } else {
                                 M::rows(e, p);
                             }
@@ -876,6 +875,8 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) E[j] += H[n][j];
             }
+            if (hi_max >= 0x7ff00000u)   // a negative, -0, inf or NaN input: the exact select, sample by sample
+                k1_entropy_exact_samples<T, VEC>(reinterpret_cast<const T*>(vol) + v0, N, C, prm.sn, prm.sc, E);
         }
         if (M::kFlagged) {
 #pragma unroll
