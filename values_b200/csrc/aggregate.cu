@@ -1219,7 +1219,7 @@ static size_t fused_smem_bytes(int ty, int tx, const int64_t* patch) {
 
 // strip filter shapes: <K output rows per strip, consumer warps, lanes per staged row>
 using StripWide = StripTile<8, 4, 32>;     // 128-wide staged rows: 32 output rows x 119 outputs per CTA
-using StripNarrow = StripTile<8, 4, 16>;   // maps up to 64 wide: 64 output rows x 55 outputs per CTA
+using StripNarrow = StripTile<8, 4, 16, 2, 3>;   // maps up to 64 wide: 64 output rows x 55 outputs per CTA, three CTAs per SM
 
 static int check_patch_shape(const int64_t* shape, const int64_t* patch) {
     for (int d = 0; d < 3; ++d) {

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 3) stitch_vec_kernel(const StitchPar
 constexpr int kBX = 8, kBY = 16, kBZ = 32;             // output box of a CTA
 constexpr int kBoxVox = kBX * kBY * kBZ;               // 4096 voxels = 1024 groups of 4 = 4 groups per thread
 constexpr int kGroups = kBoxVox / 4 / kThreads;
-constexpr int kBoxList = 256;                           // overlapping patches kept per chunk (4 KB: two CTAs per SM)
+constexpr int kBoxList = 512;                           // overlapping patches kept per round (8 KB: two CTAs per SM)
 
 template <typename TP> struct StitchRing {
     static constexpr int kBytes = kBoxVox * (int)sizeof(TP);          // one window
@@ -398,6 +398,8 @@ template <> __device__ __forceinline__ void lds_group<double>(uint32_t addr, dou
     Raw4<double>::widen(r, o);
 }
 
+constexpr int kXSteps = 4;                              // boxes a CTA walks along x (one overlap list, one ring)
+
 template <typename TP, typename TO, bool WEIGHTED>
 __global__ void __launch_bounds__(kThreads + 32, 2)
 stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams prm, int rows_per_sample) {
@@ -406,14 +408,15 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
     __shared__ __align__(8) uint64_t full_bar[SR::kStages];
     __shared__ __align__(8) uint64_t empty_bar[SR::kStages];
     __shared__ int4 s_list[kBoxList];           // {cx, cy, cz, patch index} of the overlapping patches
+    __shared__ unsigned char s_flag[kBoxList];  // bit 0: fetched by the copy engine (aligned z origin), bit 1: covers the box in y and z
     __shared__ int s_warp_cnt[kThreads / 32];
     __shared__ int s_total;
 
     int tile = blockIdx.x;
     const int tz = tile % prm.tiles_z; tile /= prm.tiles_z;
     const int ty = tile % prm.tiles_y; tile /= prm.tiles_y;
-    const int x_lo = tile * kBX, y_lo = ty * kBY, z_lo = tz * kBZ;
-    const int x_hi = (int)min((int64_t)x_lo + kBX, prm.X);
+    const int col_lo = tile * (kBX * kXSteps), y_lo = ty * kBY, z_lo = tz * kBZ;
+    const int col_hi = (int)min((int64_t)col_lo + kBX * kXSteps, prm.X);
     const int64_t n = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp == kThreads / 32;
@@ -427,29 +430,34 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
         for (int s = 0; s < SR::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, kThreads / 32 * kArriveLanes); }
         mbar_fence_init();
     }
-    // this thread's voxel groups: group g = tid + kThreads * i -> (x, y, z) inside the box
-    int gx[kGroups], gy[kGroups], gz[kGroups];
-    bool gin[kGroups];
+    // this thread's voxel groups: group g = tid + kThreads * i -> (dx, y, z) inside a box
+    int gdx[kGroups], gy[kGroups], gz[kGroups];
+    bool gyz[kGroups];
 #pragma unroll
     for (int i = 0; i < kGroups; ++i) {
         const int g = (tid & (kThreads - 1)) + kThreads * i, row = g / (kBZ / 4);
-        gx[i] = x_lo + row / kBY; gy[i] = y_lo + row % kBY; gz[i] = z_lo + (g % (kBZ / 4)) * 4;
-        gin[i] = !producer && gx[i] < prm.X && gy[i] < prm.Y && gz[i] < prm.Z;   // Z % 4 == 0: whole groups
+        gdx[i] = row / kBY; gy[i] = y_lo + row % kBY; gz[i] = z_lo + (g % (kBZ / 4)) * 4;
+        gyz[i] = !producer && gy[i] < prm.Y && gz[i] < prm.Z;                    // Z % 4 == 0: whole groups
     }
+    const uint32_t lds_off = (uint32_t)(tid & (kThreads - 1)) * 4u * (uint32_t)sizeof(TP);
     unsigned int it = 0;        // windows that went through the ring so far (producer and consumers count alike)
-    for (int64_t base = 0; base < prm.n_sel; base += kBoxList) {
-        // ---- ordered compaction of the patches overlapping this CTA's box (chunk of kBoxList)
-        const int64_t chunk = min((int64_t)kBoxList, prm.n_sel - base);
+    // Rounds: the candidate list is scanned in order until kBoxList overlapping patches are found (one
+    // round in every practical case: a box is overlapped by a few dozen patches at most); a further
+    // round continues from the sums of the previous one.
+    int64_t cursor = 0;
+    for (bool first = true; first || cursor < prm.n_sel; first = false) {
+        // ---- ordered compaction of the patches overlapping this CTA's column of boxes
         if (tid == 0) s_total = 0;
         __syncthreads();
-        for (int64_t off = 0; off < chunk; off += kThreads) {
-            const int64_t i = base + off + tid;
+        while (cursor < prm.n_sel && s_total + kThreads <= kBoxList) {
+            const int64_t i = cursor + tid;
+            cursor += kThreads;
             bool hit = false;
             int4 e = make_int4(0, 0, 0, 0);
-            if (!producer && off + tid < chunk) {
+            if (!producer && i < prm.n_sel) {
                 e.x = prm.crop_lo[3 * i]; e.y = prm.crop_lo[3 * i + 1]; e.z = prm.crop_lo[3 * i + 2];
                 e.w = prm.patch_index ? prm.patch_index[i] : (int)i;
-                hit = x_lo < e.x + prm.p0 && x_hi > e.x && y_lo < e.y + prm.p1 && y_lo + kBY > e.y &&
+                hit = col_lo < e.x + prm.p0 && col_hi > e.x && y_lo < e.y + prm.p1 && y_lo + kBY > e.y &&
                       z_lo < e.z + prm.p2 && z_lo + kBZ > e.z;
             }
             const unsigned bal = __ballot_sync(0xffffffffu, hit);
@@ -457,7 +465,13 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
             __syncthreads();
             int before = s_total;
             for (int w = 0; w < warp && w < kThreads / 32; ++w) before += s_warp_cnt[w];
-            if (hit) s_list[before + __popc(bal & ((1u << lane) - 1u))] = e;
+            if (hit) {
+                const int slot = before + __popc(bal & ((1u << lane) - 1u));
+                s_list[slot] = e;
+                s_flag[slot] = (unsigned char)((e.z % SR::kAlign == 0 ? 1 : 0) |
+                                               ((e.y <= y_lo && e.y + prm.p1 >= y_lo + kBY && e.z <= z_lo &&
+                                                 e.z + prm.p2 >= z_lo + kBZ) ? 2 : 0));
+            }
             __syncthreads();
             if (tid == 0) {
                 int t = s_total;
@@ -467,24 +481,30 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
             __syncthreads();
         }
         const int total = s_total;
-        const bool readback = base > 0 || prm.accumulate;
-        if (producer) {
-            // ---- one lane streams the windows: classes outer, listed patches inner
-            if (lane == 0) {
-                for (int c = 0; c < (int)prm.C; ++c) {
-                    for (int k = 0; k < total; ++k) {
-                        const int4 e = s_list[k];
-                        if (e.z % SR::kAlign) continue;                     // read directly by the consumers
-                        const int stage = it % SR::kStages;
-                        if (it >= SR::kStages) mbar_wait(empty_bar + stage, ((it / SR::kStages) & 1) ^ 1u);
-                        mbar_expect_tx(full_bar + stage, SR::kBytes);
-                        tma_load_5d_addr(ring + stage * SR::kBytes, &tmap, z_lo - e.z, y_lo - e.y, x_lo - e.x, c,
-                                         (int)(n * rows_per_sample + e.w), full_bar + stage);
-                        ++it;
+        const bool readback = !first || prm.accumulate;
+        for (int x_lo = col_lo; x_lo < col_hi; x_lo += kBX) {
+            const int x_hi = min(x_lo + kBX, col_hi);
+            if (producer) {
+                // ---- one lane streams the windows of this box: classes outer, listed patches inner
+                if (lane == 0) {
+                    for (int c = 0; c < (int)prm.C; ++c) {
+                        for (int k = 0; k < total; ++k) {
+                            const int4 e = s_list[k];
+                            if (!(s_flag[k] & 1) || !(x_lo < e.x + prm.p0 && x_hi > e.x)) continue;
+                            const int stage = it % SR::kStages;
+                            if (it >= SR::kStages) mbar_wait(empty_bar + stage, ((it / SR::kStages) & 1) ^ 1u);
+                            mbar_expect_tx(full_bar + stage, SR::kBytes);
+                            tma_load_5d_addr(ring + stage * SR::kBytes, &tmap, z_lo - e.z, y_lo - e.y, x_lo - e.x, c,
+                                             (int)(n * rows_per_sample + e.w), full_bar + stage);
+                            ++it;
+                        }
                     }
                 }
+                continue;
             }
-        } else {
+            bool gin[kGroups];
+#pragma unroll
+            for (int i = 0; i < kGroups; ++i) gin[i] = gyz[i] && x_lo + gdx[i] < prm.X;
             // pass c < C: class c; pass C (sample 0 only): the count -- same walk, no data
             const int passes = (int)prm.C + ((n == 0 && prm.out_count) ? 1 : 0);
             for (int c = 0; c < passes; ++c) {
@@ -492,7 +512,7 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
                 double acc[kGroups][4];
 #pragma unroll
                 for (int i = 0; i < kGroups; ++i) {
-                    const int64_t vox = ((int64_t)gx[i] * prm.Y + gy[i]) * prm.Z + gz[i];
+                    const int64_t vox = ((int64_t)(x_lo + gdx[i]) * prm.Y + gy[i]) * prm.Z + gz[i];
                     if (readback && gin[i]) {
                         if (count_pass) read4(prm.out_count + vox, acc[i]);
                         else read4(out + c * vol + vox, acc[i]);
@@ -502,41 +522,64 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
                 }
                 for (int k = 0; k < total; ++k) {
                     const int4 e = s_list[k];
-                    const bool aligned = e.z % SR::kAlign == 0;
+                    if (!(x_lo < e.x + prm.p0 && x_hi > e.x)) continue;             // not over this box
+                    const int flag = s_flag[k];
+                    const bool aligned = flag & 1;
+                    const bool covers = (flag & 2) && e.x <= x_lo && e.x + prm.p0 >= x_lo + kBX;   // the whole box
                     int stage = 0;
                     if (aligned && !count_pass) {
                         stage = it % SR::kStages;
                         mbar_wait(full_bar + stage, (it / SR::kStages) & 1);
                         ++it;
                     }
+                    const uint32_t src = ring + stage * SR::kBytes + lds_off;
+                    if (covers && aligned && !WEIGHTED) {
+                        // the usual case (patch grids aligned to the boxes): every voxel of the box is inside
+                        if (count_pass) {
 #pragma unroll
-                    for (int i = 0; i < kGroups; ++i) {
-                        const int lx = gx[i] - e.x, ly = gy[i] - e.y, lz = gz[i] - e.z;
-                        const bool in_xy = gin[i] && lx >= 0 && lx < prm.p0 && ly >= 0 && ly < prm.p1;
-                        const int64_t local = ((int64_t)lx * prm.p1 + ly) * prm.p2 + lz;
-                        if (aligned) {
-                            const bool in = in_xy && lz >= 0 && lz < prm.p2;         // whole group in or out
-                            double v[4] = {1.0, 1.0, 1.0, 1.0};
-                            if (!count_pass) lds_group<TP>(ring + stage * SR::kBytes + ((tid & (kThreads - 1)) + kThreads * i) * 4 * (int)sizeof(TP), v);
-                            if (in) {
-                                if (WEIGHTED) {
-                                    double w[4];
-                                    Raw4<double>::widen(Raw4<double>::load(prm.weight + local), w);
+                            for (int i = 0; i < kGroups; ++i) {
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q)
-                                        acc[i][q] = count_pass ? acc[i][q] + w[q] : __dadd_rn(acc[i][q], __dmul_rn(w[q], v[q]));
-                                } else {
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) acc[i][q] += v[q];
-                                }
+                                for (int q = 0; q < 4; ++q) acc[i][q] += 1.0;
                             }
-                        } else if (in_xy) {
+                        } else {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (lz + q < 0 || lz + q >= prm.p2) continue;
-                                const double w = WEIGHTED ? __ldg(prm.weight + local + q) : 1.0;
-                                const double v = count_pass ? 1.0 : (double)In<TP>::load_one(pin + (int64_t)e.w * prm.stride_p + c * pvol + local + q);
-                                acc[i][q] = !WEIGHTED ? acc[i][q] + v : count_pass ? acc[i][q] + w : __dadd_rn(acc[i][q], __dmul_rn(w, v));
+                            for (int i = 0; i < kGroups; ++i) {
+                                double v[4];
+                                lds_group<TP>(src + kThreads * i * 4 * (int)sizeof(TP), v);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) acc[i][q] += v[q];
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kGroups; ++i) {
+                            const int lx = x_lo + gdx[i] - e.x, ly = gy[i] - e.y, lz = gz[i] - e.z;
+                            const bool in_xy = gin[i] && lx >= 0 && lx < prm.p0 && ly >= 0 && ly < prm.p1;
+                            const int64_t local = ((int64_t)lx * prm.p1 + ly) * prm.p2 + lz;
+                            if (aligned) {
+                                const bool in = in_xy && lz >= 0 && lz < prm.p2;         // whole group in or out
+                                double v[4] = {1.0, 1.0, 1.0, 1.0};
+                                if (!count_pass) lds_group<TP>(src + kThreads * i * 4 * (int)sizeof(TP), v);
+                                if (in) {
+                                    if (WEIGHTED) {
+                                        double w[4];
+                                        Raw4<double>::widen(Raw4<double>::load(prm.weight + local), w);
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q)
+                                            acc[i][q] = count_pass ? acc[i][q] + w[q] : __dadd_rn(acc[i][q], __dmul_rn(w[q], v[q]));
+                                    } else {
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) acc[i][q] += v[q];
+                                    }
+                                }
+                            } else if (in_xy) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    if (lz + q < 0 || lz + q >= prm.p2) continue;
+                                    const double w = WEIGHTED ? __ldg(prm.weight + local + q) : 1.0;
+                                    const double v = count_pass ? 1.0 : (double)In<TP>::load_one(pin + (int64_t)e.w * prm.stride_p + c * pvol + local + q);
+                                    acc[i][q] = !WEIGHTED ? acc[i][q] + v : count_pass ? acc[i][q] + w : __dadd_rn(acc[i][q], __dmul_rn(w, v));
+                                }
                             }
                         }
                     }
@@ -551,7 +594,7 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
 #pragma unroll
                 for (int i = 0; i < kGroups; ++i) {
                     if (!gin[i]) continue;
-                    const int64_t vox = ((int64_t)gx[i] * prm.Y + gy[i]) * prm.Z + gz[i];
+                    const int64_t vox = ((int64_t)(x_lo + gdx[i]) * prm.Y + gy[i]) * prm.Z + gz[i];
                     if (count_pass) store4<double>(prm.out_count + vox, acc[i]);
                     else store4<TO>(out + c * vol + vox, acc[i]);
                 }
@@ -591,7 +634,7 @@ static int launch_stitch_box(StitchParams prm, cudaStream_t st) {
     if (rc) return rc;
     prm.tiles_z = (int)ceil_div(prm.Z, kBZ);
     prm.tiles_y = (int)ceil_div(prm.Y, kBY);
-    const int64_t tiles = (int64_t)prm.tiles_z * prm.tiles_y * ceil_div(prm.X, kBX);
+    const int64_t tiles = (int64_t)prm.tiles_z * prm.tiles_y * ceil_div(prm.X, kBX * kXSteps);
     if (tiles > 0x7fffffffLL || prm.N > 65535) return set_error(VALUES_ERR_UNSUPPORTED, "stitch: volume too large");
     const int rows_per_sample = prm.N > 1 ? (int)(prm.stride_n / prm.stride_p) : 0;
     const dim3 grid((unsigned)tiles, (unsigned)prm.N);
