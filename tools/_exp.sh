@@ -1,7 +1,4 @@
-python -m pytest tests/test_gpu_parity.py tests/test_configs.py -q -m gpu -x -k "stitch or cfg3 or c3" 2>&1 | tail -3
-python tools/k34_bench.py --reps 5 2>&1 | head -9
-python tools/k2_bench.py --shape 64,64,64 --maps 768,1023 --paths 0 2>&1 | tail -2
-for w in cfg3 cfg2; do python bench.py --workload $w --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import json,sys
-j=json.loads(sys.stdin.read()); r=j['roofline']; s=j['sustained']
-print(j['config']['workload'][:30], 'value %.4g ms %.3f frac %.3f pipe %.3f | sustained %.4g frac %.3f pipe %.3f' % (j['value'], j['ms_per_step'], r['frac'], r['pipeline_frac'], s['value'], s['frac'], s['pipeline_frac']))"; done
+python tools/k2_bench.py --shape 64,64,64 --maps 768 --paths 0,5 2>&1 | tail -2
+python tools/k2_probe.py cfg2 2>&1 | tail -6 | cut -c1-200
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:k1_tma|box_|stitch|normalize|map_reduce" -c 60 --csv --log-file gpurun_out/r02o_launches_cfg2.csv python bench.py --workload cfg2 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-sustained > /dev/null 2>&1
+python bench.py --workload cfg2 --no-cpu-baseline --no-e2e 2>/dev/null | cut -c1-300

@@ -923,9 +923,15 @@ __device__ __forceinline__ float4 sub4(float4 a, float4 b) {
     const float2 hi = sub2(make_float2(a.z, a.w), make_float2(b.z, b.w));
     return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
-__device__ __forceinline__ unsigned int or4(unsigned int acc, float4 v) {
-    acc |= __float_as_uint(v.x) | __float_as_uint(v.y);
-    return acc | __float_as_uint(v.z) | __float_as_uint(v.w);
+// running max |v| with NaN propagation: one FMNMX.NAN.XORSIGN per element (the sign of the result is
+// meaningless; the caller takes the magnitude).  An OR of the magnitude bits would be cheaper but is not a
+// bound: the exponent fields of 1.x and 2.x OR to all ones.
+__device__ __forceinline__ float absmax4(float acc, float4 v) {
+    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(acc) : "f"(v.x));
+    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(acc) : "f"(v.y));
+    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(acc) : "f"(v.z));
+    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(acc) : "f"(v.w));
+    return acc;
 }
 __device__ __forceinline__ float4 lds_f4(uint32_t a) {
     float4 q;
@@ -988,7 +994,7 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
         mbar_fence_init();
     }
     __syncthreads();
-    unsigned int abits = 0;
+    float amax = 0.f;
     if (warp == NW) {
         // ---- producer: one lane streams the plane tiles through the ring.  An entering plane is read
         // again as the leaving plane p0 steps later: it is marked evict-last in L2 when it enters and
@@ -1021,8 +1027,9 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
         const int r0 = strip * K;
         const int xo = 4 * c4, xlim = min(ST::XS, (int)prm.O2 - x0);        // valid outputs: xo + j < xlim
         const bool cv0 = xo < xlim, cv1 = xo + 1 < xlim, cv2 = xo + 2 < xlim, cv3 = xo + 3 < xlim;
-        // the tail rows of a strip are the own rows of the next one: only the last strip of the CTA
-        // (and every strip's own K rows) feed the bound on max |input|
+        // every strip's own K rows feed the bound on max |input| (it is reduced over the CTAs of a map, and
+        // the tail rows of a strip are the own rows of the next strip / CTA); only the last strip of the
+        // bottom CTA row reads tail rows that are nobody's own
         const bool or_tail = strip == NW * ST::SUBS - 1;
         const uint32_t lane_off = (uint32_t)(r0 * ST::WF + xo) * 4u;
         // entry slot of this half-warp: march tile row (r0 / 32) x tile column (lanes 16.. of a 128-wide row)
@@ -1041,7 +1048,7 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
 #pragma unroll
                 for (int r = 0; r < RW; ++r) {
                     zs[r] = lds_f4(pn + r * ST::WF * 4);
-                    if (r < K || or_tail) abits = or4(abits, zs[r]);
+                    if (r < K || or_tail) amax = absmax4(amax, zs[r]);
                 }
             } else if (zi >= p0) {
 #pragma unroll
@@ -1049,14 +1056,14 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
                     const float4 nw = lds_f4(pn + r * ST::WF * 4);
                     const float4 od = lds_f4(pn + kPlaneBytes + r * ST::WF * 4);
                     zs[r] = add4(zs[r], sub4(nw, od));
-                    if (r < K || or_tail) abits = or4(abits, nw);
+                    if (r < K || or_tail) amax = absmax4(amax, nw);
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < RW; ++r) {
                     const float4 nw = lds_f4(pn + r * ST::WF * 4);
                     zs[r] = add4(zs[r], nw);
-                    if (r < K || or_tail) abits = or4(abits, nw);
+                    if (r < K || or_tail) amax = absmax4(amax, nw);
                 }
             }
             // the stage is free once every lane's loads have landed in registers: the arrive is issued
@@ -1131,7 +1138,7 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
             for (int f = written; f < prm.zsub; ++f) prm.tile_max[m * prm.nent + tile * prm.zsub + f] = ninf;
         }
     }
-    box_pass_finish<0, NT, true>(prm, m, 0.0, ~0ull, red, s_flag, s_count, __uint_as_float(abits & 0x7fffffffu),
+    box_pass_finish<0, NT, true>(prm, m, 0.0, ~0ull, red, s_flag, s_count, fabsf(amax),
                                  ctas_per_map);
 }
 
@@ -1347,7 +1354,7 @@ static int run_patch_fused_pc(FusedParams prm, const FusedPlan& pl, int64_t M, c
 //                                                                   ey <= pc ez + [d pc + ys (pc + 2)] u Z
 //   x-stage, tree-shaped start over pc (depth d) + at most xs slides: ex <= pc ey + [d pc + xs (pc + 2)] u pc Z
 // doubled to cover the second-order terms and the exact pass's own fp64 rounding.  (The kernel's a is
-// the OR of the inputs' magnitude bits, up to twice the true maximum: conservative.)
+// the running maximum of |input| over the rows the strips own, NaN-propagating.)
 static double filter_err_coef(int zc, int p0, int pc, int s1, int s2) {
     const double u = 5.9604644775390625e-8;
     const double K = zc + p0 - 1, d = tree_depth(pc);
