@@ -143,6 +143,25 @@ def test_k1_kernels_agree(vb, n, c, spatial, dtype):
             assert torch.equal(a, b)
 
 
+def test_fp64_class_mean_is_true_division(vb):
+    """The fp64 kernels form the class mean as S * RN(1/N) refined by two fmas instead of a division: the
+    arg-max of the mean and PE must be those of true division for every magnitude (raw overlap sums can be
+    large), including the exponent ranges that fall back to a real division."""
+    g = torch.Generator().manual_seed(5)
+    for n in (5, 8, 10, 16, 3, 7):
+        for scale in (1.0, 1e-150, 1e150, 1e-290, 3e300 / n):
+            x = torch.rand(n, 3, 2048, generator=g, dtype=torch.float64) * scale
+            res = vb.uncertainty_fused(x.cuda().unsqueeze(0), mean_argmax=True)
+            mean = x.sum(dim=0) / n if False else torch.stack([sum(x[i, c] for i in range(n)) for c in range(3)]) / n
+            assert torch.equal(res.mean_argmax[0].cpu().to(torch.int64), mean.argmax(dim=0)), (n, scale)
+            t = mean * torch.log(mean)
+            pe = torch.zeros(2048, dtype=torch.float32)
+            for c in range(3):                         # fp32 accumulator, fp64 add, NaN terms skipped
+                ok = ~torch.isnan(t[c])
+                pe = torch.where(ok, (pe.double() + t[c]).float(), pe)
+            np.testing.assert_allclose(res.pred_entropy[0].cpu().numpy(), (-pe).numpy(), rtol=2e-7, atol=0)
+
+
 def test_c2_low_mi_regime(vb, vo):
     x = softmax_stack(5, 5, 2, (48, 48, 48), torch.float32, shared=True)
     ref = vo.calculate_uncertainty(x)
