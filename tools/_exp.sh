@@ -1,4 +1,2 @@
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_counts.py tests/test_configs.py -q -m gpu -x -k "c2 or k1 or masks or full_size or cfg or class_mean" 2>&1 | tail -3
-python tools/k1_bench.py --shape cfg3n8 --variants 0 2>&1 | tail -1
-python tools/k1_bench.py --shape cfg1 --variants 0 2>&1 | tail -1
-python tools/k1_bench.py --shape cfg5f64 --variants 0 2>&1 | tail -1
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:box_" --csv --log-file gpurun_out/r02r_launch_128.csv python tools/k2_case.py 128,128,128 96 >/dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:box_" --csv --log-file gpurun_out/r02r_launch_64.csv python tools/k2_case.py 64,64,64 768 >/dev/null 2>&1

@@ -414,10 +414,14 @@ __device__ __forceinline__ void box_pass_finish(const FusedParams& prm, int64_t 
         }
         __syncthreads();
         if (tid == 0) {
-            lst[0] = s_count > kMaxActive ? -1 : s_count;
-            prm.gmax[m] = g;
-            prm.out.put_score(m, g);
-            prm.best[m] = ~0ull;
+            if (atomicOr(prm.tickets + 4 * m + 2, 0u) & 0x80000000u) {   // score and corner already written by the
+                lst[0] = 0;                                              // CTA that walked the single candidate
+            } else {
+                lst[0] = s_count > kMaxActive ? -1 : s_count;
+                prm.gmax[m] = g;
+                prm.out.put_score(m, g);
+                prm.best[m] = ~0ull;
+            }
         }
     } else {
 #pragma unroll
@@ -659,16 +663,24 @@ constexpr int tree_depth(int n) { return n <= 1 ? 0 : 1 + tree_depth(n - n / 2);
 
 // PASS 1 after the fp32 strip filter (prm.use_list): only the (tile, z sub-chunk) entries the filter
 // listed are walked; results are bit-identical to running PASS 1 over everything.
-template <typename T, typename ACC, int TY, int TX, int PC, int PASS, int MINB>
+// FUSE (PASS 1 behind the filter): a map whose filter list holds ONE entry needs no second walk -- the
+// CTA that walks the entry keeps its window sums (at most kFusePlanes planes of TY x TX doubles) in
+// shared memory, takes their maximum and the first C-order index np.isclose to it, writes score and
+// corner and marks the map done (bit 31 of its pass-2 ticket): pass 2 then finds an empty list.
+constexpr int kFusePlanes = 2;
+constexpr unsigned int kFusedDone = 0x80000000u;
+template <typename T, typename ACC, int TY, int TX, int PC, int PASS, int MINB, bool FUSE = false>
 __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const FusedParams prm) {
     using MT = MarchTile<TY, TX, PC>;
     constexpr int NT = kFusedThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[NT / 32];
+    __shared__ unsigned long long red_idx[NT / 32];
     __shared__ int s_flag;
     __shared__ int s_count;
     ACC* A = reinterpret_cast<ACC*>(smem_raw);                // [2][R][pitchA] z-window sums
     ACC* Bs = A + 2 * MT::R * MT::pitchA;                     // [2][R][pitchB] z-x sums
+    double* saved = reinterpret_cast<double*>(Bs + 2 * MT::R * MT::pitchB);   // FUSE: [kFusePlanes][TY][TX]
     const int p0 = prm.p0;
     const int64_t m = blockIdx.y;
     const int tid = threadIdx.x;
@@ -698,6 +710,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
         if (list[0] >= 0) { n_work = list[0]; listed = true; }
         else n_work = (int)prm.ntiles;
     }
+    const bool fuse = FUSE && PASS == 1 && listed && n_work == 1 && prm.zc_fine <= kFusePlanes;
     const int zc_fine = listed ? prm.zc_fine : prm.zc;
     // z-slide ownership: column cx of the input tile, rows g, g + G, ...
     const int cx = min(tid % MT::CW, MT::W - 1), g = min(tid / MT::CW, MT::G - 1);
@@ -812,6 +825,11 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
                     for (int k = 0; k < MT::RUN; ++k) o[k] = box_mean_div(o[k], prm.denom);
                 }
                 if constexpr (PASS <= 1) {
+                    if (FUSE && fuse) {     // window sums of this plane, -inf where the window is outside the map
+#pragma unroll
+                        for (int k = 0; k < MT::RUN; ++k)
+                            saved[((t - 2) * TY + oy0 + k) * TX + ox] = ((valid >> k) & 1u) ? (double)o[k] : ninf;
+                    }
                     if (all_valid) {
 #pragma unroll
                         for (int k = 0; k < MT::RUN; ++k) { tmax = acc_max(tmax, o[k]); saw_nan |= o[k] != o[k]; }
@@ -853,6 +871,42 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
         if (PASS <= 1 && !listed && tid == 0) {   // sub-chunks past the end of a short last z-chunk hold nothing
             const int written = (int)((zo1 - zo0 + prm.zc_fine - 1) / prm.zc_fine);
             for (int f = written; f < zsub; ++f) prm.tile_max[m * prm.nent + (int64_t)tile * zsub + f] = ninf;
+        }
+        if (FUSE && fuse) {
+            // the only candidate of this map was just walked: maximum (NaN propagates, as np.max), then
+            // the first C-order window np.isclose to it, from the sums kept in shared memory
+            const int nsaved = (int)(zo1 - zo0) * TY * TX;
+            double g = ninf;
+            for (int i = tid; i < nsaved; i += NT) g = nanmax(g, saved[i]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) g = nanmax(g, __shfl_xor_sync(0xffffffffu, g, off));
+            if ((tid & 31) == 0) red[tid >> 5] = g;
+            __syncthreads();
+            g = red[0];
+            for (int w = 1; w < NT / 32; ++w) g = nanmax(g, red[w]);
+            unsigned long long best = ~0ull;
+            for (int i = tid; i < nsaved; i += NT) {
+                if (np_isclose(saved[i], g, prm.rtol, prm.atol)) {
+                    const int pz = i / (TY * TX), py = (i / TX) % TY, px = i % TX;
+                    const unsigned long long lin =
+                        (unsigned long long)(((zo0 + pz) * prm.O1 + (y0 + py)) * prm.O2 + (x0 + px));
+                    best = lin < best ? lin : best;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
+                best = other < best ? other : best;
+            }
+            if ((tid & 31) == 0) red_idx[tid >> 5] = best;
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < NT / 32; ++w) best = red_idx[w] < best ? red_idx[w] : best;
+                prm.gmax[m] = g;
+                prm.out.put_score(m, g);
+                prm.out.put_corner(m, best, prm.O1, prm.O2);
+                atomicExch(prm.tickets + 4 * m + 2, kFusedDone);     // ordered before this CTA's pass-1 ticket
+            }
         }
     }
     box_pass_finish<PASS, kFusedThreads, true>(prm, m, 0.0, tbest, red, s_flag, s_count);
@@ -1402,13 +1456,19 @@ static int launch_strip_filter(const FusedParams& prm, const FusedPlan& pl, int6
 template <typename T>
 static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cudaStream_t st) {
     using MT = MarchTile<32, 64, 10>;
-    auto k1 = box_march_kernel<T, double, 32, 64, 10, 1, 2>;
+    const bool filter = pl.strip_lw != 0;
+    // behind the filter pass 1 walks a handful of entries per map: the instantiation that can finish a
+    // single-candidate map on its own (window sums kept in 32 KB more shared memory, one CTA per SM)
+    // (it runs one CTA per SM: with many maps per call -- measured 768 maps of 64^3 -- the two-launch form
+    // with two CTAs per SM walks the entries faster than the fused form saves)
+    const bool fuse = filter && M <= 2 * 148;
+    auto k1 = fuse ? box_march_kernel<T, double, 32, 64, 10, 1, 1, true> : box_march_kernel<T, double, 32, 64, 10, 1, 2>;
     auto k2 = box_march_kernel<T, double, 32, 64, 10, 2, 2>;
     const size_t smem = MT::smem_bytes<double>();
-    if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+    const size_t smem1 = smem + (fuse ? (size_t)kFusePlanes * 32 * 64 * sizeof(double) : 0);
+    if (cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess ||
         cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute(%zu) failed", smem);
-    const bool filter = pl.strip_lw != 0;
+        return set_error(VALUES_ERR_CUDA, "patch_max: cudaFuncSetAttribute(%zu) failed", smem1);
     prm.use_list = filter ? 1 : 0;
     prm.err_coef = filter_err_coef(prm.zc, prm.p0, 10, StripWide::K - 1, 3);   // == values_patch_filter_err_coef
     if (cudaMemsetAsync(prm.tickets, 0, (size_t)M * 4 * sizeof(unsigned int), st) != cudaSuccess)
@@ -1436,7 +1496,7 @@ static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
         const unsigned g2 = (unsigned)std::min<int64_t>(prm.nent, mc >= 16 ? 8 : 32);
         // pass 1: every tile, or (after the filter) the few listed sub-chunks
         const unsigned g1 = filter ? (unsigned)std::min<int64_t>(pl.ntiles, g2) : (unsigned)pl.ntiles;
-        k1<<<dim3(g1, (unsigned)mc), kFusedThreads, smem, st>>>(q);
+        k1<<<dim3(g1, (unsigned)mc), kFusedThreads, smem1, st>>>(q);
         if ((rc = check_launch("box_march_kernel<1>"))) return rc;
         k2<<<dim3(g2, (unsigned)mc), kFusedThreads, smem, st>>>(q);
         if ((rc = check_launch("box_march_kernel<2>"))) return rc;
