@@ -284,7 +284,7 @@ class CpuReference:
 
         cores = os.cpu_count() or 1
         unit_bytes = wl["N"] * wl["C"] * int(np.prod(cpu_unit_shape(wl))) * 8
-        self.workers = max(1, min(8, cores // 4, int(48e9 // (12 * unit_bytes)) or 1))   # ~12 temporaries per stack
+        self.workers = max(1, min(8, cores // 4, int(128e9 // (12 * unit_bytes)) or 1))   # ~12 temporaries per stack, 128 GB of host memory at most
         self.threads = max(1, cores // self.workers)
         self.cores = self.workers * self.threads
         self.wl = wl

@@ -192,6 +192,17 @@ int values_radix_histogram(const void* data, int dtype, int64_t n, uint64_t pref
                            void* stream);
 int values_min_key_above(const void* data, int dtype, int64_t n, uint64_t key,
                          unsigned long long* out, void* stream);
+/* The same walk without a host round trip per digit: `state` is a device array of 5 counters
+ * {prefix, prefix_bits, rank (0-based, among the elements that match the prefix), count in the chosen
+ * bucket, count in the last bucket of the FIRST digit (fp32: the NaN count)}.
+ * values_radix_histogram_dev = values_radix_histogram with prefix / prefix_bits read from state;
+ * values_radix_select picks the bucket of `hist` that holds the rank, updates state (prefix_bits becomes
+ * all ones if the rank is out of range) and zeroes hist for the next digit.  After the last digit
+ * state[0] is the key of the wanted order statistic, rank_initial - state[2] the number of smaller
+ * elements and state[3] the number of elements equal to it. */
+int values_radix_histogram_dev(const void* data, int dtype, int64_t n, const unsigned long long* state,
+                               int digit_bits, unsigned long long* hist, void* stream);
+int values_radix_select(unsigned long long* hist, int digit_bits, unsigned long long* state, void* stream);
 
 /* Replaces the reductions of compute_ncc(gt_unc_map, pred_unc_map) evaluation/metrics/ncc.py:9-25.
  *   a [M, V] (stride_a, 1), b [M, V] (stride_b, 1), F32 or F64 each; shift: device double [M, 2]

@@ -56,6 +56,8 @@ def _load() -> C.CDLL:
         "values_count_nonzero": (C.c_int, [vp, C.c_int, i64, vp, vp]),
         "values_radix_histogram": (C.c_int, [vp, C.c_int, i64, C.c_uint64, C.c_int, C.c_int, vp, vp]),
         "values_min_key_above": (C.c_int, [vp, C.c_int, i64, C.c_uint64, vp, vp]),
+        "values_radix_histogram_dev": (C.c_int, [vp, C.c_int, i64, vp, C.c_int, vp, vp]),
+        "values_radix_select": (C.c_int, [vp, C.c_int, vp, vp]),
         "values_pair_moments_workspace_bytes": (sz, [i64, i64]),
         "values_pair_moments": (C.c_int, [vp, C.c_int, i64, vp, C.c_int, i64, i64, i64, vp, vp, vp, sz, vp]),
         "values_calib_bins_workspace_bytes": (sz, [i64]),
@@ -82,7 +84,8 @@ EXPORTED = [
     "values_patch_max_workspace_bytes", "values_patch_max", "values_stitch_accumulate",
     "values_stitch_accumulate_weighted",
     "values_normalize_maps", "values_count_nonzero", "values_radix_histogram",
-    "values_min_key_above", "values_pair_moments_workspace_bytes", "values_pair_moments",
+    "values_min_key_above", "values_radix_histogram_dev", "values_radix_select",
+    "values_pair_moments_workspace_bytes", "values_pair_moments",
     "values_calib_bins_workspace_bytes", "values_calib_bins", "values_calib_bins_fused",
     "values_confusion_counts", "values_reverse_axes", "values_patch_filter_err_coef",
 ]

@@ -102,27 +102,22 @@ def order_statistic(maps: Sequence[torch.Tensor], k: int, distributed: bool = Fa
     dev = maps[0].device
     code = _lib.dtype_code(dt)
     hist = torch.zeros(1 << 11, dtype=torch.int64, device=dev)
-    prefix, prefix_bits, below = 0, 0, 0
-    count_eq = 0
-    for db in _DIGITS[bits]:
-        hist.zero_()
-        with torch.cuda.device(dev):
+    # the digit walk stays on the device: {prefix, prefix_bits, rank, count_eq, count of the top bucket of the
+    # first digit}; ONE readback at the end (with distributed=True the histogram all-reduce is on-stream too)
+    state = torch.tensor([0, 0, int(k), 0, 0], dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        for db in _DIGITS[bits]:
             for m in maps:
-                rc = _lib.lib.values_radix_histogram(m.data_ptr(), code, m.numel(), prefix, prefix_bits,
-                                                     db, hist.data_ptr(), _lib.stream_ptr(dev))
-                _lib.check(rc)
-        if distributed:
-            _all_reduce(hist, dist.ReduceOp.SUM, group)
-        h = hist[: 1 << db].cpu().numpy()
-        cum = np.cumsum(h)
-        d = int(np.searchsorted(cum, k - below, side="right"))
-        if d >= (1 << db):
-            raise IndexError(f"order_statistic: rank {k} out of range")
-        below += int(cum[d - 1]) if d > 0 else 0
-        count_eq = int(h[d])
-        prefix = (prefix << db) | d
-        prefix_bits += db
-    return prefix, below, count_eq, bits
+                _lib.check(_lib.lib.values_radix_histogram_dev(m.data_ptr(), code, m.numel(), state.data_ptr(), db,
+                                                               hist.data_ptr(), _lib.stream_ptr(dev)))
+            if distributed:
+                _all_reduce(hist, dist.ReduceOp.SUM, group)
+            _lib.check(_lib.lib.values_radix_select(hist.data_ptr(), db, state.data_ptr(), _lib.stream_ptr(dev)))
+    prefix, prefix_bits, rank_left, count_eq, top0 = (int(v) for v in state.cpu().tolist())
+    if prefix_bits != bits:
+        raise IndexError(f"order_statistic: rank {k} out of range")
+    order_statistic.last_top_bucket = top0      # fp32: number of NaNs (their key is the only one in that bucket)
+    return prefix & ((1 << 64) - 1), int(k) - rank_left, count_eq, bits
 
 
 def _min_key_above(maps: Sequence[torch.Tensor], key: int, bits: int, distributed: bool, group) -> int:
@@ -203,17 +198,22 @@ def quantile(maps: Union[torch.Tensor, np.ndarray, Sequence], q: float, distribu
     nan_key = (1 << bits) - 1
     if key_lo == nan_key:
         return np_dtype(np.nan)
-    last_db = _DIGITS[bits][-1]
-    hist = torch.zeros(1 << last_db, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
-        for m in maps:
-            _lib.check(_lib.lib.values_radix_histogram(
-                m.data_ptr(), _lib.dtype_code(dt), m.numel(), nan_key >> last_db, bits - last_db,
-                last_db, hist.data_ptr(), _lib.stream_ptr(dev)))
-    if distributed:
-        _all_reduce(hist, dist.ReduceOp.SUM, group)
-    if int(hist[-1].item()) > 0:
-        return np_dtype(np.nan)
+    if bits == 32:
+        # fp32: the top bucket of the first digit (sign flipped, exponent 255, mantissa 11...) holds NaNs only
+        if order_statistic.last_top_bucket > 0:
+            return np_dtype(np.nan)
+    else:   # fp64: that bucket also holds finite values >= 2^1023; count the all-ones key itself
+        last_db = _DIGITS[bits][-1]
+        hist = torch.zeros(1 << last_db, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            for m in maps:
+                _lib.check(_lib.lib.values_radix_histogram(
+                    m.data_ptr(), _lib.dtype_code(dt), m.numel(), nan_key >> last_db, bits - last_db,
+                    last_db, hist.data_ptr(), _lib.stream_ptr(dev)))
+        if distributed:
+            _all_reduce(hist, dist.ReduceOp.SUM, group)
+        if int(hist[-1].item()) > 0:
+            return np_dtype(np.nan)
     a_lo = _key_to_value(key_lo, bits)
     if k_hi < below + eq:
         a_hi = a_lo
