@@ -487,6 +487,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    align = torch.zeros(1, device=dev)
+
     def timed(n_steps):
         """EXACTLY n_steps steps between two events, barrier + synchronize on both sides, ONE score gather
         at the end of the region (inside it), max over ranks."""
@@ -495,6 +497,8 @@ def main():
         launches0 = vb._lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as clocks:
+            if world > 1:   # ranks leave the host barrier milliseconds apart: an on-stream collective right in
+                dist.all_reduce(align)   # front of e0 starts the timed region at the same instant on every GPU
             e0.record()
             tables = []
             for _ in range(n_steps):          # only the score rows of a step are kept (its maps / arg-max are not)
@@ -506,17 +510,23 @@ def main():
             e1.record()
             sync_all()
         ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
         k_ms, k_bytes, k_n, k_sum = work.dominant()
+        per_rank = None
+        if world > 1:   # the line reports the MAX over ranks; every rank's own figures go along for diagnosis
+            mine = torch.tensor([ms, k_ms], dtype=torch.float64, device=dev)
+            allr = torch.empty((world, 2), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allr, mine)
+            allr = allr.cpu()
+            ms = float(allr[:, 0].max())
+            per_rank = {"elapsed_ms": [round(float(v), 3) for v in allr[:, 0]],
+                        "kernel_avg_ms": [round(float(v), 4) for v in allr[:, 1]]}
+            k_ms = float(allr[:, 1].max())      # the roofline fraction is the slowest rank's too
         achieved = k_bytes / (k_ms * 1e-3) / 1e9
         return {"elapsed_ms": ms, "steps": n_steps, "launches": vb._lib.launch_count() - launches0,
                 "value": float(work.units_per_step) * world * n_steps / (ms * 1e-3), "ms_per_step": ms / n_steps,
                 "achieved": achieved, "kernel_ms": k_ms, "kernel_bytes": k_bytes, "kernel_launches": k_n,
                 "kernel_share": k_sum / ms, "pipeline_gbs": work.step_bytes * n_steps / (ms * 1e-3) / 1e9,
-                "clocks": clocks.summary()}
+                "clocks": clocks.summary(), "per_rank": per_rank}
 
     for _ in range(args.warmup):
         work.step()
@@ -595,7 +605,8 @@ def main():
                                        + (f" + patch_level({wl['patch']})" if wl["patch"] else ""),
                        "sharding": f"volumes sharded over {world} rank(s); one all_gather of the score tables of "
                                    f"the timed region ({args.steps} x {work.pool} rows per rank), inside it"},
-            "roofline": roofline, "sustained": sustained, "cpu_baseline": cpu, "parity": parity,
+            "roofline": roofline, "sustained": sustained, "per_rank": burst["per_rank"], "cpu_baseline": cpu,
+            "parity": parity,
             "clocks": burst["clocks"], "e2e": e2e, "gpu_launches": burst["launches"],
         }
         if sweep is not None:
