@@ -1493,7 +1493,8 @@ static int run_patch_march(FusedParams prm, const FusedPlan& pl, int64_t M, cuda
         q.gmax = prm.gmax + m0; q.active = prm.active + m0 * (1 + kMaxActive);
         q.tickets = prm.tickets + 4 * m0;
         // the work list normally holds one or two (tile, z sub-chunk) entries per map
-        const unsigned g2 = (unsigned)std::min<int64_t>(prm.nent, mc >= 16 ? 8 : 32);
+        // (every CTA of the grid pays the finish protocol: with hundreds of maps two CTAs per map are enough)
+        const unsigned g2 = (unsigned)std::min<int64_t>(prm.nent, mc >= 256 ? 2 : mc >= 16 ? 8 : 32);
         // pass 1: every tile, or (after the filter) the few listed sub-chunks
         const unsigned g1 = filter ? (unsigned)std::min<int64_t>(pl.ntiles, g2) : (unsigned)pl.ntiles;
         k1<<<dim3(g1, (unsigned)mc), kFusedThreads, smem1, st>>>(q);

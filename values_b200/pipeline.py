@@ -121,8 +121,12 @@ class UncertaintyPipeline:
         self._side: Dict[torch.device, dict] = {}
 
     def _chunk(self, B: int, V: int) -> int:
+        """Volumes per chunk: as many as the map scratch holds, in EQUAL chunks (1024 volumes at 341 per
+        chunk would leave a last chunk of one volume -- a K1 and three K2b launches for 3 maps)."""
         per_volume = 3 * V * 4  # three fp32 maps
-        return max(1, min(B, self.cfg.chunk_bytes // max(per_volume, 1)))
+        cap = max(1, min(B, self.cfg.chunk_bytes // max(per_volume, 1)))
+        n_chunks = -(-B // cap) if B else 1
+        return max(1, -(-B // n_chunks))
 
     def _buf(self, name: str, shape, dtype, dev) -> torch.Tensor:
         """Grow-only scratch tensors keyed by (name, dtype, device)."""
