@@ -8,6 +8,14 @@
 //   H_n   = -sum_c p[n,c]*log(p[n,c])     NaN terms (0*log0, log of negatives) are skipped
 //   EE    = (sum_n H_n) / N               fp32, sample order
 //   MI    = PE - EE
+// fp64 stacks (the reference's 3-D path) keep exactly this order: one fp32 accumulator H_n per sample,
+// classes in index order, EE their sequential fp32 sum.  The fp32 / bf16 kernels do NOT: they stream
+// class-outer / sample-inner and add every p*log(p) of a class into one fp32 accumulator, the classes
+// then into E, with a polynomial (fp32) or MUFU (bf16) logarithm -- the same N*C terms in another
+// order.  EE, and so MI = PE - EE, therefore differ from the reference by rounding only: measured
+// <= 1.2e-6 absolute (8 ulp of EE) on the BASELINE shapes, bounded by ~N*C*2^-24*max|p log p|; the
+// parity tests hold 1e-5 |ref| + 1e-6, and tests/test_gpu_parity_counts.py counts what that does to
+// threshold masks (0-2 voxels per 2.1 M at the median threshold).
 // HBM-bound: algorithmic bytes per voxel = N*C*sizeof(T) + 3*4 (+1 arg-max byte).
 #include "common.cuh"
 
