@@ -91,6 +91,35 @@ __global__ void __launch_bounds__(kThreads) normalize_kernel(const T* __restrict
     out[m * V + v] = (double)In<T>::load_one(maps + m * stride_m + v) / c;
 }
 
+// Vector form (V % 4 == 0, 16 / 32-byte aligned rows): a thread owns four consecutive voxels of EVERY map,
+// so the count is read once, not once per map, and every access is 16 bytes wide.  Same arithmetic (one
+// IEEE division per element).  cfg3 (3 fp32 maps of 256^3): 0.28 ms -> see DESIGN.md.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) normalize_vec_kernel(const T* __restrict__ maps, int64_t V, int64_t M,
+                                                                 int64_t stride_m, const double* __restrict__ count,
+                                                                 double clip_min, double* __restrict__ out) {
+    const int64_t v = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (v >= V) return;
+    const double2 c01 = *reinterpret_cast<const double2*>(count + v), c23 = *reinterpret_cast<const double2*>(count + v + 2);
+    double c[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[q] = clip_min > 0.0 ? fmax(c[q], clip_min) : (c[q] > 0.0 ? c[q] : 1.0);
+    for (int64_t m = 0; m < M; ++m) {
+        double x[4];
+        if constexpr (sizeof(T) == 4) {
+            const float4 r = *reinterpret_cast<const float4*>(maps + m * stride_m + v);
+            x[0] = (double)r.x; x[1] = (double)r.y; x[2] = (double)r.z; x[3] = (double)r.w;
+        } else {
+            const double2 a = *reinterpret_cast<const double2*>(maps + m * stride_m + v);
+            const double2 b = *reinterpret_cast<const double2*>(maps + m * stride_m + v + 2);
+            x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+        }
+        double* o = out + m * V + v;
+        *reinterpret_cast<double2*>(o) = make_double2(x[0] / c[0], x[1] / c[1]);
+        *reinterpret_cast<double2*>(o + 2) = make_double2(x[2] / c[2], x[3] / c[3]);
+    }
+}
+
 // =============================================================================== K2b
 constexpr int kTX = 32;   // outputs per tile along the contiguous axis
 constexpr int kTY = 16;   // outputs per tile along axis 1
@@ -1575,6 +1604,19 @@ extern "C" int values_normalize_maps(const void* maps, int dtype, int64_t M, int
     if (M < 0 || V < 0) return set_error(VALUES_ERR_INVALID_ARG, "normalize: bad sizes");
     if (M == 0 || V == 0) return VALUES_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype != VALUES_F32 && dtype != VALUES_F64)
+        return set_error(VALUES_ERR_INVALID_ARG, "normalize: dtype must be f32 or f64");
+    const size_t es = dtype == VALUES_F32 ? 4 : 8;
+    if (V % 4 == 0 && stride_m % 4 == 0 && reinterpret_cast<uintptr_t>(maps) % (4 * es) == 0 &&
+        reinterpret_cast<uintptr_t>(count) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+        const int64_t blocks = ceil_div(V / 4, kThreads);
+        if (blocks > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "normalize: grid too large");
+        if (dtype == VALUES_F32)
+            normalize_vec_kernel<float><<<(unsigned)blocks, kThreads, 0, st>>>((const float*)maps, V, M, stride_m, count, clip_min, out);
+        else
+            normalize_vec_kernel<double><<<(unsigned)blocks, kThreads, 0, st>>>((const double*)maps, V, M, stride_m, count, clip_min, out);
+        return check_launch("normalize_vec_kernel");
+    }
     const int64_t bpm = ceil_div(V, kThreads);
     if (bpm * M > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "normalize: grid too large");
     const unsigned grid = (unsigned)(bpm * M);
