@@ -69,7 +69,7 @@ def main():
     maps32 = [torch.rand((128, 128, 128), generator=g, device=dev) ** 2 for _ in range(32)]
     n = sum(m.numel() for m in maps32)
     ms = timed(lambda: vb.quantile(maps32, 0.98), args.reps)
-    report("K4 quantile(0.98) fp32, 32 x 128^3 (3 digit passes + NaN check, host syncs)", ms, 4 * n * 4, "(4 sweeps)")
+    report("K4 quantile(0.98) fp32, 32 x 128^3 (3 digit passes, digit selection on the device, one readback)", ms, 4 * n * 4, "(4 sweeps)")
     maps64 = [m.double() for m in maps32[:16]]
     n64 = sum(m.numel() for m in maps64)
     ms = timed(lambda: vb.quantile(maps64, 0.98), args.reps)
