@@ -442,10 +442,10 @@ def test_c3_map_reduce_vs_oracle(vb, vo):
 
 
 # --------------------------------------------------------------------------------- stitch
-@pytest.fixture(params=[0, 1], ids=["k3-auto", "k3-scalar"])
+@pytest.fixture(params=[0, 1, 2], ids=["k3-auto", "k3-scalar", "k3-vector"])
 def stitch_path(request):
-    """The vector kernel (4 z voxels per thread, used when rows are 16-byte aligned) and the scalar
-    kernel must both be bit-exact."""
+    """The box kernel (tensor-map copies through a shared-memory ring; the default when rows are 16-byte
+    aligned), the register-staged vector kernel and the scalar kernel must all be bit-exact."""
     return request.param
 
 
@@ -508,6 +508,40 @@ def test_stitch_vs_oracle(vb, vo, shape, p, overlap, dtype, stitch_path):
     if dtype == torch.float32:
         t32, _ = vb.stitch_volume(patches.cuda(), crops, shape, out_dtype=torch.float32, path=stitch_path)
         np.testing.assert_allclose(t32.cpu().numpy(), st.data["v"]["softmax_pred"], rtol=1e-6)
+
+
+def test_stitch_selected_patches_of_a_padded_stack(vb, vo, stitch_path):
+    """A subset of the patches (patch_index), in a different order than they are stored, out of a stack whose
+    sample stride is larger than patches x patch size (a view of a bigger tensor): the box kernel addresses
+    (sample, patch) rows through one merged tensor-map dimension."""
+    shape, p = (48, 32, 64), 16
+    crops = vo.patch_grid(shape, p, 0.5)
+    g = torch.Generator().manual_seed(8)
+    store = torch.rand(3, len(crops) + 5, 2, p, p, p, generator=g, dtype=torch.float32).cuda()
+    patches = store[:, 2:2 + len(crops)]                      # stride_n = (P + 5) * stride_p, offset base
+    sel = [i for i in range(len(crops)) if i % 3 != 1][::-1]   # a subset, reversed: summation order = list order
+    lo = vb.stitching.crops_to_lo([crops[i] for i in sel], "cuda")
+    out = torch.empty((3, 2) + shape, dtype=torch.float64, device="cuda")
+    cnt = torch.empty(shape, dtype=torch.float64, device="cuda")
+    vb.stitch_accumulate(patches, lo, out, cnt, patch_index=torch.tensor(sel, dtype=torch.int32, device="cuda"),
+                         accumulate=False, path=stitch_path)
+    want = np.zeros((3, 2) + shape)
+    want_cnt = np.zeros(shape)
+    ph = patches.cpu().numpy().astype(np.float64)
+    for i in sel:
+        (x0, x1), (y0, y1), (z0, z1) = crops[i]
+        want[:, :, x0:x1, y0:y1, z0:z1] += ph[:, i]
+        want_cnt[x0:x1, y0:y1, z0:z1] += 1
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), want_cnt)
+    # a second call accumulates on top (read-modify-write of every voxel)
+    vb.stitch_accumulate(patches, lo, out, cnt, patch_index=torch.tensor(sel, dtype=torch.int32, device="cuda"),
+                         accumulate=True, path=stitch_path)
+    for i in sel:                                              # the same slabs added again, in list order
+        (x0, x1), (y0, y1), (z0, z1) = crops[i]
+        want[:, :, x0:x1, y0:y1, z0:z1] += ph[:, i]
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), 2 * want_cnt)
 
 
 def test_stitch_many_patches_chunked_list(vb, vo, stitch_path):

@@ -44,7 +44,7 @@ def stitch_accumulate(
     patch_index: Optional[torch.Tensor] = None,  # int32 [n_sel] or None (identity)
     accumulate: bool = True,
     weight: Optional[torch.Tensor] = None,     # fp64 [p0, p1, p2] importance map (None = uniform)
-    path: int = 0,                             # 0 automatic, 1 scalar kernel (tests; same results)
+    path: int = 0,                             # 0 automatic (box kernel), 1 scalar, 2 vector kernel (tests; same results)
 ) -> None:
     if patches.device.type != "cuda":
         raise RuntimeError("stitch_accumulate expects CUDA tensors (no CPU fallback)")
