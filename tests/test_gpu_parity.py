@@ -281,6 +281,8 @@ def test_c3_golden(vb, patch_path):
     ((35, 200, 37), [20, 1, 30], np.float32), ((256, 478), 10, np.float32),
     ((20, 30, 100), [3, 4, 40], np.float64),   # patch wider than a warp -> tiled shared-memory fallback
     ((9, 70, 33), [9, 33, 32], np.float32), ((1024, 2048), 10, np.float32),
+    ((300, 500), 10, np.float32), ((75, 260), 10, np.float32),     # 2-D: the strip filter marches along y
+    ((40, 45, 252), 10, np.float32),                               # three x tiles of the strip filter
 ])
 def test_c3_patch_vs_oracle(vb, vo, shape, patch, dtype, patch_path):
     rng = np.random.default_rng(sum(shape) * 7 + len(shape))
@@ -304,6 +306,25 @@ def test_c3_batched_and_isclose_rule(vb, vo, patch_path):
         np.testing.assert_allclose(score[i].item(), r["max_score"], rtol=1e-12)
         assert bbox[i].tolist() == [b[0] for b in r["bounding_box"]]
     assert bbox[3].tolist() == [0, 0, 0] and score[3].item() == 0.0
+
+
+@pytest.mark.parametrize("M,shape", [(1, (200, 300)), (20, (200, 300)), (7, (530, 136)), (40, (64, 64))])
+def test_c3_2d_batches_march_along_y(vb, vo, M, shape):
+    """2-D images go through the y-march of the strip filter; how many CTA rows a CTA walks depends on the
+    number of maps in the call.  Same results as the exact march alone and as the oracle, with values on both
+    sides of 2.0 (the exponent fields of 1.x and 2.x once fooled the filter's bound on max |input|)."""
+    rng = np.random.default_rng(M * 1000 + shape[0])
+    maps = (rng.random((M,) + shape) * 3.0).astype(np.float32)
+    maps[M // 2, shape[0] // 3:shape[0] // 3 + 10, 5:15] += 0.5
+    t = torch.from_numpy(maps).cuda()
+    s0, b0 = vb.patch_max(t, 10, path=0)
+    s5, b5 = vb.patch_max(t, 10, path=5)
+    np.testing.assert_allclose(s0.cpu().numpy(), s5.cpu().numpy(), rtol=1e-13, atol=0)
+    assert torch.equal(b0, b5)
+    for i in range(0, M, max(1, M // 4)):
+        r = vo.patch_level_aggregation(maps[i], 10)
+        np.testing.assert_allclose(s0[i].item(), r["max_score"], rtol=1e-12)
+        assert b0[i].tolist() == [b[0] for b in r["bounding_box"]]
 
 
 def _filter_cases():
