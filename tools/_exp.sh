@@ -1,11 +1,9 @@
-python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "k1 or c2 or c3_golden or stitch_golden" 2>&1 | tail -2
-python tools/k1_bench.py --shape cfg5 --batch 8 2>&1 | tail -1
-python tools/k1_bench.py --shape cfg4bf16 2>&1 | tail -1
-python tools/k1_bench.py --shape cfg2 --batch 256 2>&1 | tail -1
-python tools/k1_bench.py --shape cfg3n8 2>&1 | tail -1
-python tools/k2_bench.py --shape 128,128,128 --maps 96 --paths 0 2>&1 | tail -1
-python tools/k34_bench.py --reps 5 2>&1 | head -2
-for w in cfg5; do python bench.py --workload $w --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import json,sys
-j=json.loads(sys.stdin.read()); r=j['roofline']; s=j['sustained']
-print(j['config']['workload'][:12], j['dtype'], 'value %.4g ms %.3f frac %.3f pipe %.3f | sustained %.4g frac %.3f pipe %.3f launches %d' % (j['value'], j['ms_per_step'], r['frac'], r['pipeline_frac'], s['value'], s['frac'], s['pipeline_frac'], j['gpu_launches']))"; done
+set -x
+K='regex:k1_|box_|stitch_|normalize|map_reduce|radix|patch_'
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 200 --csv --log-file gpurun_out/r02u_launches_cfg5.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-sustained > gpurun_out/r02u_b.log 2>&1
+for w in cfg1 cfg2 cfg3 cfg4; do ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 200 --csv --log-file gpurun_out/r02u_launches_$w.csv python bench.py --workload $w --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-sustained --no-sweep >> gpurun_out/r02u_b.log 2>&1; done
+ncu --set full --clock-control none --import-source on -k regex:k1_tma -c 1 -o gpurun_out/r02u_k1_f64 python tools/k1_bench.py --shape cfg3n8 --reps 1 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:box_strip -c 1 -o gpurun_out/r02u_k2b_strip python tools/k2_case.py 128,128,128 96 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:box_strip -c 1 -o gpurun_out/r02u_k2b_strip_2d python tools/k2_case.py 1024,2048 18 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:box_march -c 1 -o gpurun_out/r02u_k2b_pass1 python tools/k2_case.py 128,128,128 96 > /dev/null 2>&1
+ls gpurun_out/r02u*
