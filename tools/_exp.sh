@@ -1,9 +1,13 @@
-set -x
-K='regex:k1_|box_|stitch_|normalize|map_reduce|radix|patch_'
-ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 200 --csv --log-file gpurun_out/r02u_launches_cfg5.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-sustained > gpurun_out/r02u_b.log 2>&1
-for w in cfg1 cfg2 cfg3 cfg4; do ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 200 --csv --log-file gpurun_out/r02u_launches_$w.csv python bench.py --workload $w --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-sustained --no-sweep >> gpurun_out/r02u_b.log 2>&1; done
-ncu --set full --clock-control none --import-source on -k regex:k1_tma -c 1 -o gpurun_out/r02u_k1_f64 python tools/k1_bench.py --shape cfg3n8 --reps 1 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:box_strip -c 1 -o gpurun_out/r02u_k2b_strip python tools/k2_case.py 128,128,128 96 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:box_strip -c 1 -o gpurun_out/r02u_k2b_strip_2d python tools/k2_case.py 1024,2048 18 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:box_march -c 1 -o gpurun_out/r02u_k2b_pass1 python tools/k2_case.py 128,128,128 96 > /dev/null 2>&1
-ls gpurun_out/r02u*
+python -m pytest tests -q -m gpu 2>&1 | tail -3 > gpurun_out/r02v_pytest_gpu.txt; cat gpurun_out/r02v_pytest_gpu.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+(for tool in memcheck synccheck; do echo "== compute-sanitizer --tool $tool, product build"; compute-sanitizer --tool $tool python tools/sanitize_k1_k3.py 2>&1 | tail -4; compute-sanitizer --tool $tool python tools/sanitize_k2.py 2>&1 | tail -3; done
+echo "== compute-sanitizer --tool racecheck, all-lanes-arrive build (python values_b200/build.py --sanitize)"
+VALUES_B200_LIB=values_b200/lib_sanitize/libvalues_b200.so compute-sanitizer --tool racecheck python tools/sanitize_k1_k3.py 2>&1 | tail -4
+VALUES_B200_LIB=values_b200/lib_sanitize/libvalues_b200.so compute-sanitizer --tool racecheck python tools/sanitize_k2.py 2>&1 | tail -3
+echo "== compute-sanitizer --tool racecheck, product build (lane 0 arrives for its warp after __syncwarp: reported as hazards, see DESIGN.md section 6)"
+compute-sanitizer --tool racecheck python tools/sanitize_k1_k3.py 2>&1 | grep -E "RACECHECK SUMMARY|Race reported" | sort | uniq -c | head -5) > gpurun_out/r02v_sanitizer.txt 2>&1; cat gpurun_out/r02v_sanitizer.txt
+python bench.py > gpurun_out/r02v_bench_cfg5.json 2> gpurun_out/r02v_bench.err; tail -1 gpurun_out/r02v_bench.err
+python bench.py --impl reference > gpurun_out/r02v_bench_cfg5_reference_arm.json 2>> gpurun_out/r02v_bench.err
+rm -f gpurun_out/r02v_bench_others.jsonl
+for w in cfg1 cfg2 cfg3 cfg4 cfg4bf16; do python bench.py --workload $w >> gpurun_out/r02v_bench_others.jsonl 2>> gpurun_out/r02v_bench.err; done
+wc -l gpurun_out/r02v_bench_others.jsonl
