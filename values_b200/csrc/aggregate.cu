@@ -779,8 +779,30 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
             if (y0 + oy0 + k < prm.O1 && x0 + ox < prm.O2) valid |= 1u << k;
         const bool all_valid = valid == (1u << MT::RUN) - 1;
 
-        {   // plane 0 enters
-            const T* pn = src;
+        // A listed entry is serial latency (one CTA, zc_fine + p0 - 1 planes, one plane of look-ahead): the
+        // p0 - 1 planes that only fill the z-window are fetched kWarm planes at a time instead (same adds,
+        // same order).
+        int zi_first = 0;
+        if (listed) {
+            constexpr int kWarm = MINB == 1 ? 3 : 2;
+            const int warm = p0 - 1;
+            for (; zi_first + kWarm <= warm; zi_first += kWarm) {
+                T w[kWarm][MT::NSLOT];
+#pragma unroll
+                for (int k = 0; k < kWarm; ++k) {
+                    const T* pk = src + (int64_t)(zi_first + k) * plane_elems;
+#pragma unroll
+                    for (int i = 0; i < MT::NSLOT; ++i) w[k][i] = In<T>::load_one(pk + off[i]);
+                }
+#pragma unroll
+                for (int k = 0; k < kWarm; ++k) {
+#pragma unroll
+                    for (int i = 0; i < MT::NSLOT; ++i) zs[i] += (ACC)w[k][i];
+                }
+            }
+        }
+        {   // the first plane of the pipelined march enters
+            const T* pn = src + (int64_t)zi_first * plane_elems;
 #pragma unroll
             for (int i = 0; i < MT::NSLOT; ++i) nw[i] = In<T>::load_one(pn + off[i]);
         }
@@ -789,7 +811,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
         // (A[(t-1) & 1] -> Bs[(t-1) & 1]) and y-passes plane t-2 (Bs[t & 1]); two drain steps.
         const int nout = nplanes - (p0 - 1);
         int sub_planes = 0, sub_idx = 0;      // planes finished in the current z sub-chunk, its index
-        for (int zi = 0; zi < nplanes + 2; ++zi) {
+        for (int zi = zi_first; zi < nplanes + 2; ++zi) {
             const int t = zi - (p0 - 1);
             if (zi < nplanes) {
 #pragma unroll
