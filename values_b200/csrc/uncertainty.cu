@@ -116,13 +116,17 @@ __device__ __forceinline__ void log64_split(int hi, int& k, int& mhi, int& idx) 
     mhi = (int)((unsigned int)hi - ((unsigned int)k << 20));
     idx = (mhi >> 11) - kLog64Base;
 }
+// (double)k without the XU-pipe conversion: 2^52 + 2^31 + k is exact in the low word of a double
+__device__ __forceinline__ double log64_k(int k) {
+    return __hiloint2double(0x43300000, k ^ (int)0x80000000) - 4503601774854144.0;
+}
 __device__ __forceinline__ double log64_finish(int k, double m, double2 t) {
     const double r = fma(m, t.x, -1.0);
     const double r2 = r * r;
     // log1p(r) = r + r^2 (-1/2 + r/3 + r^2 (-1/4 + r/5)): Estrin, three dependent levels instead of five
     const double q = fma(r2, fma(0.2, r, -0.25), fma(1.0 / 3.0, r, -0.5));
     const double l1p = fma(r2, q, r);
-    return fma((double)k, 0.6931471805599453, t.y + l1p);
+    return fma(log64_k(k), 0.6931471805599453, t.y + l1p);
 }
 // any input: zero, negative, NaN, inf and subnormal values take log()
 __device__ __forceinline__ double fast_log_f64(double p) {
@@ -131,6 +135,17 @@ __device__ __forceinline__ double fast_log_f64(double p) {
     int k, mhi, idx;
     log64_split(hi, k, mhi, idx);
     return log64_finish(k, __hiloint2double(mhi, __double2loint(p)), __ldg(&kLog64Tab[idx]));
+}
+
+// the same, table read from the CTA's shared-memory copy (`tab` = its shared-memory address)
+__device__ __forceinline__ double fast_log_f64_tab(double p, uint32_t tab) {
+    const int hi = __double2hiint(p);
+    if ((unsigned int)(hi - 0x00100000) >= 0x7fe00000u) return log(p);
+    int k, mhi, idx;
+    log64_split(hi, k, mhi, idx);
+    double2 t;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(tab + (uint32_t)idx * 16u));
+    return log64_finish(k, __hiloint2double(mhi, __double2loint(p)), t);
 }
 
 // acc += p*log(p), NaN terms skipped (test_3D.py:490-494, 500-504).  A term is NaN exactly when
@@ -472,6 +487,18 @@ __device__ __forceinline__ void pe_terms(float (&PE)[VEC], const double (&m)[VEC
 #pragma unroll
     for (int j = 0; j < VEC; ++j) accum_term(PE[j], m[j]);
 }
+// fp64 ring kernel: the log table is already in shared memory (the global-memory lookup of accum_term was
+// 9 % of the kernel's stall samples, ncu r02u); same arithmetic, bit-identical
+template <int VEC>
+__device__ __forceinline__ void pe_terms_tab(float (&PE)[VEC], const double (&m)[VEC], uint32_t tab) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const double t = m[j] * fast_log_f64_tab(m[j], tab);
+        PE[j] = (t == t) ? (float)((double)PE[j] + t) : PE[j];
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void pe_terms_tab(float (&PE)[VEC], const float (&m)[VEC], uint32_t) { pe_terms<VEC>(PE, m); }
 
 template <typename T> struct Math;
 template <> struct Math<float> {
@@ -882,7 +909,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                     E[j] += e[j];
                     e[j] = 0.f;
                 }
-                pe_terms<VEC>(PE, m);
+                if constexpr (NS > 0) pe_terms_tab<VEC>(PE, m, log_tab); else pe_terms<VEC>(PE, m);
             }
         }
         if (!active) continue;
