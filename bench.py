@@ -57,6 +57,14 @@ WORKLOADS = {
                       "patches -> fp64 sums; K1 fp64 on the raw sums; normalised maps",
                  N=8, C=2, spatial=(256, 256, 256), dtype="f64", patch_dtype="f32", pool=1, e2e_pool=1,
                  stitch=dict(patch=64, overlap=0.5), patch=None, thr=False, cfg=3),
+    # the same with the Gaussian patch weight BASELINE.json's configs[2] / north_star name (the reference itself
+    # accumulates with uniform weights, SURVEY D1: its CPU arm runs the uniform concat_data): separable
+    # factors in the stitch kernel's shared memory, sums normalised by the weight sum
+    "cfg3gauss": dict(name="cfg3 (Gaussian-weighted): stitch 343 patches 64^3 (overlap 0.5) into a 256^3 volume with "
+                           "the separable Gaussian importance map, N=8 (TTA), C=2, fp32 patches -> fp64 weighted "
+                           "sums + weight sum; K1 fp64 on the raw sums; maps normalised by the weight sum",
+                      N=8, C=2, spatial=(256, 256, 256), dtype="f64", patch_dtype="f32", pool=1, e2e_pool=1,
+                      stitch=dict(patch=64, overlap=0.5, weight="gaussian"), patch=None, thr=False, cfg=3),
     # BASELINE.json configs[3] (19 classes + the zero channel test_2D appends)
     "cfg4": dict(name="cfg4: 1024x2048 images, N=10, C=19+1, fp32; all C3 aggregations",
                  N=10, C=20, spatial=(1024, 2048), dtype="f32", pool=6, e2e_pool=2, patch=10, thr=True, cfg=4,
@@ -403,6 +411,9 @@ class StitchWorkload:
             self.patches[n] = torch.softmax(logits, dim=1).to(pdt)
             del logits
         self.crop_lo = vb.stitching.crops_to_lo(crops, dev)
+        self.weight = (vb.gaussian_importance_factors((p, p, p), device=dev)
+                       if wl["stitch"].get("weight") == "gaussian" else None)
+        self.clip_min = 1.0 if self.weight is None else 0.0
         self.sums = torch.empty((wl["N"], wl["C"]) + shape, dtype=torch.float64, device=dev)
         self.count = torch.empty(shape, dtype=torch.float64, device=dev)
         self.maps = torch.empty((1, 3) + shape, dtype=torch.float32, device=dev)
@@ -410,7 +421,7 @@ class StitchWorkload:
         self.argmax = torch.empty((1,) + shape, dtype=torch.uint8, device=dev)
         self.pool_bytes = self.patches.numel() * self.patches.element_size()
         self.events = []
-        self.kernel = "k3 stitch accumulator (stitch_vec_kernel)"
+        self.kernel = "k3 stitch accumulator (stitch_box_kernel" + (", separable weights)" if self.weight is not None else ")")
         k3 = self.pool_bytes + self.sums.numel() * 8 + self.count.numel() * 8
         k1 = self.V * (wl["N"] * wl["C"] * 8 + 13)
         norm = self.V * (3 * (4 + 8) + 8)
@@ -423,12 +434,12 @@ class StitchWorkload:
         vb = self.vb
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        vb.stitch_accumulate(self.patches, self.crop_lo, self.sums, self.count, accumulate=False)
+        vb.stitch_accumulate(self.patches, self.crop_lo, self.sums, self.count, accumulate=False, weight=self.weight)
         e1.record()
         self.events.append((e0, e1, 1))
         vb.uncertainty_fused(self.sums.unsqueeze(0), maps=True, mean_argmax=True, scores=True, out_maps=self.maps,
                              volume_major=True, out_scores=self.scores[:, :, :3], out_argmax=self.argmax)
-        self.norm = vb.normalize_maps(self.maps[0], self.count)
+        self.norm = vb.normalize_maps(self.maps[0], self.count, self.clip_min)
         return self
 
     def wait(self):
@@ -726,11 +737,11 @@ def run_e2e_stitch(vb, wl, work, dev, world, args, main, copy_stream):
                 ready[s].record(copy_stream)
             main.wait_event(ready[s])
             vb.stitch_accumulate(bufs[s].unsqueeze(0), work.crop_lo, work.sums[n:n + 1],
-                                 work.count if n == 0 else None, accumulate=False)
+                                 work.count if n == 0 else None, accumulate=False, weight=work.weight)
             freed[s].record(main)
         vb.uncertainty_fused(work.sums.unsqueeze(0), maps=True, mean_argmax=True, scores=True, out_maps=work.maps,
                              volume_major=True, out_scores=work.scores[:, :, :3], out_argmax=work.argmax)
-        work.norm = vb.normalize_maps(work.maps[0], work.count)
+        work.norm = vb.normalize_maps(work.maps[0], work.count, work.clip_min)
         host_scores.copy_(work.scores.reshape(-1), non_blocking=True)
         main.synchronize()
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VALUES_ABI_VERSION 6
+#define VALUES_ABI_VERSION 7
 
 typedef enum {
     VALUES_F32 = 0, VALUES_F64 = 1, VALUES_BF16 = 2,
@@ -158,6 +158,21 @@ int values_stitch_accumulate_weighted(const void* patches, int patch_dtype, int6
                                       int64_t N, int64_t C, const int64_t* patch3_host,
                                       const int64_t* vol3_host, void* out_sum, int out_dtype,
                                       double* out_count, int accumulate, int path, void* stream);
+
+/* The weighted accumulator for a SEPARABLE importance map (the Gaussian of sliding-window inference is one):
+ *   weight[x][y][z] = fl(fl(wx[x] * wy[y]) * wz[z])   (two fp64 roundings, in this order)
+ * with wx / wy / wz double [p0] / [p1] / [p2] on the device.  Results are bit-identical to
+ * values_stitch_accumulate_weighted on the materialised map; the factors live in shared memory, so the
+ * weights cost no memory traffic.  Only the box kernel takes them: returns VALUES_ERR_UNSUPPORTED (nothing
+ * launched) when path != 0, a patch edge exceeds 128 or the rows are not 16-byte aligned -- the caller then
+ * materialises the map and calls values_stitch_accumulate_weighted. */
+int values_stitch_accumulate_separable(const void* patches, int patch_dtype, int64_t patch_stride_n,
+                                       int64_t patch_stride_p, const int32_t* patch_index,
+                                       const int32_t* crop_lo, const double* wx, const double* wy,
+                                       const double* wz, int64_t n_sel, int64_t N, int64_t C,
+                                       const int64_t* patch3_host, const int64_t* vol3_host, void* out_sum,
+                                       int out_dtype, double* out_count, int accumulate, int path,
+                                       void* stream);
 
 /* Save-time normalisation (data_carrier_3D.py:215-217, 326-329):
  *   out[m, v] = (double) maps[m, v] / max(count[v], clip_min)   -> fp64 as written to NIfTI;

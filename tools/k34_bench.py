@@ -62,7 +62,15 @@ def main():
             report(f"K3 stitch vol={vol} p={p} ov={ov} N={N} {len(crops)} patches -> {str(out_dtype)[6:]}", ms, nbytes)
         w = vb.gaussian_importance_map((p, p, p), device=dev)
         ms = timed(lambda: vb.stitch_accumulate(patches, lo, out, cnt, accumulate=False, weight=w), args.reps)
-        report(f"K3 stitch (gaussian weight) vol={vol} ov={ov} -> float32", ms, nbytes)
+        report(f"K3 stitch (gaussian weight map) vol={vol} ov={ov} -> float32", ms, nbytes)
+        fac = vb.gaussian_importance_factors((p, p, p), device=dev)
+        ms = timed(lambda: vb.stitch_accumulate(patches, lo, out, cnt, accumulate=False, weight=fac), args.reps)
+        report(f"K3 stitch (gaussian weight, separable factors) vol={vol} ov={ov} -> float32", ms, nbytes)
+        out64 = torch.empty((N, 2) + vol, dtype=torch.float64, device=dev)
+        ms = timed(lambda: vb.stitch_accumulate(patches, lo, out64, cnt, accumulate=False, weight=fac), args.reps)
+        report(f"K3 stitch (gaussian weight, separable factors) vol={vol} ov={ov} -> float64", ms,
+               patches.numel() * 4 + out64.numel() * 8 + cnt.numel() * 8)
+        del out64
         del patches, out, cnt
 
     # ---------------- K4: statistics over 32 x 128^3 maps

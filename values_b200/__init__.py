@@ -18,7 +18,7 @@ from .metrics import (calc_ace, calib_stats, calibration_error, calibration_erro
 from .pipeline import AggregationConfig, PipelineResult, UncertaintyPipeline
 from .segmetrics import calculate_ged, confusion_counts, dice_from_confusion, mean_prediction_dice
 from .sharding import AsyncScoreGather, gather_scores, shard_range, shard_sizes
-from .stitching import gaussian_importance_map, patch_grid, stitch_accumulate, stitch_volume
+from .stitching import gaussian_importance_factors, gaussian_importance_map, importance_map_from_factors, patch_grid, stitch_accumulate, stitch_volume
 from .threshold import (calculate_foreground_quantile_image, calculate_threshold_image,
                         count_nonzero, find_threshold, get_foreground_quantile, quantile,
                         save_foreground_quantiles)
@@ -31,7 +31,7 @@ __all__ = [
     "calculate_uncertainty_multiple_pred", "uncertainty_fused", "FusedResult",
     "patch_level_aggregation", "image_level_aggregation", "threshold_aggregation",
     "aggregate_uncertainties", "patch_max", "map_reduce", "normalize_maps",
-    "DataCarrier3D", "patch_grid", "stitch_accumulate", "stitch_volume", "gaussian_importance_map",
+    "DataCarrier3D", "patch_grid", "stitch_accumulate", "stitch_volume", "gaussian_importance_map", "gaussian_importance_factors", "importance_map_from_factors",
     "UncertaintyPipeline", "AggregationConfig", "PipelineResult",
     "shard_range", "shard_sizes", "gather_scores", "AsyncScoreGather",
     "calculate_foreground_quantile_image", "get_foreground_quantile", "save_foreground_quantiles",

@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VALUES_B200_LIB") or os.path.join(_PKG, "lib", "libvalues_b200.so")
 
 F32, F64, BF16, U8, I32, I64 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 6  # include/values_b200.h VALUES_ABI_VERSION
+ABI_VERSION = 7  # include/values_b200.h VALUES_ABI_VERSION
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 _LABEL_DTYPES = {torch.uint8: U8, torch.int32: I32, torch.int64: I64}
 
@@ -52,6 +52,8 @@ def _load() -> C.CDLL:
                                                pi64, pi64, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
         "values_stitch_accumulate_weighted": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, vp, i64, i64, i64,
                                                         pi64, pi64, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
+        "values_stitch_accumulate_separable": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, vp, vp, vp, i64, i64, i64,
+                                                         pi64, pi64, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
         "values_normalize_maps": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, dbl, vp, vp]),
         "values_count_nonzero": (C.c_int, [vp, C.c_int, i64, vp, vp]),
         "values_radix_histogram": (C.c_int, [vp, C.c_int, i64, C.c_uint64, C.c_int, C.c_int, vp, vp]),
@@ -82,7 +84,7 @@ EXPORTED = [
     "values_uncertainty_workspace_bytes", "values_uncertainty_fused", "values_one_minus_msr",
     "values_map_reduce_workspace_bytes", "values_map_reduce",
     "values_patch_max_workspace_bytes", "values_patch_max", "values_stitch_accumulate",
-    "values_stitch_accumulate_weighted",
+    "values_stitch_accumulate_weighted", "values_stitch_accumulate_separable",
     "values_normalize_maps", "values_count_nonzero", "values_radix_histogram",
     "values_min_key_above", "values_radix_histogram_dev", "values_radix_select",
     "values_pair_moments_workspace_bytes", "values_pair_moments",

@@ -1066,9 +1066,11 @@ static int launch_smem(const K1Params& prm, int64_t grid, cudaStream_t st) {
 // Stacks with few rows per voxel (cfg1/2: N*C = 10) do little work per tile, so the fixed cost per
 // CTA (setup, score reduction, ticket) wants more tiles: measured on cfg2, 4 -> 16 tiles per CTA
 // lifts K1 from 0.67 to 0.72 of the HBM peak, while cfg5 (N*C = 64) and cfg4 (200) peak at 4.
-static int choose_iter(int64_t total_tiles, int minb, int64_t rows) {
+static int choose_iter(int64_t total_tiles, int minb, int64_t rows, bool f64 = false) {
     const int64_t resident = 148LL * minb;
-    int want = rows <= 12 ? 16 : (rows <= 24 ? 8 : 4);
+    // fp64 tiles hold half the voxels and every CTA copies the 8 KB log table first: 16 tiles per CTA
+    // measured +3 % on 256^3 N=8 C=2 (0.640 -> 0.663) and 128^3 N=16 C=4 (0.714 -> 0.733)
+    int want = (f64 || rows <= 12) ? 16 : (rows <= 24 ? 8 : 4);
     while (want > 4 && total_tiles < 8 * want * resident) want >>= 1;
     if (want > 4) return want;
     if (total_tiles >= 32 * resident) return 4;
@@ -1090,7 +1092,7 @@ static int launch_stream(K1Params& prm, int64_t B, cudaStream_t st) {
 template <typename T, int VEC, int MINB, int RS, int STAGES, int NS = 0>
 static int launch_tma(K1Params& prm, int64_t B, cudaStream_t st) {
     const int64_t tiles = ceil_div(ceil_div(prm.V, VEC), kThreads);
-    prm.iter = prm.tiles_per_cta > 0 ? prm.tiles_per_cta : choose_iter(tiles * B, MINB, prm.N * prm.C);
+    prm.iter = prm.tiles_per_cta > 0 ? prm.tiles_per_cta : choose_iter(tiles * B, MINB, prm.N * prm.C, sizeof(T) == 8);
     prm.blocks_per_vol = ceil_div(tiles, prm.iter);
     const int64_t grid = prm.blocks_per_vol * B;
     if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");

@@ -43,7 +43,8 @@ def stitch_accumulate(
     out_count: Optional[torch.Tensor] = None,  # fp64 [X, Y, Z]
     patch_index: Optional[torch.Tensor] = None,  # int32 [n_sel] or None (identity)
     accumulate: bool = True,
-    weight: Optional[torch.Tensor] = None,     # fp64 [p0, p1, p2] importance map (None = uniform)
+    weight=None,                               # fp64 [p0, p1, p2] importance map, or its three 1-D factors
+                                               # (wx, wy, wz) -- see gaussian_importance_factors; None = uniform
     path: int = 0,                             # 0 automatic (box kernel), 1 scalar, 2 vector kernel (tests; same results)
 ) -> None:
     if patches.device.type != "cuda":
@@ -68,6 +69,24 @@ def stitch_accumulate(
                                   or tuple(out_count.shape) != tuple(out_sum.shape[2:])):
         raise ValueError("out_count must be contiguous fp64 [X, Y, Z]")
     dev = patches.device
+    if isinstance(weight, (tuple, list)):
+        # separable map: the factors go to the box kernel's shared memory (no weight traffic); whatever
+        # that kernel cannot take gets the materialised map below -- bit-identical either way
+        if len(weight) != 3 or any(w.dim() != 1 or w.numel() != n for w, n in zip(weight, patches.shape[3:])):
+            raise ValueError("weight factors must be three 1-D tensors of lengths p0, p1, p2")
+        fac = [w.to(device=dev, dtype=torch.float64).contiguous() for w in weight]
+        with torch.cuda.device(dev):
+            rc = _lib.lib.values_stitch_accumulate_separable(
+                patches.data_ptr(), _lib.dtype_code(patches.dtype), patches.stride()[0],
+                patches.stride()[1], _lib.ptr(patch_index), crop_lo.data_ptr(), fac[0].data_ptr(),
+                fac[1].data_ptr(), fac[2].data_ptr(), n_sel, N, Cn,
+                _lib.i64x3(patches.shape[3:]), _lib.i64x3(out_sum.shape[2:]), out_sum.data_ptr(),
+                _lib.dtype_code(out_sum.dtype), _lib.ptr(out_count), int(accumulate), int(path),
+                _lib.stream_ptr(dev))
+        if rc != _lib.ERR_UNSUPPORTED:
+            _lib.check(rc)
+            return
+        weight = importance_map_from_factors(fac)
     if weight is not None:
         if tuple(weight.shape) != tuple(patches.shape[3:]):
             raise ValueError("weight must have the patch shape [p0, p1, p2]")
@@ -82,21 +101,34 @@ def stitch_accumulate(
     _lib.check(rc)
 
 
+def gaussian_importance_factors(patch_shape: Sequence[int], sigma_scale: float = 0.125,
+                                device=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The three 1-D factors of the Gaussian patch weight: exp(-((i - c) / sigma)^2 / 2) with c the centre of
+    the axis and sigma = sigma_scale * extent, scaled to a maximum of 1, zeros lifted to the smallest positive
+    value of the factor (the usual sliding-window-inference importance map, axis by axis).  Passed as
+    `weight=(wx, wy, wz)` they reach the stitch kernel without a weight map in memory."""
+    fac = []
+    for n in patch_shape:
+        x = torch.arange(n, dtype=torch.float64)
+        g = torch.exp(-0.5 * ((x - (n - 1) / 2.0) / (sigma_scale * n)) ** 2)
+        g = g / g.max()
+        g = torch.clamp(g, min=float(g[g > 0].min()))
+        fac.append(g.to(device) if device is not None else g)
+    return tuple(fac)
+
+
+def importance_map_from_factors(factors) -> torch.Tensor:
+    """weight[x][y][z] = fl(fl(wx[x] * wy[y]) * wz[z]) -- the rounding order of the separable kernel path."""
+    wx, wy, wz = factors
+    return (wx[:, None, None] * wy[None, :, None]) * wz[None, None, :]
+
+
 def gaussian_importance_map(patch_shape: Sequence[int], sigma_scale: float = 0.125,
                             device=None) -> torch.Tensor:
-    """Separable Gaussian patch weight, centre 1, sigma = sigma_scale * extent per axis, zeros
-    lifted to the smallest positive weight (the usual sliding-window-inference importance map).
+    """Gaussian patch weight fp64 [p0, p1, p2]: the outer product of gaussian_importance_factors (centre 1).
     The reference accumulates with UNIFORM weights; this is the opt-in
-    Gaussian-weighted variant BASELINE.json's north_star names.  fp64 [p0, p1, p2]."""
-    axes = []
-    for n in patch_shape:
-        c = (n - 1) / 2.0
-        x = torch.arange(n, dtype=torch.float64)
-        axes.append(torch.exp(-0.5 * ((x - c) / (sigma_scale * n)) ** 2))
-    w = axes[0][:, None, None] * axes[1][None, :, None] * axes[2][None, None, :]
-    w = w / w.max()
-    w = torch.clamp(w, min=float(w[w > 0].min()))
-    return w.to(device) if device is not None else w
+    Gaussian-weighted variant BASELINE.json's north_star names."""
+    return importance_map_from_factors(gaussian_importance_factors(patch_shape, sigma_scale, device))
 
 
 def stitch_volume(patches: torch.Tensor, crops, vol_shape: Sequence[int],
