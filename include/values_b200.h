@@ -265,6 +265,21 @@ int values_confusion_counts(const void* labels_a, int64_t Na, int64_t stride_a, 
                             int64_t Nb, int64_t stride_b, int label_dtype, int64_t V, int n_classes,
                             unsigned long long* out, void* stream);
 
+/* The sums behind calculate_test_metrics (uncertainty_modeling/test_3D.py:250-281): SoftDiceLoss
+ * (uncertainty_modeling/loss_modules.py:7-90, smooth 1e-5, background included) + torch.nn.NLLLoss of
+ * log(mean softmax), per rater.  probs [C, V] (F32 / F64, class stride stride_c), labels [R, V] (U8 / I32 /
+ * I64, rater stride stride_r), C <= 8.  With CT = C rounded up to 2, 4 or 8:
+ *   out double [R, 3 CT + 1] (device, overwritten):
+ *     out[r][c]          = sum_v probs[c][v] [labels[r][v] == c]     (intersect)
+ *     out[r][CT + c]     = #{ v : labels[r][v] == c }
+ *     out[r][2 CT + c]   = sum_v probs[c][v]
+ *     out[r][3 CT]       = sum_v log(probs[labels[r][v]][v])          (NaN if a label is outside [0, C))
+ * fp64, fixed summation order (deterministic). */
+size_t values_seg_loss_workspace_bytes(int64_t R, int C, int64_t V);
+int values_seg_loss_terms(const void* probs, int dtype, int64_t stride_c, const void* labels,
+                          int label_dtype, int64_t stride_r, int64_t R, int C, int64_t V, double* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Axis-order conversion for the hand-off files: medpy.io.load / save
  * (data_carrier_3D.py:233-371, experiment_dataloader.py:38-49, aggregate_uncertainties.py:77-79)
  * present a NIfTI payload -- stored x-fastest, a C-order [Z][Y][X] array -- to Python as an array

@@ -269,6 +269,38 @@ def test_confusion_counts_exact(vb, ldt):
             np.testing.assert_array_equal(got[i, j], want)
 
 
+@pytest.mark.parametrize("c,r,shape,dtype,ldt", [(2, 4, (40, 36, 33), torch.float64, torch.int32),
+                                                 (4, 3, (48, 65), torch.float64, torch.int64),
+                                                 (2, 1, (31, 30, 29), torch.float32, torch.uint8),
+                                                 (7, 2, (20, 21, 22), torch.float64, torch.int32)])
+def test_test_metrics_vs_oracle(vb, vo, c, r, shape, dtype, ldt):
+    """calculate_test_metrics (test_3D.py:250-281; SoftDiceLoss loss_modules.py:7-90 + NLLLoss + Dice) against
+    the oracle, whose loss half is pinned to the reference (tests/test_oracle_vs_reference.py)."""
+    g = torch.Generator().manual_seed(c * 7 + r)
+    x = torch.softmax(2 * torch.randn(1, c, *shape, generator=g, dtype=torch.float64), dim=1).to(dtype)
+    gt = torch.randint(0, c, (r,) + shape, generator=g)
+    want = vo.calculate_test_metrics(x, gt)
+    got = vb.calculate_test_metrics(x.cuda(), gt.to(ldt).cuda())
+    tol = 1e-12 if dtype == torch.float64 else 2e-6      # the reference sums fp32 inputs in fp32, the kernel in fp64
+    np.testing.assert_allclose(got["loss"], want["loss"], rtol=tol)
+    np.testing.assert_allclose(got["dice"], want["dice"], rtol=1e-12)
+    # the raw sums of the kernel against numpy
+    terms = vb.seg_loss_terms(x[0].reshape(c, -1).cuda(), gt.reshape(r, -1).to(ldt).cuda()).cpu().numpy()
+    ct = 2 if c <= 2 else (4 if c <= 4 else 8)
+    xn, gn = x[0].reshape(c, -1).double().numpy(), gt.reshape(r, -1).numpy()
+    for rr in range(r):
+        for cc in range(c):
+            np.testing.assert_allclose(terms[rr, cc], xn[cc][gn[rr] == cc].sum(), rtol=1e-12)
+            assert terms[rr, ct + cc] == float((gn[rr] == cc).sum())
+            np.testing.assert_allclose(terms[rr, 2 * ct + cc], xn[cc].sum(), rtol=1e-12)
+        np.testing.assert_allclose(terms[rr, 3 * ct], np.log(np.take_along_axis(xn, gn[rr][None], 0)).sum(), rtol=1e-12)
+    # a probability of exactly 0 under the label: -inf log, +inf loss, as torch
+    x0 = x.clone()
+    x0[0, int(gt[0].reshape(-1)[0])].view(-1)[0] = 0.0
+    assert vb.calculate_test_metrics(x0.cuda(), gt[:1].to(ldt).cuda())["loss"] == float("inf")
+    assert vo.calculate_test_metrics(x0, gt[:1])["loss"] == float("inf")
+
+
 @pytest.mark.parametrize("n,c,r,shape,ignore", [(5, 2, 4, (40, 36, 32), 0), (10, 4, 3, (48, 64), 0),
                                                  (3, 3, 1, (20, 20, 20), 0), (4, 3, 2, (24, 24, 24), 1)])
 def test_ged_vs_oracle(vb, vo, n, c, r, shape, ignore):

@@ -46,6 +46,27 @@ def test_c3_random(ref):
         assert float(ra["max_score"]) == float(rb["max_score"])
 
 
+@pytest.mark.parametrize("c,r,shape,dtype", [(2, 4, (12, 11, 10), torch.float64), (4, 2, (20, 18), torch.float64),
+                                             (2, 1, (9, 9, 9), torch.float32)])
+def test_f2_test_metrics_loss_is_the_reference_loss(ref, c, r, shape, dtype):
+    """calculate_test_metrics (test_3D.py:250-281) run UNMODIFIED, with only the absent torchmetrics `dice`
+    bound to the oracle's dice_micro: the SoftDiceLoss + NLLLoss half of the oracle is pinned bit for bit."""
+    t3d = ref.modules["test_3D"]
+    g = torch.Generator().manual_seed(c * 10 + r)
+    x = torch.softmax(2 * torch.randn(1, c, *shape, generator=g, dtype=torch.float64), dim=1).to(dtype)
+    gt = torch.randint(0, c, (r,) + shape, generator=g)
+    saved = t3d.dice
+    t3d.dice = lambda p, t, ignore_index=None: torch.tensor(
+        vo.dice_micro(torch.argmax(p, dim=1).numpy(), t.numpy(), p.shape[1], ignore_index), dtype=torch.float64)
+    try:
+        want = t3d.calculate_test_metrics(x, gt)
+    finally:
+        t3d.dice = saved
+    got = vo.calculate_test_metrics(x, gt)
+    assert got["loss"] == want["loss"] and got["dice"] == want["dice"]
+    assert float(t3d.SoftDiceLoss()(x, gt[:1])) == float(vo.soft_dice_loss(x, gt[:1]))
+
+
 def test_k4_stats_random(ref):
     rng = np.random.default_rng(11)
     for dt in (np.float64, np.float32):

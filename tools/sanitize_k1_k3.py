@@ -6,7 +6,7 @@
 K1: every ring shape (rows per stage 8 / 4 / 5 / 2 / 1, fp32 / bf16 / fp64 with per-sample accumulators),
 ragged last tiles, several tiles per CTA, and the register-stream / sample-outer variants the ring is
 checked against.  K3: vector and scalar kernels, overlapping patches, a volume with an uncovered
-remainder, the weighted form."""
+remainder, the weighted form (importance map and separable factors)."""
 import os
 import sys
 
@@ -49,7 +49,10 @@ for shape, p, ov in [((24, 20, 16), 8, 0.5), ((21, 19, 18), 8, 0.5), ((16, 16, 1
     torch.cuda.synchronize()
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), shape
     w = vb.gaussian_importance_map((p, p, p), device="cuda")
-    vb.stitch_volume(patches, crops, shape, weight=w)
+    wa = vb.stitch_volume(patches, crops, shape, weight=w)
+    fa = vb.stitch_volume(patches, crops, shape, weight=vb.gaussian_importance_factors((p, p, p), device="cuda"))
+    torch.cuda.synchronize()
+    assert torch.equal(wa[0], fa[0]) and torch.equal(wa[1], fa[1]), ("separable weights", shape)
     carrier_sum = torch.zeros((3, 2) + shape, dtype=torch.float64, device="cuda")
     cnt = torch.zeros(shape, dtype=torch.float64, device="cuda")
     vb.stitch_accumulate(patches, vb.stitching.crops_to_lo(crops, "cuda"), carrier_sum, cnt, accumulate=True)

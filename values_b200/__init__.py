@@ -16,7 +16,8 @@ from .data_carrier import DataCarrier3D
 from .metrics import (calc_ace, calib_stats, calibration_error, calibration_error_image,
                       compute_ncc, ncc_batched, ncc_main, platt_scale_confid)
 from .pipeline import AggregationConfig, PipelineResult, UncertaintyPipeline
-from .segmetrics import calculate_ged, confusion_counts, dice_from_confusion, mean_prediction_dice
+from .segmetrics import (calculate_ged, calculate_test_metrics, confusion_counts, dice_from_confusion,
+                         mean_prediction_dice, seg_loss_terms)
 from .sharding import AsyncScoreGather, gather_scores, shard_range, shard_sizes
 from .stitching import gaussian_importance_factors, gaussian_importance_map, importance_map_from_factors, patch_grid, stitch_accumulate, stitch_volume
 from .threshold import (calculate_foreground_quantile_image, calculate_threshold_image,
@@ -38,6 +39,6 @@ __all__ = [
     "calculate_threshold_image", "find_threshold", "quantile", "count_nonzero",
     "compute_ncc", "ncc_batched", "ncc_main", "calib_stats", "calc_ace", "platt_scale_confid",
     "calibration_error_image", "calibration_error",
-    "calculate_ged", "confusion_counts", "dice_from_confusion", "mean_prediction_dice",
+    "calculate_ged", "calculate_test_metrics", "seg_loss_terms", "confusion_counts", "dice_from_confusion", "mean_prediction_dice",
     "formats", "ExperimentDataloader", "load_to_device", "save_from_device", "reverse_axes",
 ]

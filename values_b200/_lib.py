@@ -55,6 +55,8 @@ def _load() -> C.CDLL:
         "values_stitch_accumulate_separable": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, vp, vp, vp, i64, i64, i64,
                                                          pi64, pi64, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
         "values_normalize_maps": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, dbl, vp, vp]),
+        "values_seg_loss_workspace_bytes": (sz, [i64, C.c_int, i64]),
+        "values_seg_loss_terms": (C.c_int, [vp, C.c_int, i64, vp, C.c_int, i64, i64, C.c_int, i64, vp, vp, sz, vp]),
         "values_count_nonzero": (C.c_int, [vp, C.c_int, i64, vp, vp]),
         "values_radix_histogram": (C.c_int, [vp, C.c_int, i64, C.c_uint64, C.c_int, C.c_int, vp, vp]),
         "values_min_key_above": (C.c_int, [vp, C.c_int, i64, C.c_uint64, vp, vp]),
@@ -90,6 +92,7 @@ EXPORTED = [
     "values_pair_moments_workspace_bytes", "values_pair_moments",
     "values_calib_bins_workspace_bytes", "values_calib_bins", "values_calib_bins_fused",
     "values_confusion_counts", "values_reverse_axes", "values_patch_filter_err_coef",
+    "values_seg_loss_workspace_bytes", "values_seg_loss_terms",
 ]
 
 

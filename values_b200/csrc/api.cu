@@ -54,6 +54,12 @@ int launch_reduce_partials(const double* partials, int64_t n_items, int64_t n_bl
         reduce_partials_kernel<5><<<(unsigned)n_items, kThreads, 0, stream>>>(partials, n_blocks, out);
     else if (K == 3)
         reduce_partials_kernel<3><<<(unsigned)n_items, kThreads, 0, stream>>>(partials, n_blocks, out);
+    else if (K == 7)     // seg_loss_terms, CT = 2 / 4 / 8
+        reduce_partials_kernel<7><<<(unsigned)n_items, kThreads, 0, stream>>>(partials, n_blocks, out);
+    else if (K == 13)
+        reduce_partials_kernel<13><<<(unsigned)n_items, kThreads, 0, stream>>>(partials, n_blocks, out);
+    else if (K == 25)
+        reduce_partials_kernel<25><<<(unsigned)n_items, kThreads, 0, stream>>>(partials, n_blocks, out);
     else
         return set_error(VALUES_ERR_INVALID_ARG, "reduce_partials: K=%d", K);
     return check_launch("reduce_partials_kernel");

@@ -473,6 +473,57 @@ static int stat_grid(int64_t n_units) {
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
+// =============================================================================== seg_loss_terms
+// The sums behind calculate_test_metrics (uncertainty_modeling/test_3D.py:250-281): per rater r of a label
+// stack [R, V] against ONE probability map [C, V] (the mean softmax prediction),
+//   inter[r][c] = sum_v x[c][v] [gt_r[v] == c]      SoftDiceLoss intersect   loss_modules.py:56-66, 86
+//   count[r][c] = #{ v : gt_r[v] == c }             (x + onehot).sum = sumx + count            :87
+//   sumx[c]     = sum_v x[c][v]                     (stored per rater row)
+//   logp[r]     = sum_v log x[gt_r[v]][v]           torch.nn.NLLLoss(torch.log(x), gt) numerator, log in fp64
+// in one sweep, fp64 fixed-order block-then-grid reduction.  A label outside [0, C) makes logp NaN (torch
+// raises there).  partials [R, blocks, 3 CT + 1]; CT = C rounded up to 2, 4 or 8.
+template <typename T, typename L, int CT>
+__global__ void __launch_bounds__(kThreads) seg_loss_kernel(const T* __restrict__ probs, int64_t stride_c,
+                                                            const L* __restrict__ labels, int64_t stride_r, int C,
+                                                            int64_t V, int64_t bpm, double* __restrict__ partials) {
+    constexpr int K = 3 * CT + 1;
+    __shared__ double red[K * 8];
+    const int64_t r = blockIdx.x / bpm;
+    const int64_t blk = blockIdx.x - r * bpm;
+    const L* lab = labels + r * stride_r;
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    const int64_t base = blk * (int64_t)(kThreads * kStatEPT) + threadIdx.x;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll 2
+    for (int i = 0; i < kStatEPT; ++i) {
+        const int64_t v = base + (int64_t)i * kThreads;
+        if (v < V) {
+            const long long l = (long long)ld_elem(lab + v);
+            double xl = qnan;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                if (c < C) {
+                    const double x = (double)ld_elem(probs + c * stride_c + v);
+                    const bool hit = l == c;
+                    acc[c] += hit ? x : 0.0;
+                    acc[CT + c] += hit ? 1.0 : 0.0;
+                    acc[2 * CT + c] += x;
+                    xl = hit ? x : xl;
+                }
+            }
+            acc[3 * CT] += log(xl);
+        }
+    }
+    block_sum<K>(acc, red);
+    if (threadIdx.x == 0) {
+        double* dst = partials + (int64_t)blockIdx.x * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) dst[k] = acc[k];
+    }
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -711,4 +762,59 @@ extern "C" int values_confusion_counts(const void* labels_a, int64_t Na, int64_t
         default: return set_error(VALUES_ERR_INVALID_ARG, "confusion_counts: labels must be u8, i32 or i64");
     }
     return check_launch("confusion_kernel");
+}
+
+static int seg_loss_ct(int C) { return C <= 2 ? 2 : (C <= 4 ? 4 : 8); }
+
+extern "C" size_t values_seg_loss_workspace_bytes(int64_t R, int C, int64_t V) {
+    if (R <= 0 || V <= 0 || C <= 0 || C > 8) return 0;
+    return (size_t)(R * ceil_div(V, kThreads * kStatEPT) * (3 * seg_loss_ct(C) + 1)) * sizeof(double);
+}
+
+template <typename T, typename L>
+static void launch_seg_loss(const void* probs, int64_t stride_c, const void* labels, int64_t stride_r, int C,
+                            int64_t V, int64_t bpm, unsigned grid, double* partials, cudaStream_t st) {
+    const T* p = (const T*)probs;
+    const L* l = (const L*)labels;
+    switch (seg_loss_ct(C)) {
+        case 2: seg_loss_kernel<T, L, 2><<<grid, kThreads, 0, st>>>(p, stride_c, l, stride_r, C, V, bpm, partials); break;
+        case 4: seg_loss_kernel<T, L, 4><<<grid, kThreads, 0, st>>>(p, stride_c, l, stride_r, C, V, bpm, partials); break;
+        default: seg_loss_kernel<T, L, 8><<<grid, kThreads, 0, st>>>(p, stride_c, l, stride_r, C, V, bpm, partials); break;
+    }
+}
+
+extern "C" int values_seg_loss_terms(const void* probs, int dtype, int64_t stride_c, const void* labels,
+                                     int label_dtype, int64_t stride_r, int64_t R, int C, int64_t V,
+                                     double* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (R < 0 || V < 0 || C < 1) return set_error(VALUES_ERR_INVALID_ARG, "seg_loss_terms: bad sizes");
+    if (C > 8) return set_error(VALUES_ERR_UNSUPPORTED, "seg_loss_terms: C = %d > 8 classes", C);
+    if (dtype != VALUES_F32 && dtype != VALUES_F64)
+        return set_error(VALUES_ERR_INVALID_ARG, "seg_loss_terms: probabilities must be f32 or f64");
+    if (R == 0) return VALUES_OK;
+    if (!out) return set_error(VALUES_ERR_INVALID_ARG, "seg_loss_terms: NULL output");
+    const int K = 3 * seg_loss_ct(C) + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (V == 0) {
+        if (cudaMemsetAsync(out, 0, (size_t)R * K * sizeof(double), st) != cudaSuccess)
+            return set_error(VALUES_ERR_CUDA, "seg_loss_terms: memset failed");
+        return VALUES_OK;
+    }
+    if (!probs || !labels) return set_error(VALUES_ERR_INVALID_ARG, "seg_loss_terms: NULL input");
+    const size_t need = values_seg_loss_workspace_bytes(R, C, V);
+    if (!workspace || workspace_bytes < need)
+        return set_error(VALUES_ERR_WORKSPACE, "seg_loss_terms: workspace %zu < %zu", workspace_bytes, need);
+    const int64_t bpm = ceil_div(V, kThreads * kStatEPT);
+    if (bpm * R > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "seg_loss_terms: grid too large");
+    const unsigned grid = (unsigned)(bpm * R);
+    double* partials = reinterpret_cast<double*>(workspace);
+#define VB_SEGLOSS(T) do { switch (label_dtype) { \
+        case VALUES_U8: launch_seg_loss<T, uint8_t>(probs, stride_c, labels, stride_r, C, V, bpm, grid, partials, st); break; \
+        case VALUES_I32: launch_seg_loss<T, int32_t>(probs, stride_c, labels, stride_r, C, V, bpm, grid, partials, st); break; \
+        case VALUES_I64: launch_seg_loss<T, int64_t>(probs, stride_c, labels, stride_r, C, V, bpm, grid, partials, st); break; \
+        default: return set_error(VALUES_ERR_INVALID_ARG, "seg_loss_terms: labels must be u8, i32 or i64"); } } while (0)
+    if (dtype == VALUES_F32) VB_SEGLOSS(float); else VB_SEGLOSS(double);
+#undef VB_SEGLOSS
+    int rc = check_launch("seg_loss_kernel");
+    if (rc) return rc;
+    return launch_reduce_partials(partials, R, bpm, K, out, st);
 }

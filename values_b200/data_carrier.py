@@ -266,13 +266,13 @@ def calculate_metrics(test_datacarrier) -> None:
     """Drop-in for calculate_metrics (uncertainty_modeling/test_3D.py:537-575) on a device-resident
     carrier: the mean softmax prediction and the rater labels are normalised on the GPU
     (`normalize_maps`, the `/ clip(count, 1)` of :545-547, 553-566); GED / max-Dice come from
-    values_b200.segmetrics.calculate_ged; the SoftDice + NLL loss and Dice of the mean prediction
-    (calculate_test_metrics, test_3D.py:250-281 -- model quality, not on the hot path) are taken from
-    the reference module when it is imported, on the host as the reference does.  A reference
-    (numpy) DataCarrier3D is passed through to the reference's own function."""
+    values_b200.segmetrics.calculate_ged, the SoftDice + NLL loss and the Dice of the mean prediction
+    (calculate_test_metrics, test_3D.py:250-281) from values_b200.segmetrics.calculate_test_metrics --
+    all on the device.  A reference (numpy) DataCarrier3D is passed through to the reference's own
+    function."""
     import sys
 
-    from .segmetrics import calculate_ged
+    from .segmetrics import calculate_ged, calculate_test_metrics
 
     ref = sys.modules.get("uncertainty_modeling.test_3D") or sys.modules.get("test_3D")
     if not isinstance(test_datacarrier, DataCarrier3D):
@@ -288,10 +288,9 @@ def calculate_metrics(test_datacarrier) -> None:
         sm = normalize_maps(value["softmax_pred"].reshape((n_pred * n_cls,) + size), cnt, clip_min)
         sm = sm.reshape((n_pred, n_cls) + size)
         metrics_dict = {}
-        if ref is not None and hasattr(ref, "calculate_test_metrics"):
+        if value["seg"].shape[0] > 0 and n_cls <= 8:
             # :545-552 -- the reference averages RAW sums / count over samples, gt = raw label sums
-            mean_sm = torch.mean(sm, dim=0).unsqueeze(0).cpu()
-            metrics_dict.update(ref.calculate_test_metrics(mean_sm, value["seg"].cpu()))
+            metrics_dict.update(calculate_test_metrics(torch.mean(sm, dim=0), value["seg"]))
         if value["seg"].shape[0] > 1 or n_pred > 1:
             gt = normalize_maps(value["seg"].to(torch.float64), cnt, clip_min).to(torch.int32)   # np.asarray(.., intc)
             metrics_dict.update(calculate_ged(sm, gt))

@@ -16,6 +16,7 @@ _PATCHES = {
         "calculate_one_minus_msr": uncertainty.calculate_one_minus_msr,
         "caculcate_uncertainty_multiple_pred": uncertainty.caculcate_uncertainty_multiple_pred,
         "calculate_ged": segmetrics.calculate_ged,
+        "calculate_test_metrics": segmetrics.calculate_test_metrics,
         "calculate_metrics": data_carrier.calculate_metrics,
         "DataCarrier3D": data_carrier.DataCarrier3D,
     },

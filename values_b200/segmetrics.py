@@ -11,7 +11,9 @@ vendored under the reference and not installed in the build image, and the refer
 for it.  `dice_from_confusion` restates torchmetrics' documented micro-average Dice
 (2 tp / (2 tp + fp + fn) over the classes left after dropping `ignore_index`, zero_division = 0);
 the counts are exact integers, the ratios are evaluated in fp64 (torchmetrics divides in fp32).
-The SoftDice + NLL loss of calculate_test_metrics (test_3D.py:250-281) is not covered.
+The SoftDice + NLL loss of calculate_test_metrics (test_3D.py:250-281) is `calculate_test_metrics` below
+(kernel `values_seg_loss_terms`); that part IS pinned: against the reference's own SoftDiceLoss
+(uncertainty_modeling/loss_modules.py:7-90) and torch.nn.NLLLoss, tests/test_oracle_vs_reference.py.
 """
 from __future__ import annotations
 
@@ -117,3 +119,57 @@ def mean_prediction_dice(mean_argmax: torch.Tensor, ground_truth: torch.Tensor, 
     pred = mean_argmax.reshape(1, -1).to(gt.dtype)
     conf = confusion_counts(pred, gt, n_classes).cpu().numpy()
     return float(np.mean([dice_from_confusion(conf[0, r], ignore_index) for r in range(gt.shape[0])]))
+
+
+def seg_loss_terms(probs: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """probs [C, V] (CUDA fp32 / fp64), labels [R, V] (CUDA u8 / i32 / i64) -> fp64 [R, 3 CT + 1] on the
+    device, CT = C rounded up to 2, 4 or 8: per rater {intersect[c], count[c], sum_x[c]} and
+    sum_v log probs[label_v][v] (include/values_b200.h, values_seg_loss_terms).  One sweep, no sync."""
+    if probs.device.type != "cuda" or labels.device.type != "cuda":
+        raise RuntimeError("seg_loss_terms expects CUDA tensors (no CPU fallback)")
+    C, V = probs.shape
+    R = labels.shape[0]
+    if labels.shape[1] != V:
+        raise ValueError("seg_loss_terms: probabilities and labels must cover the same voxels")
+    probs, labels = probs.contiguous(), labels.contiguous()
+    ct = 2 if C <= 2 else (4 if C <= 4 else 8)
+    out = torch.empty((R, 3 * ct + 1), dtype=torch.float64, device=probs.device)
+    ws_bytes = _lib.lib.values_seg_loss_workspace_bytes(R, C, V)
+    ws = torch.empty((max(1, ws_bytes),), dtype=torch.uint8, device=probs.device)
+    with torch.cuda.device(probs.device):
+        rc = _lib.lib.values_seg_loss_terms(probs.data_ptr(), _lib.dtype_code(probs.dtype), V, labels.data_ptr(),
+                                            _lib.label_dtype_code(labels.dtype), V, R, int(C), V, out.data_ptr(),
+                                            ws.data_ptr(), ws_bytes, _lib.stream_ptr(probs.device))
+    _lib.check(rc)
+    return out
+
+
+def calculate_test_metrics(output_softmax: torch.Tensor, ground_truth: torch.Tensor, ignore_index: int = 0,
+                           smooth: float = 1e-5) -> Dict[str, float]:
+    """Drop-in for calculate_test_metrics (uncertainty_modeling/test_3D.py:250-281): per rater
+    SoftDiceLoss()(x, gt) + NLLLoss()(log x, gt) and torchmetrics `dice(x, gt, ignore_index=0)`, averaged over
+    the raters.  output_softmax [1, C, *S] (or [C, *S]), ground_truth [R, *S] integer labels < C, C <= 8.
+    The sums come from one sweep of `values_seg_loss_terms` (fp64; the reference sums in the input dtype),
+    the Dice from the confusion counts of the arg-max (first maximum wins, as torch.argmax); the few
+    scalars after that are host arithmetic."""
+    dev = _lib.require_cuda()
+    x = output_softmax if isinstance(output_softmax, torch.Tensor) else torch.from_numpy(np.asarray(output_softmax))
+    if x.device != dev:
+        x = x.to(dev)
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.float()
+    gt = _labels(ground_truth, dev)
+    if x.dim() == gt.dim() + 1:          # [1, C, *S] against [R, *S]
+        if x.shape[0] != 1:
+            raise ValueError("calculate_test_metrics: one prediction (batch 1) against R raters")
+        x = x[0]
+    n_cls, n_rater = x.shape[0], gt.shape[0]
+    V = x[0].numel()
+    ct = 2 if n_cls <= 2 else (4 if n_cls <= 4 else 8)
+    terms = seg_loss_terms(x.reshape(n_cls, V), gt.reshape(n_rater, V)).cpu().numpy()
+    inter, count, sumx, logp = terms[:, :n_cls], terms[:, ct:ct + n_cls], terms[:, 2 * ct:2 * ct + n_cls], terms[:, 3 * ct]
+    soft_dice = np.mean(-((2.0 * inter + smooth) / (sumx + count + smooth)), axis=1)      # loss_modules.py:86-90
+    nll = -logp / V                                                                       # NLLLoss, mean reduction
+    pred = uncertainty_fused(x.reshape((1, 1, n_cls) + tuple(x.shape[1:])), maps=False, mean_argmax=True).mean_argmax[0]
+    return {"loss": float(np.mean(soft_dice + nll)),
+            "dice": mean_prediction_dice(pred, gt, n_cls, ignore_index)}
