@@ -265,8 +265,70 @@ def patch_grid_cases():
     print("patch_grid", len(out), "cases,", sum(len(c["crops"]) for c in out), "crops")
 
 
+def process_output_2d_case():
+    """The 2-D caller: the reference's own Tester.process_output (uncertainty_modeling/test_2D.py:204-254) and
+    the calculate_test_metrics / calculate_ged it calls, run UNMODIFIED on one synthetic test batch with a bare
+    object standing in for the Tester (device, ignore_index, results_dict; the two file writers record their
+    arguments instead of writing).  torchmetrics is absent: `dice` is bound to the oracle's dice_micro in both
+    modules, so the Dice numbers are the oracle's while everything else (zero channel, relabelling, slicing,
+    means, which maps go where) is the reference's."""
+    import importlib
+    import types
+
+    from oracle import values_oracle as vo
+
+    ref_loader.load()
+    t2d = importlib.import_module("uncertainty_modeling.test_2D")
+    t3d = importlib.import_module("uncertainty_modeling.test_3D")
+
+    def micro(preds, target, ignore_index=None):
+        p = torch.argmax(preds, dim=1) if preds.dim() == target.dim() + 1 else preds
+        n_cls = preds.shape[1] if preds.dim() == target.dim() + 1 else int(max(p.max(), target.max())) + 1
+        return torch.tensor(vo.dice_micro(p.numpy(), target.numpy(), n_cls, ignore_index), dtype=torch.float64)
+
+    gen = torch.Generator().manual_seed(77)
+    out = {}
+    for name, n, b, c, hw, ssn in (("mc", 4, 3, 5, (24, 40), False), ("ssn", 3, 2, 4, (16, 24), True), ("single", 1, 2, 3, (12, 20), False)):
+        base = 2.0 * torch.randn(1, b, c, *hw, generator=gen)
+        sm = torch.softmax(base + torch.randn(n, b, c, *hw, generator=gen), dim=2)
+        gt = torch.argmax(base[0], dim=1, keepdim=True)
+        flip = torch.rand(gt.shape, generator=gen) < 0.15
+        gt = torch.where(flip, (gt + 1) % c, gt)
+        gt[torch.rand(gt.shape, generator=gen) < 0.1] = 255
+        saved = {"pred": {}, "unc": {}}
+        fake = types.SimpleNamespace(device="cpu", ignore_index=255, results_dict={})
+        fake.calculate_test_metrics = types.MethodType(t2d.Tester.calculate_test_metrics, fake)
+        fake.save_prediction = lambda image_id, image_preds, mean_pred, ign, _s=saved: _s["pred"].__setitem__(
+            image_id, (torch.argmax(mean_pred, dim=0).numpy().astype(np.uint8),
+                       torch.argmax(image_preds, dim=1).numpy().astype(np.uint8), ign[..., 0].astype(bool)))
+        fake.save_uncertainty = lambda image_id, d, _s=saved: _s["unc"].__setitem__(
+            image_id, {k: v.numpy() for k, v in d.items()})
+        keep = (t2d.dice, t3d.dice)
+        t2d.dice = t3d.dice = micro
+        try:
+            t2d.Tester.process_output(fake, {"softmax_pred": sm.clone(), "gt": gt.clone(),
+                                             "image_id": [f"{name}_{i}" for i in range(b)],
+                                             "dataset": ["synthetic"] * b}, ssn)
+        finally:
+            t2d.dice, t3d.dice = keep
+        out[name + "/softmax_pred"], out[name + "/gt"] = sm.numpy(), gt.numpy().astype(np.int64)
+        out[name + "/ssn"] = np.asarray(ssn)
+        for i in range(b):
+            key = f"{name}_{i}"
+            for m, v in fake.results_dict[key]["metrics"].items():
+                out[f"{name}/{i}/metrics/{m}"] = np.asarray(v, dtype=np.float64)
+            out[f"{name}/{i}/mean_argmax"], out[f"{name}/{i}/sample_argmax"], out[f"{name}/{i}/ignore"] = saved["pred"][key]
+            for k, v in saved["unc"][key].items():
+                out[f"{name}/{i}/unc/{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "process_output_2d.npz"), **out)
+    print("process_output_2d", len(out), "arrays")
+
+
 def main():
     ref = ref_loader.load()
+    if "--only-2d" in sys.argv:
+        process_output_2d_case()
+        return
     if "--only-k4" in sys.argv:
         k4_cases(ref)
         return

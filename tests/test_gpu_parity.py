@@ -605,6 +605,14 @@ def test_stitch_gaussian_weighted(vb, vo, stitch_path):
     want = ref_total / np.where(ref_cnt > 0, ref_cnt, 1.0)
     np.testing.assert_allclose(norm, want, rtol=1e-15)
     assert np.all(norm[:, :, :, 32:, :] == 0) and np.all(ref_cnt[:, 32:, :] == 0)
+    # the same carrier fed with the separable factors of the map: bit-identical accumulators
+    carrier_f = vb.DataCarrier3D(patch_weight=vb.gaussian_importance_factors((p, p, p)), stitch_path=stitch_path)
+    for pred_idx in range(2):
+        batch = {"image_paths": ["v"] * len(crops), "label_paths": [None] * len(crops),
+                 "org_image_size": [shape] * len(crops), "crop_idx": crops, "data": None, "seg": None}
+        carrier_f.concat_data(batch, patches[pred_idx], n_pred=2, pred_idx=pred_idx)
+    assert torch.equal(carrier_f.data["v"]["softmax_pred"], carrier.data["v"]["softmax_pred"])
+    assert torch.equal(carrier_f.data["v"]["_count"], carrier.data["v"]["_count"])
 
 
 def test_stitch_separable_weights(vb, vo, stitch_path):

@@ -9,7 +9,7 @@ from . import _lib  # noqa: F401  (raises ValuesExtensionMissing when the .so is
 from .aggregation import (aggregate_uncertainties, image_level_aggregation, map_reduce,
                           normalize_maps, patch_level_aggregation, patch_max,
                           threshold_aggregation)
-from . import formats, metrics, segmetrics, threshold
+from . import formats, metrics, segmetrics, tester2d, threshold
 from .experiment_dataloader import ExperimentDataloader
 from .formats import load_to_device, reverse_axes, save_from_device
 from .data_carrier import DataCarrier3D

@@ -86,9 +86,15 @@ def calculate_ged(output_softmax: torch.Tensor, ground_truth: torch.Tensor, igno
     n_rater = gt.shape[0]
     # per-sample arg-max: one sweep of the stack (first maximum wins, as torch.argmax)
     pred = uncertainty_fused(sm.unsqueeze(0), maps=False, sample_argmax=True).sample_argmax[0]
-    pred = pred.reshape(n_pred, -1)
-    gt_flat = gt.reshape(n_rater, -1).to(torch.uint8) if n_cls <= 255 and int(gt.max()) < 256 and int(gt.min()) >= 0 \
-        else gt.reshape(n_rater, -1)
+    return ged_from_labels(pred.reshape(n_pred, -1), gt.reshape(n_rater, -1), n_cls, ignore_index, ged_only)
+
+
+def ged_from_labels(pred: torch.Tensor, gt: torch.Tensor, n_cls: int, ignore_index: int = 0,
+                    ged_only: bool = False) -> Dict[str, float]:
+    """The arithmetic of calculate_ged (test_3D.py:290-358) on label maps: pred [N, V] (the per-sample arg-max),
+    gt [R, V] (CUDA integer labels < n_cls).  Three launches of the confusion-count kernel, the rest on the host."""
+    n_pred, n_rater = pred.shape[0], gt.shape[0]
+    gt_flat = gt.to(torch.uint8) if n_cls <= 255 and gt.dtype != torch.uint8 and int(gt.max()) < 256 and int(gt.min()) >= 0 else gt
     if gt_flat.dtype != pred.dtype:
         pred = pred.to(gt_flat.dtype)
     conf_pg = confusion_counts(pred, gt_flat, n_cls).cpu().numpy()      # [N, R, C, C]
