@@ -377,11 +377,17 @@ template <int VEC> __device__ __forceinline__ uint32_t sign_or(const Raw<float, 
     for (int j = 0; j < VEC; ++j) s |= r.w[j];
     return s;
 }
+// bf16: two elements per word, signs at bits 15 and 31 -- the words are OR-ed as they are (one LOP3 per two
+// words instead of a shift and an OR per word) and bit 15 is folded onto bit 31 once per voxel (fold_sign)
 template <int VEC> __device__ __forceinline__ uint32_t sign_or(const Raw<__nv_bfloat16, VEC>& r) {
     uint32_t s = 0;
 #pragma unroll
-    for (int j = 0; j < Raw<__nv_bfloat16, VEC>::WORDS; ++j) s |= r.w[j] | (r.w[j] << 16);
+    for (int j = 0; j < Raw<__nv_bfloat16, VEC>::WORDS; ++j) s |= r.w[j];
     return s;
+}
+template <typename T> __device__ __forceinline__ uint32_t fold_sign(uint32_t bad) {
+    if constexpr (sizeof(T) == 2) return bad | (bad << 16);
+    else return bad;
 }
 template <int VEC> __device__ __forceinline__ uint32_t sign_or(const Raw<double, VEC>&) { return 0; }
 
@@ -704,6 +710,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k1_stream_kernel(const K1Param
             for (int j = 0; j < VEC; ++j)
                 bad |= ((__float_as_uint(Sacc[j]) & 0x7f800000u) == 0x7f800000u) ? 0x80000000u : 0u;
         }
+        bad = fold_sign<T>(bad);
         if (M::kFlagged && (bad & 0x80000000u)) {
             k1_entropy_exact<T, VEC>(base, N, C, prm.sn, prm.sc, E);
 #pragma unroll
@@ -926,6 +933,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
                 bad |= ((__float_as_uint(Sacc[j]) & 0x7f800000u) == 0x7f800000u) ? 0x80000000u : 0u;
+            bad = fold_sign<T>(bad);
             if (bad & 0x80000000u) {
                 k1_entropy_exact<T, VEC>(reinterpret_cast<const T*>(vol) + v0, N, C, prm.sn, prm.sc, E);
 #pragma unroll
