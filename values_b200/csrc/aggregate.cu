@@ -1243,6 +1243,11 @@ box_strip_filter_kernel(const __grid_constant__ CUtensorMap tmap, const FusedPar
             for (int f = written; f < prm.zsub; ++f) prm.tile_max[m * prm.nent + tile * prm.zsub + f] = ninf;
         }
     }
+    __syncthreads();
+    if (tid == 0) {   // the march is over for every warp: the ring's barriers are idle (common.cuh, mbar_inval)
+#pragma unroll
+        for (int s = 0; s < ST::NSTAGE; ++s) { mbar_inval(full_bar + s); mbar_inval(empty_bar + s); }
+    }
     box_pass_finish<0, NT, true>(prm, m, 0.0, ~0ull, red, s_flag, s_count, fabsf(amax),
                                  ctas_per_map);
 }

@@ -132,6 +132,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+// A CTA invalidates its mbarriers before it exits: the next CTA scheduled on the SM finds the same
+// shared-memory words, and PTX leaves re-using a word that still holds a live mbarrier object for anything
+// but that object undefined (mbarrier.init / mbarrier.inval).  Hygiene: no measured effect.
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
     uint32_t done;

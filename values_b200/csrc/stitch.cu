@@ -637,6 +637,10 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
         }
         __syncthreads();
     }
+    if (tid == 0) {   // all copies consumed, all threads past the last block barrier: see mbar_inval
+#pragma unroll
+        for (int s = 0; s < SR::kStages; ++s) { mbar_inval(full_bar + s); mbar_inval(empty_bar + s); }
+    }
 }
 
 // patches [rows = (sample, patch)][C][p0][p1][p2] as a 5-D tensor map with a [1][1][kBX][kBY][kBZ] box

@@ -973,6 +973,13 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
         }
         k1_write_partials<1>(prm, part);
     }
+    // every consumer has passed its last full-barrier wait, so the producer lane has issued its last copy and
+    // every copy has landed: the barriers are idle and can be invalidated (see mbar_inval)
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) { mbar_inval(full_bar + s); mbar_inval(empty_bar + s); }
+    }
 }
 
 // ---- class sums in shared memory (any C); thread-private columns, conflict-free
