@@ -58,4 +58,11 @@ for shape, p, ov in [((24, 20, 16), 8, 0.5), ((21, 19, 18), 8, 0.5), ((16, 16, 1
     vb.stitch_accumulate(patches, vb.stitching.crops_to_lo(crops, "cuda"), carrier_sum, cnt, accumulate=True)
     torch.cuda.synchronize()
     assert torch.equal(carrier_sum, a[0])
+    # the DataCarrier3D form: one sample, a patch_index into a larger batch (row count unknown to the library)
+    sel = torch.arange(len(crops) - 1, -1, -1, dtype=torch.int32, device="cuda")
+    one = torch.zeros((1, 2) + shape, dtype=torch.float64, device="cuda")
+    vb.stitch_accumulate(patches[1:2], vb.stitching.crops_to_lo(crops, "cuda")[sel.long()], one, None,
+                         patch_index=sel, accumulate=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(one[0], a[0][1], rtol=1e-12, atol=0)
 print("sanitize K3: ok")

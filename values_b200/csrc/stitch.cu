@@ -650,9 +650,21 @@ static int make_patch_tensor(const StitchParams& prm, CUtensorMap* tm) {
     if (!enc) return set_error(VALUES_ERR_CUDA, "stitch: cuTensorMapEncodeTiled is not available");
     const cuuint64_t es = sizeof(TP);
     const cuuint64_t pvol = (cuuint64_t)prm.p0 * prm.p1 * prm.p2;
-    // the number of (sample, patch) rows behind the pointer is not known here: any index the caller's
-    // patch_index / sample count can produce is inside the declared extent
-    const cuuint64_t gdim[5] = {(cuuint64_t)prm.p2, (cuuint64_t)prm.p1, (cuuint64_t)prm.p0, (cuuint64_t)prm.C, 0x7fffffffull};
+    // (sample, patch) rows behind the pointer: exact when the patches are taken in order (rows 0 .. n_sel - 1
+    // of every sample) or the samples are whole multiples of a row apart; with a patch_index on a single
+    // sample the row count is not known here: as many rows as the allocation holds
+    const cuuint64_t rps = prm.N > 1 ? (cuuint64_t)(prm.stride_n / prm.stride_p) : 0;
+    cuuint64_t rows = !prm.patch_index ? (cuuint64_t)(prm.N - 1) * rps + (cuuint64_t)prm.n_sel
+                    : prm.N > 1        ? (cuuint64_t)prm.N * rps
+                                       : 0x7fffffffull;
+    // ... and never past the end of the allocation the patches live in (see bytes_to_allocation_end)
+    const size_t room = bytes_to_allocation_end(prm.patches);
+    if (room >= pvol * prm.C * es) {
+        const cuuint64_t fit = (room - pvol * prm.C * es) / ((cuuint64_t)prm.stride_p * es) + 1;
+        if (rows == 0 || fit < rows) rows = fit;
+    }
+    const cuuint64_t gdim[5] = {(cuuint64_t)prm.p2, (cuuint64_t)prm.p1, (cuuint64_t)prm.p0, (cuuint64_t)prm.C,
+                                rows > 0 && rows < 0x7fffffffull ? rows : 0x7fffffffull};
     const cuuint64_t gstr[4] = {(cuuint64_t)prm.p2 * es, (cuuint64_t)prm.p1 * prm.p2 * es, pvol * es,
                                 (cuuint64_t)prm.stride_p * es};
     const cuuint32_t box[5] = {kBZ, kBY, kBX, 1, 1};

@@ -21,4 +21,27 @@ static inline EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+// Bytes from `ptr` to the end of the device allocation that contains it (cuMemGetAddressRange), or 0 when
+// the driver cannot say.  A tensor map's declared extent is kept inside this range: the copies never touch
+// what lies beyond the caller's rows either way, but an extent that runs past the allocation is something
+// compute-sanitizer's synccheck / racecheck instrumentation of the tensor-map copies does not survive
+// (r02: "illegal memory access" with 0 errors reported on a 2^31-row map over a 737 KB tensor).
+typedef CUresult (*AddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+static inline size_t bytes_to_allocation_end(const void* ptr) {
+    static AddressRangeFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<AddressRangeFn>(f);
+    }();
+    if (!fn) return 0;
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    const CUdeviceptr p = reinterpret_cast<CUdeviceptr>(ptr);
+    if (fn(&base, &size, p) != CUDA_SUCCESS || p < base || p - base >= size) return 0;
+    return size - (size_t)(p - base);
+}
+
 }  // namespace vb
