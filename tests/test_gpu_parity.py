@@ -565,6 +565,32 @@ def test_stitch_selected_patches_of_a_padded_stack(vb, vo, stitch_path):
     np.testing.assert_array_equal(cnt.cpu().numpy(), 2 * want_cnt)
 
 
+def test_stitch_one_sample_with_patch_index(vb, vo, stitch_path):
+    """DataCarrier3D's form (data_carrier_3D.py:154-162 per image): ONE sample and a patch_index into a larger
+    batch -- the row count behind the pointer is unknown to the library, so the box kernel's tensor map takes
+    its row extent from the allocation (tma_host.cuh, bytes_to_allocation_end).  The last selected row is the
+    last row of the tensor."""
+    shape, p = (32, 32, 32), 16
+    crops = vo.patch_grid(shape, p, 0.5)
+    g = torch.Generator().manual_seed(21)
+    batch = torch.rand(len(crops) + 3, 2, p, p, p, generator=g, dtype=torch.float32).cuda()
+    sel = list(range(3, len(crops) + 3))[::-1]                 # ends at the last row of the batch
+    lo = vb.stitching.crops_to_lo(crops[::-1], "cuda")
+    out = torch.zeros((1, 2) + shape, dtype=torch.float64, device="cuda")
+    cnt = torch.zeros(shape, dtype=torch.float64, device="cuda")
+    vb.stitch_accumulate(batch.unsqueeze(0), lo, out, cnt, patch_index=torch.tensor(sel, dtype=torch.int32, device="cuda"),
+                         accumulate=True, path=stitch_path)
+    want = np.zeros((2,) + shape)
+    want_cnt = np.zeros(shape)
+    bh = batch.cpu().numpy().astype(np.float64)
+    for i, crop in zip(sel, crops[::-1]):
+        (x0, x1), (y0, y1), (z0, z1) = crop
+        want[:, x0:x1, y0:y1, z0:z1] += bh[i]
+        want_cnt[x0:x1, y0:y1, z0:z1] += 1
+    np.testing.assert_array_equal(out[0].cpu().numpy(), want)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), want_cnt)
+
+
 def test_stitch_many_patches_chunked_list(vb, vo, stitch_path):
     shape, p = (44, 44, 44), 8
     crops = vo.patch_grid(shape, p, 0.25)  # stride 2 -> 19^3 = 6859 patches > list chunk
