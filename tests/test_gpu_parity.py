@@ -143,6 +143,56 @@ def test_k1_kernels_agree(vb, n, c, spatial, dtype):
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("n,c,spatial,dtype", [
+    (16, 4, (31, 33, 29), torch.float32),   # odd voxel count: rows at every 16-byte phase; RS = 4
+    (5, 2, (63, 63, 63), torch.float32),    # RS = 5, many tiles, ragged end
+    (10, 20, (61, 77), torch.float32),      # RS = 5, C = 20
+    (6, 3, (45, 51), torch.float32),        # RS = 2
+    (7, 5, (33, 39), torch.float32),        # RS = 1
+    (3, 2, (7, 5), torch.float32),          # less than one tile
+    (8, 4, (33, 61), torch.bfloat16),       # rows 2 bytes off
+    (16, 4, (21, 23, 25), torch.float64),   # fp64: rows 8 bytes off
+    (8, 2, (31, 49), torch.float64),
+    (5, 2, (33, 31, 29), torch.float64),
+    (10, 3, (41, 37), torch.float64),
+])
+def test_k1_unaligned_stacks_take_the_ring(vb, vo, n, c, spatial, dtype):
+    """Stacks whose rows are not 16-byte aligned (voxel count not a multiple of the vector) run through the
+    bulk-copy ring in its element-strided mode instead of the scalar kernel: maps and arg-max bit-identical
+    to the scalar kernel (variant 1) and the sample-outer kernel (variant 4); the fp64 scores group the
+    voxels differently (1e-13); one volume against the oracle; stale bytes past a ragged end, negative and
+    NaN inputs (the flagged cold paths) included."""
+    x = softmax_stack(n * 5 + c, 3 * n, c, spatial).reshape(3, n, c, *spatial).to(dtype)
+    flat = x.view(3, n, c, -1)
+    if dtype != torch.bfloat16:                    # cold paths: negative, NaN, zero inputs (bf16: the exact
+        flat[1, 0, 0, 3] = -0.25                   # recompute uses the polynomial log for every voxel of the
+        flat[1, n - 1, c - 1, 17] = float("nan")   # flagged thread, the fast path MUFU.LG2: ownership shows)
+    flat[2, 0, 0, -1] = 0.0
+    xg = x.cuda()
+    outs = []
+    for variant, it in [(0, 0), (0, 1), (0, 2), (1, 0), (4, 0)]:
+        r = vb.uncertainty_fused(xg, mean_argmax=True, scores=True, thresholds=(0.5, 0.4, 0.05),
+                                 variant=variant, tiles_per_cta=it)
+        outs.append((r.pred_entropy, r.expected_entropy, r.mutual_information, r.mean_argmax, r.scores))
+    for o in outs[1:]:
+        for a, b in zip(outs[0][:4], o[:4]):
+            assert torch.equal(torch.nan_to_num(a.float(), nan=-7.0), torch.nan_to_num(b.float(), nan=-7.0))
+        np.testing.assert_allclose(o[4][0].cpu().numpy(), outs[0][4][0].cpu().numpy(), rtol=1e-13, atol=0)
+    ref = vo.calculate_uncertainty(x[0].float() if dtype == torch.bfloat16 else x[0])
+    res = vb.uncertainty_fused(xg[:1])
+    if dtype == torch.bfloat16:
+        assert_maps_close(res.as_dict(0), ref, rtol=1e-3, atol=1e-5)
+    else:
+        assert_maps_close(res.as_dict(0), ref)
+    # an offset base: the same stack as a view that starts one element into its storage
+    store = torch.zeros(xg.numel() + 1, dtype=dtype, device="cuda")
+    store[1:] = xg.reshape(-1)
+    view = store[1:].view_as(xg)
+    r2 = vb.uncertainty_fused(view, mean_argmax=True)
+    for a, b in zip(outs[0][:4], (r2.pred_entropy, r2.expected_entropy, r2.mutual_information, r2.mean_argmax)):
+        assert torch.equal(torch.nan_to_num(a.float(), nan=-7.0), torch.nan_to_num(b.float(), nan=-7.0))
+
+
 def test_fp64_class_mean_is_true_division(vb):
     """The fp64 kernels form the class mean as S * RN(1/N) refined by two fmas instead of a division: the
     arg-max of the mean and PE must be those of true division for every magnitude (raw overlap sums can be

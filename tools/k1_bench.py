@@ -24,6 +24,11 @@ SHAPES = {
     "cfg5f64": (16, 4, (128, 128, 128), torch.float64, 8),
     "cfg1": (5, 2, (64, 64, 64), torch.float64, 160),
     "cfg3n8": (8, 2, (256, 256, 256), torch.float64, 2),
+    # volumes whose voxel count is not a multiple of the 16-byte vector: rows start at every phase
+    "odd32": (16, 4, (127, 127, 127), torch.float32, 24),
+    "odd64": (8, 2, (255, 255, 255), torch.float64, 2),
+    "oddbf16": (10, 20, (1023, 2047), torch.bfloat16, 4),
+    "odd2": (5, 2, (63, 63, 63), torch.float32, 512),
 }
 
 

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cstdint>
 
 namespace vb {
 
@@ -27,7 +28,8 @@ static inline EncodeTiledFn encode_tiled_fn() {
 // compute-sanitizer's synccheck / racecheck instrumentation of the tensor-map copies does not survive
 // (r02: "illegal memory access" with 0 errors reported on a 2^31-row map over a 737 KB tensor).
 typedef CUresult (*AddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
-static inline size_t bytes_to_allocation_end(const void* ptr) {
+// [base, base + size) of the device allocation that contains `ptr`; false when the driver cannot say
+static inline bool allocation_range(const void* ptr, uintptr_t* base_out, size_t* size_out) {
     static AddressRangeFn fn = [] {
         void* f = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -36,12 +38,20 @@ static inline size_t bytes_to_allocation_end(const void* ptr) {
             f = nullptr;
         return reinterpret_cast<AddressRangeFn>(f);
     }();
-    if (!fn) return 0;
+    if (!fn) return false;
     CUdeviceptr base = 0;
     size_t size = 0;
     const CUdeviceptr p = reinterpret_cast<CUdeviceptr>(ptr);
-    if (fn(&base, &size, p) != CUDA_SUCCESS || p < base || p - base >= size) return 0;
-    return size - (size_t)(p - base);
+    if (fn(&base, &size, p) != CUDA_SUCCESS || p < base || p - base >= size) return false;
+    *base_out = (uintptr_t)base;
+    *size_out = size;
+    return true;
+}
+static inline size_t bytes_to_allocation_end(const void* ptr) {
+    uintptr_t base = 0;
+    size_t size = 0;
+    if (!allocation_range(ptr, &base, &size)) return 0;
+    return size - (size_t)(reinterpret_cast<uintptr_t>(ptr) - base);
 }
 
 }  // namespace vb

@@ -18,6 +18,7 @@
 // threshold masks (0-2 voxels per 2.1 M at the median threshold).
 // HBM-bound: algorithmic bytes per voxel = N*C*sizeof(T) + 3*4 (+1 arg-max byte).
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace vb {
 
@@ -594,6 +595,43 @@ __device__ __noinline__ void k1_entropy_exact_samples(const T* base, int N, int 
     for (int j = 0; j < VEC; ++j) E_out[j] = E[j];
 }
 
+// SH mode of the ring kernel: element j of a thread is VEC-strided through the tile (voxel tid + 256 j), read
+// from shared memory element by element into the same Raw words the vector path fills
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+template <typename T, int VEC> __device__ __forceinline__ void lds_strided(uint32_t a, Raw<T, VEC>& r) {
+    constexpr uint32_t kStep = (uint32_t)kThreads * (uint32_t)sizeof(T);
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) r.w[j] = lds32(a + j * kStep);
+    } else if constexpr (sizeof(T) == 8) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.w[2 * j]), "=r"(r.w[2 * j + 1]) : "r"(a + j * kStep));
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) {
+            uint16_t lo, hi;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(a + j * kStep));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(a + (j + 1) * kStep));
+            r.w[j / 2] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+    }
+}
+// elements past the ragged end of a volume's last tile read as +0 (no term, no flag)
+template <typename T, int VEC> __device__ __forceinline__ void mask_strided(Raw<T, VEC>& r, int tid, int nvalid) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        if (tid + kThreads * j < nvalid) continue;
+        if constexpr (sizeof(T) == 4) r.w[j] = 0u;
+        else if constexpr (sizeof(T) == 8) { r.w[2 * j] = 0u; r.w[2 * j + 1] = 0u; }
+        else r.w[j / 2] &= (j & 1) ? 0x0000ffffu : 0xffff0000u;
+    }
+}
+
 // S += p, packed two at a time for fp32
 template <int VEC> __device__ __forceinline__ void add_rows(float (&S)[VEC], const float (&p)[VEC]) {
     if constexpr (VEC % 2 == 0) {
@@ -765,13 +803,25 @@ __global__ void __launch_bounds__(kThreads, MINB) k1_stream_kernel(const K1Param
 // fp32 entropy accumulator H[n], so each H_n still adds its classes in index order and EE is their
 // sequential fp32 sum -- the reference's order (test_3D.py:499-507) -- while the rows stream
 // class-outer through the ring like the fp32 path.  Bit-identical to the sample-outer k1_smem_kernel.
-template <typename T, int VEC, int MINB, int RS, int kTmaStages, int NS = 0>
+//
+// SH (stacks whose rows are not 16-byte aligned: a voxel count that is not a multiple of the vector, odd
+// strides, an offset base): every (class, sample) row of a tile starts at its own 16-byte phase, so no
+// thread can read its four voxels of every row as one aligned vector.  The producer copies the aligned
+// 16-byte granules that cover the row's 4 KB (a slot is 16 bytes longer), and a thread owns the voxels
+// tid, tid + 256, tid + 512, ... of the tile instead of VEC consecutive ones: its element of row r sits at
+// slot + phase_r + (tid + 256 j) * sizeof(T) -- element loads, lane-consecutive and conflict-free -- and
+// the maps are written with lane-consecutive element stores.  Same arithmetic per voxel, so maps and
+// arg-max are bit-identical to the other kernels; the fp64 score sums group the voxels differently.
+// The granules before the first and after the last element of the stack are read as well: the host
+// checks that they lie inside the allocation (dispatch_k1, allocation_range).
+template <typename T, int VEC, int MINB, int RS, int kTmaStages, int NS = 0, bool SH = false>
 __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Params prm) {
     using A = typename In<T>::acc_t;
     using M = Math<T>;
     static_assert(VEC * sizeof(T) == 16, "vector path only");
     constexpr int kRowBytes = kThreads * 16;
-    constexpr int kStageBytes = RS * kRowBytes;
+    constexpr int kRowPitch = kRowBytes + (SH ? 16 : 0);
+    constexpr int kStageBytes = RS * kRowPitch;
     extern __shared__ __align__(128) unsigned char ring[];            // [kTmaStages][RS][kRowBytes]
     __shared__ __align__(8) uint64_t full_bar[kTmaStages], empty_bar[kTmaStages];
     __shared__ __align__(16) double2 s_log_tab[NS > 0 ? 513 : 1];     // fp64 stacks: the log table, 8 KB
@@ -807,10 +857,26 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                     const char* row = row_c;
                     for (int n = 0; n < N; n += RS) {
                         mbar_wait(empty_bar + stage, phase ^ 1u);
-                        mbar_expect_tx(full_bar + stage, bytes * RS);
+                        if constexpr (SH) {
+                            // the 16-byte granules covering [row, row + bytes) of every row of the stage
+                            uint32_t total = 0;
+                            const char* r2 = row;
 #pragma unroll
-                        for (int u = 0; u < RS; ++u, row += snb)
-                            bulk_g2s(ring + stage * kStageBytes + u * kRowBytes, row, bytes, full_bar + stage, policy);
+                            for (int u = 0; u < RS; ++u, r2 += snb)
+                                total += (((uint32_t)reinterpret_cast<uintptr_t>(r2) & 15u) + bytes + 15u) & ~15u;
+                            mbar_expect_tx(full_bar + stage, total);
+#pragma unroll
+                            for (int u = 0; u < RS; ++u, row += snb) {
+                                const uint32_t a = (uint32_t)reinterpret_cast<uintptr_t>(row) & 15u;
+                                bulk_g2s(ring + stage * kStageBytes + u * kRowPitch, row - a, (a + bytes + 15u) & ~15u,
+                                         full_bar + stage, policy);
+                            }
+                        } else {
+                            mbar_expect_tx(full_bar + stage, bytes * RS);
+#pragma unroll
+                            for (int u = 0; u < RS; ++u, row += snb)
+                                bulk_g2s(ring + stage * kStageBytes + u * kRowBytes, row, bytes, full_bar + stage, policy);
+                        }
                         if (++stage == kTmaStages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -826,7 +892,9 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
     // (the empty asm makes them opaque): at the 72-register cap it otherwise rebuilds them from
     // %tid / %cluster_ctaid and a 64-bit compare in EVERY stage -- ~20 of 420 instructions, and K1 is
     // issue-bound.
-    uint32_t ring_tid = smem_u32(ring) + (uint32_t)tid * 16u;
+    uint32_t ring_tid = smem_u32(ring) + (uint32_t)tid * (SH ? (uint32_t)sizeof(T) : 16u);
+    // SH: 16-byte phase of the rows, from the low address bits (tiles are whole multiples of 4 KB apart)
+    const uint32_t ph_vol = (uint32_t)reinterpret_cast<uintptr_t>(vol), ph_sn = (uint32_t)snb, ph_sc = (uint32_t)scb;
     uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     int is_lane0 = arrives(lane);
     uint32_t log_tab = smem_u32(s_log_tab);
@@ -842,9 +910,12 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
     for (int it = 0; it < prm.iter; ++it) {
         const int64_t t0 = (blk * prm.iter + it) * tile_vox;
         if (t0 >= prm.V) break;                     // uniform: the producer stops at the same tile
-        const int64_t v0 = t0 + (int64_t)tid * VEC;
+        const int64_t v0 = SH ? t0 + tid : t0 + (int64_t)tid * VEC;
         int active = v0 < prm.V;                    // only the last tile of a volume is ragged
         asm volatile("" : "+r"(active));
+        // SH: voxels of the tile (a thread's element j is voxel tid + 256 j: past a ragged end it is zeroed)
+        const int nvalid = SH ? (int)min(tile_vox, prm.V - t0) : 0;
+        const bool ragged = SH && nvalid < (int)tile_vox;
         A S[VEC], best[VEC];
         float e[VEC], E[VEC], PE[VEC], Sacc[VEC];
         int idx[VEC];
@@ -871,8 +942,14 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                     Raw<T, VEC> raw[SB];
 #pragma unroll
                     for (int u = 0; u < SB; ++u) {
-                        const uint4 q = lds128(ring_tid + stage * kStageBytes + (h + u) * kRowBytes);
-                        raw[u].w[0] = q.x; raw[u].w[1] = q.y; raw[u].w[2] = q.z; raw[u].w[3] = q.w;
+                        if constexpr (SH) {
+                            const uint32_t a = (ph_vol + (uint32_t)c * ph_sc + (uint32_t)(n + h + u) * ph_sn) & 15u;
+                            lds_strided<T, VEC>(ring_tid + stage * kStageBytes + (h + u) * kRowPitch + a, raw[u]);
+                            if (ragged) mask_strided<T, VEC>(raw[u], tid, nvalid);
+                        } else {
+                            const uint4 q = lds128(ring_tid + stage * kStageBytes + (h + u) * kRowBytes);
+                            raw[u].w[0] = q.x; raw[u].w[1] = q.y; raw[u].w[2] = q.z; raw[u].w[3] = q.w;
+                        }
                     }
                     if (active) {
 #pragma unroll
@@ -926,8 +1003,17 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) E[j] += H[n][j];
             }
-            if (hi_max >= 0x7ff00000u)   // a negative, -0, inf or NaN input: the exact select, sample by sample
-                k1_entropy_exact_samples<T, VEC>(reinterpret_cast<const T*>(vol) + v0, N, C, prm.sn, prm.sc, E);
+            if (hi_max >= 0x7ff00000u) {   // a negative, -0, inf or NaN input: the exact select, sample by sample
+                if constexpr (SH) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        if (tid + kThreads * j < nvalid)
+                            k1_entropy_exact_samples<T, 1>(reinterpret_cast<const T*>(vol) + v0 + kThreads * j, N, C,
+                                                           prm.sn, prm.sc, &E[j]);
+                } else {
+                    k1_entropy_exact_samples<T, VEC>(reinterpret_cast<const T*>(vol) + v0, N, C, prm.sn, prm.sc, E);
+                }
+            }
         }
         if (M::kFlagged) {
 #pragma unroll
@@ -935,7 +1021,15 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                 bad |= ((__float_as_uint(Sacc[j]) & 0x7f800000u) == 0x7f800000u) ? 0x80000000u : 0u;
             bad = fold_sign<T>(bad);
             if (bad & 0x80000000u) {
-                k1_entropy_exact<T, VEC>(reinterpret_cast<const T*>(vol) + v0, N, C, prm.sn, prm.sc, E);
+                if constexpr (SH) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+                        if (tid + kThreads * j < nvalid)
+                            k1_entropy_exact<T, 1>(reinterpret_cast<const T*>(vol) + v0 + kThreads * j, N, C, prm.sn,
+                                                   prm.sc, &E[j]);
+                } else {
+                    k1_entropy_exact<T, VEC>(reinterpret_cast<const T*>(vol) + v0, N, C, prm.sn, prm.sc, E);
+                }
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) E[j] = E[j] / M::kScale;
             }
@@ -949,13 +1043,25 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
             mi[j] = pe[j] - ee[j];
         }
         const int64_t o = b * prm.so + v0;
-        if (prm.pe) store_f32<VEC>(prm.pe + o, pe);
-        if (prm.ee) store_f32<VEC>(prm.ee + o, ee);
-        if (prm.mi) store_f32<VEC>(prm.mi + o, mi);
-        if (prm.amax) store_u8<VEC>(prm.amax + b * prm.V + v0, idx);
+        if constexpr (SH) {   // element stores, lane-consecutive: no alignment asked of the maps
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                if (ragged && tid + kThreads * j >= nvalid) continue;
+                if (prm.pe) prm.pe[o + kThreads * j] = pe[j];
+                if (prm.ee) prm.ee[o + kThreads * j] = ee[j];
+                if (prm.mi) prm.mi[o + kThreads * j] = mi[j];
+                if (prm.amax) prm.amax[b * prm.V + v0 + kThreads * j] = (uint8_t)idx[j];
+            }
+        } else {
+            if (prm.pe) store_f32<VEC>(prm.pe + o, pe);
+            if (prm.ee) store_f32<VEC>(prm.ee + o, ee);
+            if (prm.mi) store_f32<VEC>(prm.mi + o, mi);
+            if (prm.amax) store_u8<VEC>(prm.amax + b * prm.V + v0, idx);
+        }
         if (prm.partials) {
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
+                if (SH && ragged && tid + kThreads * j >= nvalid) continue;
                 const float m3[3] = {pe[j], ee[j], mi[j]};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -1104,29 +1210,43 @@ static int launch_stream(K1Params& prm, int64_t B, cudaStream_t st) {
     return check_launch("k1_stream_kernel");
 }
 
-template <typename T, int VEC, int MINB, int RS, int STAGES, int NS = 0>
+template <typename T, int VEC, int MINB, int RS, int STAGES, int NS = 0, bool SH = false>
 static int launch_tma(K1Params& prm, int64_t B, cudaStream_t st) {
     const int64_t tiles = ceil_div(ceil_div(prm.V, VEC), kThreads);
     prm.iter = prm.tiles_per_cta > 0 ? prm.tiles_per_cta : choose_iter(tiles * B, MINB, prm.N * prm.C, sizeof(T) == 8);
     prm.blocks_per_vol = ceil_div(tiles, prm.iter);
     const int64_t grid = prm.blocks_per_vol * B;
     if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
-    auto kern = k1_tma_kernel<T, VEC, MINB, RS, STAGES, NS>;
-    const size_t smem = (size_t)STAGES * RS * kThreads * 16;
+    auto kern = k1_tma_kernel<T, VEC, MINB, RS, STAGES, NS, SH>;
+    const size_t smem = (size_t)STAGES * RS * (kThreads * 16 + (SH ? 16 : 0));
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return set_error(VALUES_ERR_CUDA, "cudaFuncSetAttribute(k1_tma_kernel) failed");
     kern<<<(unsigned)grid, kThreads + 32, smem, st>>>(prm);
     return check_launch("k1_tma_kernel");
 }
 
+// aligned: every row, stride and map is 16-byte aligned (vector loads / stores); shiftable: it is not, but
+// the 16-byte granules around the stack lie inside its allocation, so the ring kernel's SH mode can run
 template <typename T>
-static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, cudaStream_t st) {
+static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, bool shiftable, cudaStream_t st) {
     constexpr int NV = In<T>::VEC;
     const int64_t V = prm.V;
     // fp64 stacks (the reference's 3D path, raw overlap sums with large magnitudes) keep the
     // reference's exact accumulation order: sample-outer kernel below.
     if (prm.need_ent && !prm.samax && sizeof(T) != 8) {  // fp32 / bf16: class-outer stream kernel
-        if (!aligned) return launch_stream<T, 1, 4, 4, false>(prm, B, st);
+        if (!aligned) {
+            if constexpr (sizeof(T) != 8) {
+                // rows at every 16-byte phase: the ring kernel with element-strided ownership (0.40 -> of the
+                // HBM peak on 127^3 volumes with the scalar kernel below)
+                if (shiftable && prm.variant != K1_STREAM) {
+                    if (prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4, 0, true>(prm, B, st);
+                    if (prm.N % 5 == 0) return launch_tma<T, NV, 3, 5, 3, 0, true>(prm, B, st);
+                    if (prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8, 0, true>(prm, B, st);
+                    return launch_tma<T, NV, 3, 1, 8, 0, true>(prm, B, st);
+                }
+            }
+            return launch_stream<T, 1, 4, 4, false>(prm, B, st);
+        }
         // batch = U samples of one class; unguarded when U divides N (N = 4k: MC-dropout/TTA
         // 8, 16; N = 5k: the reference's 5-member ensembles and N = 10)
         // Occupancy beats register comfort here (measured on B200, profiles/r01b_k1_variants.txt):
@@ -1159,6 +1279,13 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, cudaStream_t st) 
             if (prm.N == 8) return launch_tma<T, NV, 3, 4, 4, 8>(prm, B, st);
             if (prm.N == 10) return launch_tma<T, NV, 2, 5, 3, 10>(prm, B, st);
             if (prm.N == 5) return launch_tma<T, NV, 3, 5, 3, 5>(prm, B, st);
+        }
+        // odd voxel counts (rows 8 bytes off): the same kernels in SH mode
+        if (prm.need_ent && !prm.samax && !aligned && shiftable && prm.variant != K1_SAMPLE_OUTER) {
+            if (prm.N == 16) return launch_tma<T, NV, 2, 4, 4, 16, true>(prm, B, st);
+            if (prm.N == 8) return launch_tma<T, NV, 3, 4, 4, 8, true>(prm, B, st);
+            if (prm.N == 10) return launch_tma<T, NV, 2, 5, 3, 10, true>(prm, B, st);
+            if (prm.N == 5) return launch_tma<T, NV, 3, 5, 3, 5, true>(prm, B, st);
         }
     }
     // per-sample arg-max / arg-max only: sample-outer kernel with class sums in shared memory
@@ -1244,11 +1371,21 @@ extern "C" int values_uncertainty_fused(const void* probs, int dtype, int64_t B,
     const bool aligned = V % nv == 0 && stride_b % nv == 0 && stride_n % nv == 0 &&
                          stride_c % nv == 0 && prm.so % 4 == 0 && al(probs, 16) && al(pe, 16) && al(ee, 16) &&
                          al(mi, 16) && al(mean_argmax, nv) && al(sample_argmax, nv);
+    bool shiftable = false;
+    if (!aligned && ((uintptr_t)probs % es) == 0) {
+        uintptr_t base = 0;
+        size_t size = 0;
+        if (allocation_range(probs, &base, &size)) {
+            const uintptr_t first = (uintptr_t)probs;
+            const uintptr_t last = first + (uintptr_t)((B - 1) * stride_b + (N - 1) * stride_n + (C - 1) * stride_c + V) * es;
+            shiftable = (first & ~(uintptr_t)15) >= base && ((last + 15) & ~(uintptr_t)15) <= base + size;
+        }
+    }
     int rc;
     switch (dtype) {
-        case VALUES_F32: rc = dispatch_k1<float>(prm, B, aligned, st); break;
-        case VALUES_F64: rc = dispatch_k1<double>(prm, B, aligned, st); break;
-        case VALUES_BF16: rc = dispatch_k1<__nv_bfloat16>(prm, B, aligned, st); break;
+        case VALUES_F32: rc = dispatch_k1<float>(prm, B, aligned, shiftable, st); break;
+        case VALUES_F64: rc = dispatch_k1<double>(prm, B, aligned, shiftable, st); break;
+        case VALUES_BF16: rc = dispatch_k1<__nv_bfloat16>(prm, B, aligned, shiftable, st); break;
         default: return set_error(VALUES_ERR_INVALID_ARG, "unknown dtype %d", dtype);
     }
     return rc;
