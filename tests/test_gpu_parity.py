@@ -562,6 +562,10 @@ def test_stitch_golden(vb, vo, stitch_path):
     ((40, 24, 200), 8, 1.0, torch.bfloat16),
     ((24, 40, 256), 16, 0.5, torch.float32),     # full-width vector tiles (64 threads x 4 voxels)
     ((20, 24, 136), 12, 0.5, torch.float64),     # stride 6: z origins not multiples of 4
+    ((33, 31, 45), 16, 0.5, torch.float32),      # Z % 4 != 0: rows are not whole groups of four voxels
+    ((24, 40, 70), 8, 1.0, torch.float32),       # ... Z % 4 == 2, fully covered along z up to 64
+    ((17, 19, 23), 8, 0.5, torch.float64),
+    ((20, 24, 27), 12, 0.5, torch.bfloat16),     # ... and z origins the copy engine cannot fetch
 ])
 def test_stitch_vs_oracle(vb, vo, shape, p, overlap, dtype, stitch_path):
     crops = vo.patch_grid(shape, p, overlap)
@@ -579,6 +583,20 @@ def test_stitch_vs_oracle(vb, vo, shape, p, overlap, dtype, stitch_path):
     if dtype == torch.float32:
         t32, _ = vb.stitch_volume(patches.cuda(), crops, shape, out_dtype=torch.float32, path=stitch_path)
         np.testing.assert_allclose(t32.cpu().numpy(), st.data["v"]["softmax_pred"], rtol=1e-6)
+    # a second pass on top of the sums (read-modify-write of every voxel): the oracle adds the patches again;
+    # and the separable-weight form agrees with the weight map (Z % 4 != 0: the same element-wise epilogue)
+    lo = vb.stitching.crops_to_lo(crops, "cuda")
+    vb.stitch_accumulate(patches.cuda(), lo, total, cnt, accumulate=True, path=stitch_path)
+    for pi in range(n_pred):
+        st.concat_data({"image_paths": ["v"] * len(crops), "org_image_size": [shape] * len(crops),
+                        "crop_idx": crops}, patches[pi].double(), n_pred=n_pred, pred_idx=pi)
+    np.testing.assert_array_equal(total.cpu().numpy(), st.data["v"]["softmax_pred"])
+    np.testing.assert_array_equal(cnt.cpu().numpy(), st.data["v"]["num_predictions"][0])
+    if shape[2] % 4 and p <= 128:
+        fac = vb.gaussian_importance_factors((p, p, p), sigma_scale=0.25)
+        wa = vb.stitch_volume(patches.cuda(), crops, shape, weight=tuple(f.cuda() for f in fac), path=stitch_path)
+        wb = vb.stitch_volume(patches.cuda(), crops, shape, weight=vb.importance_map_from_factors(fac).cuda(), path=1)
+        assert torch.equal(wa[0], wb[0]) and torch.equal(wa[1], wb[1])
 
 
 def test_stitch_selected_patches_of_a_padded_stack(vb, vo, stitch_path):

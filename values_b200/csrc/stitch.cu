@@ -447,6 +447,9 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
         gyz[i] = !producer && gy[i] < prm.Y && gz[i] < prm.Z;                    // Z % 4 == 0: whole groups
     }
     const uint32_t lds_off = (uint32_t)(tid & (kThreads - 1)) * 4u * (uint32_t)sizeof(TP);
+    // Z % 4 != 0: the volume's rows are not whole (or aligned) groups of four voxels -- the sums are read back
+    // and written element by element, the last group of a row guarded; the arithmetic between is the same
+    const bool zr = (prm.Z & 3) != 0;
     unsigned int it = 0;        // windows that went through the ring so far (producer and consumers count alike)
     // Rounds: the candidate list is scanned in order until kBoxList overlapping patches are found (one
     // round in every practical case: a box is overlapped by a few dozen patches at most); a further
@@ -520,11 +523,18 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
 #pragma unroll
                 for (int i = 0; i < kGroups; ++i) {
                     const int64_t vox = ((int64_t)(x_lo + gdx[i]) * prm.Y + gy[i]) * prm.Z + gz[i];
+                    acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0;
                     if (readback && gin[i]) {
-                        if (count_pass) read4(prm.out_count + vox, acc[i]);
-                        else read4(out + c * vol + vox, acc[i]);
-                    } else {
-                        acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0;
+                        if (zr) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (gz[i] + q < prm.Z)
+                                    acc[i][q] = count_pass ? prm.out_count[vox + q] : (double)out[c * vol + vox + q];
+                        } else if (count_pass) {
+                            read4(prm.out_count + vox, acc[i]);
+                        } else {
+                            read4(out + c * vol + vox, acc[i]);
+                        }
                     }
                 }
                 for (int k = 0; k < total; ++k) {
@@ -630,8 +640,18 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
                 for (int i = 0; i < kGroups; ++i) {
                     if (!gin[i]) continue;
                     const int64_t vox = ((int64_t)(x_lo + gdx[i]) * prm.Y + gy[i]) * prm.Z + gz[i];
-                    if (count_pass) store4<double>(prm.out_count + vox, acc[i]);
-                    else store4<TO>(out + c * vol + vox, acc[i]);
+                    if (zr) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (gz[i] + q >= prm.Z) continue;
+                            if (count_pass) prm.out_count[vox + q] = acc[i][q];
+                            else out[c * vol + vox + q] = (TO)acc[i][q];
+                        }
+                    } else if (count_pass) {
+                        store4<double>(prm.out_count + vox, acc[i]);
+                    } else {
+                        store4<TO>(out + c * vol + vox, acc[i]);
+                    }
                 }
             }
         }
@@ -704,10 +724,13 @@ static bool stitch_box_ok(const StitchParams& prm, int patch_dtype, int out_dtyp
     const int al = pes == 2 ? 8 : 4;
     const bool rows_mergeable = prm.N == 1 || (prm.stride_p > 0 && prm.stride_n % prm.stride_p == 0 &&
                                                prm.stride_n / prm.stride_p < 0x7fffffffLL / 65536);
-    return prm.Z % 4 == 0 && prm.p2 % al == 0 && rows_mergeable && (prm.stride_p * (int64_t)pes) % 16 == 0 &&
+    // the sums leave as 4-voxel vectors when the volume's rows are whole groups of four (Z % 4 == 0), else
+    // element by element: only then do the output pointers need vector alignment
+    const size_t ovec = prm.Z % 4 == 0 ? 4 : 1;
+    return prm.p2 % al == 0 && rows_mergeable && (prm.stride_p * (int64_t)pes) % 16 == 0 &&
            (prm.stride_p * (int64_t)pes) < (1LL << 40) && (reinterpret_cast<uintptr_t>(prm.patches) % 16) == 0 &&
-           (reinterpret_cast<uintptr_t>(prm.out_sum) % (4 * oes)) == 0 &&
-           (!prm.out_count || reinterpret_cast<uintptr_t>(prm.out_count) % 32 == 0) &&
+           (reinterpret_cast<uintptr_t>(prm.out_sum) % (ovec * oes)) == 0 &&
+           (!prm.out_count || reinterpret_cast<uintptr_t>(prm.out_count) % (ovec * 8) == 0) &&
            (!prm.weight || reinterpret_cast<uintptr_t>(prm.weight) % 32 == 0) &&
            prm.X < 0x7fffffffLL && prm.Y < 0x7fffffffLL && prm.Z < 0x7fffffffLL && prm.C < 0x7fffffffLL &&
            (patch_dtype != VALUES_F64 || out_dtype == VALUES_F64) && encode_tiled_fn() != nullptr;
