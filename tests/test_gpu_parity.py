@@ -193,6 +193,45 @@ def test_k1_unaligned_stacks_take_the_ring(vb, vo, n, c, spatial, dtype):
         assert torch.equal(torch.nan_to_num(a.float(), nan=-7.0), torch.nan_to_num(b.float(), nan=-7.0))
 
 
+@pytest.mark.parametrize("n,c,spatial,dtype", [
+    (16, 4, (40, 40, 40), torch.float32),
+    (10, 20, (96, 132), torch.float32),     # cfg4 class count
+    (5, 2, (32, 32, 32), torch.float64),    # the 3-D save path: data_carrier_3D.py:253-285
+    (8, 2, (24, 40, 26), torch.float64),
+    (1, 7, (30, 52), torch.float32),        # one sample: arg-max of the sample == arg-max of the mean
+    (3, 1, (16, 24), torch.float32),        # one class
+    (7, 5, (33, 64), torch.bfloat16),
+    (6, 3, (21, 19, 17), torch.float32),    # unaligned rows: the shared-memory kernel (both variants alike)
+])
+def test_argmax_only_sweeps(vb, vo, n, c, spatial, dtype):
+    """maps=False calls (mean_seg / pred_seg at save time, the per-sample arg-max of test_2D.py:119-127, the
+    Dice / GED inputs): the segmented sweeps (k1_argmax_kernel) against the sample-outer shared-memory kernel
+    (variant 4) and the oracle -- first maximum wins, NaN counts as maximal, ties and zero channels included."""
+    x = softmax_stack(n * 3 + c, 2 * n, c, spatial).reshape(2, n, c, *spatial).to(dtype)
+    flat = x.view(2, n, c, -1)
+    if c > 1:
+        flat[0, 0, 1, 5] = flat[0, 0, 0, 5]                 # a tie: the first class wins
+        flat[1, n - 1, c - 1, 9] = float("nan")             # NaN is maximal
+        flat[1, :, :, 11] = 0.0                             # all-zero voxel -> class 0
+    xg = x.cuda()
+    for kw in (dict(mean_argmax=True, sample_argmax=True), dict(sample_argmax=True), dict(mean_argmax=True)):
+        new = vb.uncertainty_fused(xg, maps=False, **kw)
+        old = vb.uncertainty_fused(xg, maps=False, variant=4, **kw)
+        if "sample_argmax" in kw:
+            assert torch.equal(new.sample_argmax, old.sample_argmax)
+            for b in range(2):
+                np.testing.assert_array_equal(new.sample_argmax[b].cpu().numpy(), vo.sample_argmax(x[b].float() if dtype == torch.bfloat16 else x[b]).numpy())
+        if "mean_argmax" in kw:
+            assert torch.equal(new.mean_argmax, old.mean_argmax)
+    withmaps = vb.uncertainty_fused(xg, mean_argmax=True)
+    assert torch.equal(withmaps.mean_argmax, vb.uncertainty_fused(xg, maps=False, mean_argmax=True).mean_argmax)
+    # a strided [N, B, C, H, W] stack (test_2D.py:317) sliced per image, no copy
+    perm = xg.permute(1, 0, 2, *range(3, xg.dim())).contiguous().permute(1, 0, 2, *range(3, xg.dim()))
+    r = vb.uncertainty_fused(perm, maps=False, mean_argmax=True, sample_argmax=True)
+    ref = vb.uncertainty_fused(xg, maps=False, mean_argmax=True, sample_argmax=True, variant=4)
+    assert torch.equal(r.sample_argmax, ref.sample_argmax) and torch.equal(r.mean_argmax, ref.mean_argmax)
+
+
 def test_fp64_class_mean_is_true_division(vb):
     """The fp64 kernels form the class mean as S * RN(1/N) refined by two fmas instead of a division: the
     arg-max of the mean and PE must be those of true division for every magnitude (raw overlap sums can be

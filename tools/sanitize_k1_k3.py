@@ -43,6 +43,8 @@ for n, c, spatial, dtype in cases:
         assert all(torch.equal(a, b) for a, b in zip(ref[:4], out[:4])), (n, c, spatial, dtype, variant, tiles)
         assert torch.allclose(ref[4], out[4], rtol=1e-13, atol=0), (n, c, spatial, dtype, variant, tiles)
     vb.uncertainty_fused(x, maps=False, sample_argmax=True)
+    vb.uncertainty_fused(x, maps=False, mean_argmax=True, sample_argmax=True, variant=4)
+    vb.uncertainty_fused(x, maps=False, mean_argmax=True)
 print("sanitize K1: ok")
 
 for shape, p, ov in [((24, 20, 16), 8, 0.5), ((21, 19, 18), 8, 0.5), ((16, 16, 16), 8, 1.0)]:

@@ -1088,6 +1088,106 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
     }
 }
 
+// ---- arg-max only (no entropy maps, no scores): data_carrier_3D.py:253-285 (mean_seg / pred_seg at save
+// time), test_2D.py:119-127 (per-sample arg-max incl. the zero channel), the Dice / GED inputs of f2.
+// A segmented sweep over the stack's (N x C) rows of one 16-byte voxel vector, U rows per batch with the
+// next batch already in flight (register double buffer, read-once evict-first loads):
+//   MEAN = false  per-sample arg-max: rows sample-outer / class-inner, a segment is one sample (C rows),
+//                 state = running best + index; the u8 map of sample n leaves when its segment closes;
+//   MEAN = true   arg-max of the mean: rows class-outer / sample-inner, a segment is one class (N rows),
+//                 state = class sum (sequential over n, as every other kernel) -> mean by the correctly
+//                 rounded class_mean -> running best over the classes.
+// First maximum wins, NaN counts as maximal (np.argmax / torch.argmax); results are those of k1_smem_kernel
+// (which this replaces for aligned stacks: 0.26-0.61 of the HBM peak, a shared-memory round trip per element).
+template <typename T, int VEC, int U, bool MEAN>
+__global__ void __launch_bounds__(kThreads) k1_argmax_kernel(const K1Params prm) {
+    using A = typename In<T>::acc_t;
+    static_assert(VEC * sizeof(T) == 16, "vector path only");
+    const int64_t b = blockIdx.x / prm.blocks_per_vol;
+    const int64_t blk = blockIdx.x - b * prm.blocks_per_vol;
+    const int64_t v0 = (blk * kThreads + threadIdx.x) * VEC;
+    if (v0 >= prm.V) return;
+    const int L = MEAN ? (int)prm.N : (int)prm.C;            // rows per segment
+    const int nseg = MEAN ? (int)prm.C : (int)prm.N;
+    const int64_t s_in = MEAN ? prm.sn : prm.sc;             // row to row inside a segment
+    const int64_t s_out = (MEAN ? prm.sc : prm.sn) - (int64_t)L * s_in;   // last row of a segment to the next segment
+    const int R = L * nseg;
+    const uint64_t pol = l2_evict_first_policy();
+    const T* lp = reinterpret_cast<const T*>(prm.probs) + b * prm.sb + v0;   // load cursor
+    int lpos = 0;
+    Raw<T, VEC> buf[2][U];
+    auto issue = [&](Raw<T, VEC> (&dst)[U], int r0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r0 + u < R) {
+                load_raw_stream<T, VEC>(lp, dst[u], pol);
+                lp += s_in;
+                if (++lpos == L) { lpos = 0; lp += s_out; }
+            }
+        }
+    };
+    A acc[VEC], best[VEC];
+    int idx[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { acc[j] = (A)0; best[j] = (A)0; idx[j] = 0; }
+    const A Nf = (A)prm.N;
+    int pos = 0, seg = 0;
+    auto consume = [&](const Raw<T, VEC> (&src)[U], int r0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r0 + u >= R) break;
+            A p[VEC];
+            unpack(src[u], p);
+            if constexpr (MEAN) {
+                if (pos == 0) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[j] = p[j];
+                } else {
+                    add_rows<VEC>(acc, p);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if (pos == 0) { best[j] = p[j]; idx[j] = 0; }
+                    else argmax_update_sel(p[j], pos, best[j], idx[j]);
+                }
+            }
+            if (++pos == L) {
+                pos = 0;
+                if constexpr (MEAN) {
+                    A m[VEC];
+                    class_mean<VEC>(acc, Nf, prm.inv_n, m);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        if (seg == 0) { best[j] = m[j]; idx[j] = 0; }
+                        else argmax_update_sel(m[j], seg, best[j], idx[j]);
+                    }
+                } else {
+                    store_u8<VEC>(prm.samax + (b * prm.N + seg) * prm.V + v0, idx);
+                }
+                ++seg;
+            }
+        }
+    };
+    issue(buf[0], 0);
+    for (int r0 = 0; r0 < R; r0 += 2 * U) {
+        issue(buf[1], r0 + U);
+        consume(buf[0], r0);
+        issue(buf[0], r0 + 2 * U);
+        consume(buf[1], r0 + U);
+    }
+    if constexpr (MEAN) store_u8<VEC>(prm.amax + b * prm.V + v0, idx);
+}
+
+template <typename T, int VEC, bool MEAN>
+static int launch_argmax(K1Params prm, int64_t B, cudaStream_t st) {
+    prm.blocks_per_vol = ceil_div(ceil_div(prm.V, VEC), kThreads);
+    const int64_t grid = prm.blocks_per_vol * B;
+    if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
+    k1_argmax_kernel<T, VEC, 4, MEAN><<<(unsigned)grid, kThreads, 0, st>>>(prm);
+    return check_launch(MEAN ? "k1_argmax_kernel<mean>" : "k1_argmax_kernel<sample>");
+}
+
 // ---- class sums in shared memory (any C); thread-private columns, conflict-free
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) k1_smem_kernel(const K1Params prm) {
@@ -1231,6 +1331,15 @@ template <typename T>
 static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, bool shiftable, cudaStream_t st) {
     constexpr int NV = In<T>::VEC;
     const int64_t V = prm.V;
+    // The per-sample arg-max wants the rows sample-outer, everything else class-outer: it is its own sweep
+    // (1.0 of the HBM peak), and the maps / scores / mean arg-max follow through the ring as if it had not
+    // been asked for -- two sweeps at the roofline instead of one shared-memory kernel at 0.26-0.47 of it.
+    if (prm.samax && aligned && prm.variant != K1_SAMPLE_OUTER) {
+        const int rc = launch_argmax<T, NV, false>(prm, B, st);
+        if (rc) return rc;
+        prm.samax = nullptr;
+        if (!prm.need_ent && !prm.amax) return VALUES_OK;
+    }
     // fp64 stacks (the reference's 3D path, raw overlap sums with large magnitudes) keep the
     // reference's exact accumulation order: sample-outer kernel below.
     if (prm.need_ent && !prm.samax && sizeof(T) != 8) {  // fp32 / bf16: class-outer stream kernel
@@ -1288,7 +1397,10 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, bool shiftable, c
             if (prm.N == 5) return launch_tma<T, NV, 3, 5, 3, 5, true>(prm, B, st);
         }
     }
-    // per-sample arg-max / arg-max only: sample-outer kernel with class sums in shared memory
+    // the arg-max of the mean alone (no maps, no scores): its segmented sweep
+    if (!prm.need_ent && aligned && prm.amax && !prm.samax && prm.variant != K1_SAMPLE_OUTER)
+        return launch_argmax<T, NV, true>(prm, B, st);
+    // per-sample arg-max next to the maps, unaligned stacks: sample-outer kernel with class sums in shared memory
     int rc = 1;
     if (aligned) {
         // widest vector whose class sums fit in shared memory
