@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VALUES_ABI_VERSION 7
+#define VALUES_ABI_VERSION 8
 
 typedef enum {
     VALUES_F32 = 0, VALUES_F64 = 1, VALUES_BF16 = 2,
@@ -218,6 +218,17 @@ int values_min_key_above(const void* data, int dtype, int64_t n, uint64_t key,
 int values_radix_histogram_dev(const void* data, int dtype, int64_t n, const unsigned long long* state,
                                int digit_bits, unsigned long long* hist, void* stream);
 int values_radix_select(unsigned long long* hist, int digit_bits, unsigned long long* state, void* stream);
+/* The same two sweeps over a SET of maps in one launch per 96 maps (find_threshold.py:31-40, 90-96 walk a
+ * validation set of separate images; a launch per image and digit made the quantile launch-bound):
+ * maps_host / counts_host are HOST arrays of n_maps device pointers / element counts (empty maps allowed).
+ * values_radix_histogram_set: state != NULL reads the prefix from the device state (as _dev), else prefix /
+ * prefix_bits are the arguments (as values_radix_histogram). */
+int values_radix_histogram_set(const void* const* maps_host, const int64_t* counts_host, int64_t n_maps,
+                               int dtype, uint64_t prefix, int prefix_bits,
+                               const unsigned long long* state, int digit_bits,
+                               unsigned long long* hist, void* stream);
+int values_min_key_above_set(const void* const* maps_host, const int64_t* counts_host, int64_t n_maps,
+                             int dtype, uint64_t key, unsigned long long* out, void* stream);
 
 /* Replaces the reductions of compute_ncc(gt_unc_map, pred_unc_map) evaluation/metrics/ncc.py:9-25.
  *   a [M, V] (stride_a, 1), b [M, V] (stride_b, 1), F32 or F64 each; shift: device double [M, 2]

@@ -105,6 +105,24 @@ def test_quantile_matches_numpy_large(vb, dtype):
         assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True), (q, got, want)  # q=1: inf-inf=NaN in numpy too
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_quantile_over_many_ragged_maps(vb, dtype):
+    """A validation set of many separate images (find_threshold.py:90-96): more maps than one launch's table
+    holds (96), different sizes, empty maps, views that start off a 16-byte boundary -- one launch per digit
+    and table, same exact result as np.quantile of the concatenation."""
+    rng = np.random.default_rng(11)
+    sizes = [int(s) for s in rng.integers(0, 5000, size=203)]
+    sizes[5] = 0
+    sizes[96] = 0
+    host = [(rng.random(s + 3) ** 2).astype(dtype) for s in sizes]
+    dev = [torch.from_numpy(h).cuda()[(i % 3):(i % 3) + sizes[i]] for i, h in enumerate(host)]
+    flat = np.concatenate([h[(i % 3):(i % 3) + sizes[i]] for i, h in enumerate(host)])
+    for q in (0.0, 0.25, 0.98, 1.0):
+        got = vb.quantile(dev, q)
+        want = np.quantile(flat, q)
+        assert got.dtype == want.dtype and got == want, (q, got, want)
+
+
 def test_quantile_nan_and_errors(vb):
     x = torch.rand(1000, dtype=torch.float64)
     x[17] = float("nan")

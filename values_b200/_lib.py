@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VALUES_B200_LIB") or os.path.join(_PKG, "lib", "libvalues_b200.so")
 
 F32, F64, BF16, U8, I32, I64 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 7  # include/values_b200.h VALUES_ABI_VERSION
+ABI_VERSION = 8  # include/values_b200.h VALUES_ABI_VERSION
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16}
 _LABEL_DTYPES = {torch.uint8: U8, torch.int32: I32, torch.int64: I64}
 
@@ -62,6 +62,9 @@ def _load() -> C.CDLL:
         "values_min_key_above": (C.c_int, [vp, C.c_int, i64, C.c_uint64, vp, vp]),
         "values_radix_histogram_dev": (C.c_int, [vp, C.c_int, i64, vp, C.c_int, vp, vp]),
         "values_radix_select": (C.c_int, [vp, C.c_int, vp, vp]),
+        "values_radix_histogram_set": (C.c_int, [C.POINTER(vp), pi64, i64, C.c_int, C.c_uint64, C.c_int, vp,
+                                                 C.c_int, vp, vp]),
+        "values_min_key_above_set": (C.c_int, [C.POINTER(vp), pi64, i64, C.c_int, C.c_uint64, vp, vp]),
         "values_pair_moments_workspace_bytes": (sz, [i64, i64]),
         "values_pair_moments": (C.c_int, [vp, C.c_int, i64, vp, C.c_int, i64, i64, i64, vp, vp, vp, sz, vp]),
         "values_calib_bins_workspace_bytes": (sz, [i64]),
@@ -89,11 +92,20 @@ EXPORTED = [
     "values_stitch_accumulate_weighted", "values_stitch_accumulate_separable",
     "values_normalize_maps", "values_count_nonzero", "values_radix_histogram",
     "values_min_key_above", "values_radix_histogram_dev", "values_radix_select",
+    "values_radix_histogram_set", "values_min_key_above_set",
     "values_pair_moments_workspace_bytes", "values_pair_moments",
     "values_calib_bins_workspace_bytes", "values_calib_bins", "values_calib_bins_fused",
     "values_confusion_counts", "values_reverse_axes", "values_patch_filter_err_coef",
     "values_seg_loss_workspace_bytes", "values_seg_loss_terms",
 ]
+
+
+def map_set(maps):
+    """(pointer array, count array, n) of a sequence of CUDA tensors, for the *_set entry points."""
+    n = len(maps)
+    ptrs = (C.c_void_p * n)(*[m.data_ptr() for m in maps])
+    counts = (C.c_int64 * n)(*[m.numel() for m in maps])
+    return ptrs, counts, n
 
 
 def check(rc: int) -> None:

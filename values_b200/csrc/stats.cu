@@ -81,19 +81,29 @@ template <> struct Key<double> {
 constexpr int kMaxDigitBits = 11;
 
 // hist[d] += #{ i : key(x_i) >> (BITS - prefix_bits) == prefix  and  (key >> shift) & mask == d }
-// Block-private shared histogram, warp-aggregated: the leading digits (sign + exponent) repeat heavily,
-// so a warp votes twice on the digit of its first live lane (ballot + popc, one shared atomic per vote)
-// and only the lanes left over add individually.  (match.any did the same grouping exactly but bounded
-// the kernel: 0.8 TB/s on the top digit of fp32 maps.)
+// Block-private shared histogram in R = 8192 / bins replicas (32 KB: 4 replicas of 2048 bins, 8 of 1024,
+// 32 of 256), a lane adds into replica lane % R: the leading digits (sign + exponent) repeat heavily, and the
+// replicas keep lanes that hold the same digit on different words.  One shared atomic per matching element
+// and no cross-lane dependency; two 16-byte vectors in flight per thread.  (r01 / early r02 aggregated equal
+// digits per warp first -- match.any, then two ballot rounds per element: exact, but every element paid a
+// chain of votes and shuffles, 0.12-0.18 of the HBM peak on the top digit of fp32 maps.)
+constexpr int kHistWords = 8192;
+// The maps of one launch: a validation set is many separate images, and a launch per image and digit made the
+// exact quantile launch-bound (131 launches for 32 maps: 1.1 ms for 0.27 ms of memory traffic).  The table
+// travels as a kernel parameter; blockIdx.y picks the map.
+constexpr int kSetMax = 96;
+struct MapSet { const void* p[kSetMax]; int64_t n[kSetMax]; };
 template <typename T>
-__global__ void __launch_bounds__(kThreads) radix_hist_kernel(const T* __restrict__ x, int64_t n,
+__global__ void __launch_bounds__(kThreads) radix_hist_kernel(const __grid_constant__ MapSet set,
                                                               uint64_t prefix, int prefix_bits,
                                                               int shift, int digit_bits,
                                                               unsigned long long* __restrict__ hist,
                                                               const unsigned long long* __restrict__ state) {
     using K = typename Key<T>::type;
     constexpr int VEC = 16 / sizeof(T);
-    __shared__ unsigned int sh[1 << kMaxDigitBits];
+    __shared__ unsigned int sh[kHistWords];
+    const T* __restrict__ x = reinterpret_cast<const T*>(set.p[blockIdx.y]);
+    const int64_t n = set.n[blockIdx.y];
     if (state) {   // prefix chosen on the device by radix_select_kernel (no host round trip per digit)
         if (state[1] + (unsigned long long)digit_bits > (unsigned long long)Key<T>::BITS) return;   // select flagged an error
         prefix = state[0];
@@ -101,28 +111,23 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const T* __restric
         shift = Key<T>::BITS - prefix_bits - digit_bits;
     }
     const int nbins = 1 << digit_bits;
-    for (int i = threadIdx.x; i < nbins; i += kThreads) sh[i] = 0;
+    const int rbits = 13 - digit_bits > 5 ? 5 : 13 - digit_bits;      // log2 of the replica count (<= 32)
+    const int words = nbins << rbits;
+    for (int i = threadIdx.x; i < words; i += kThreads) sh[i] = 0;
     __syncthreads();
     const K mask = (K)(nbins - 1);
     const int pshift = Key<T>::BITS - prefix_bits;
-    const int lane = threadIdx.x & 31;
-    auto add = [&](bool live, T v) {
+    const unsigned rep = threadIdx.x & ((1u << rbits) - 1u);
+    auto add = [&](T v) {
         const K key = Key<T>::of(v);
-        const bool in = live && (prefix_bits == 0 || (uint64_t)(key >> pshift) == prefix);
-        const unsigned d = (unsigned)((key >> shift) & mask);
-        unsigned active = __ballot_sync(0xffffffffu, in);
-        bool todo = in;
+        if (prefix_bits == 0 || (uint64_t)(key >> pshift) == prefix)
+            atomicAdd(&sh[((unsigned)((key >> shift) & mask) << rbits) + rep], 1u);
+    };
+    auto add_vec = [&](const uint4& r) {
+        T e[VEC];
+        memcpy(e, &r, 16);
 #pragma unroll
-        for (int round = 0; round < 2; ++round) {
-            if (active == 0) break;                                   // warp-uniform
-            const int leader = __ffs(active) - 1;
-            const unsigned dl = __shfl_sync(0xffffffffu, d, leader);
-            const unsigned same = __ballot_sync(0xffffffffu, todo && d == dl);
-            if (lane == leader) atomicAdd(&sh[dl], (unsigned)__popc(same));
-            todo = todo && d != dl;
-            active &= ~same;
-        }
-        if (todo) atomicAdd(&sh[d], 1u);
+        for (int k = 0; k < VEC; ++k) add(e[k]);
     };
     const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
     int64_t head = (int64_t)(((16 - (addr & 15)) & 15) / sizeof(T));
@@ -131,26 +136,28 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const T* __restric
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     const uint4* xv = reinterpret_cast<const uint4*>(x + head);
-    // whole warps iterate together (the ballot needs every lane)
-    for (int64_t base = tid - lane; base < nvec; base += nthr) {
-        const int64_t i = base + lane;
-        const bool live = i < nvec;
-        uint4 r = make_uint4(0, 0, 0, 0);
-        if (live) r = ldg_stream_128(xv + i);
-        T e[VEC];
-        memcpy(e, &r, 16);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) add(live, e[k]);
+    int64_t i = tid;
+    for (; i + 3 * nthr < nvec; i += 4 * nthr) {
+        const uint4 r0 = ldg_stream_128(xv + i), r1 = ldg_stream_128(xv + i + nthr);
+        const uint4 r2 = ldg_stream_128(xv + i + 2 * nthr), r3 = ldg_stream_128(xv + i + 3 * nthr);
+        add_vec(r0);
+        add_vec(r1);
+        add_vec(r2);
+        add_vec(r3);
     }
+    for (; i < nvec; i += nthr) add_vec(ldg_stream_128(xv + i));
     const int64_t tail0 = head + nvec * VEC;
-    if (blockIdx.x == 0 && threadIdx.x < 32) {   // < VEC head and < VEC tail elements: one warp
-        add(lane < head, lane < head ? ld_elem(x + lane) : (T)0);
-        const bool lt = tail0 + lane < n;
-        add(lt, lt ? ld_elem(x + tail0 + lane) : (T)0);
+    if (blockIdx.x == 0 && threadIdx.x < 32) {   // < VEC head and < VEC tail elements
+        const int lane = threadIdx.x;
+        if (lane < head) add(ld_elem(x + lane));
+        if (tail0 + lane < n) add(ld_elem(x + tail0 + lane));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nbins; i += kThreads)
-        if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+    for (int b = threadIdx.x; b < nbins; b += kThreads) {
+        unsigned int c = 0;
+        for (int r = 0; r < (1 << rbits); ++r) c += sh[(b << rbits) + r];
+        if (c) atomicAdd(hist + b, (unsigned long long)c);
+    }
 }
 
 // One thread block: the bucket of `hist` that holds the wanted rank becomes the next digit of the prefix.
@@ -194,10 +201,12 @@ __global__ void __launch_bounds__(kThreads) radix_select_kernel(unsigned long lo
 
 // out[0] = min(out[0], min key(x_i) > key)   (atomicMin: order-free)
 template <typename T>
-__global__ void __launch_bounds__(kThreads) min_key_above_kernel(const T* __restrict__ x, int64_t n,
+__global__ void __launch_bounds__(kThreads) min_key_above_kernel(const __grid_constant__ MapSet set,
                                                                  uint64_t key,
                                                                  unsigned long long* __restrict__ out) {
     __shared__ unsigned long long red[kThreads / 32];
+    const T* __restrict__ x = reinterpret_cast<const T*>(set.p[blockIdx.y]);
+    const int64_t n = set.n[blockIdx.y];
     unsigned long long best = ~0ull;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthr) {
@@ -548,39 +557,81 @@ extern "C" int values_count_nonzero(const void* data, int dtype, int64_t n,
     return check_launch("count_nonzero_kernel");
 }
 
-static int radix_histogram_impl(const void* data, int dtype, int64_t n, uint64_t prefix, int prefix_bits,
-                                int digit_bits, unsigned long long* hist, const unsigned long long* state,
-                                void* stream) {
+// launches over a set of maps, kSetMax maps per launch: grid = (CTAs per map, maps)
+template <typename Launch>
+static int for_each_map_chunk(const void* const* maps, const int64_t* counts, int64_t n_maps, size_t es, int per_sm,
+                              const char* what, Launch launch) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    for (int64_t m0 = 0; m0 < n_maps;) {
+        MapSet set{};
+        int k = 0;
+        int64_t nmax = 0;
+        for (; m0 < n_maps && k < kSetMax; ++m0) {
+            if (counts[m0] < 0) return set_error(VALUES_ERR_INVALID_ARG, "%s: negative size", what);
+            if (counts[m0] == 0) continue;
+            if (!maps[m0]) return set_error(VALUES_ERR_INVALID_ARG, "%s: NULL input", what);
+            set.p[k] = maps[m0]; set.n[k] = counts[m0];
+            nmax = counts[m0] > nmax ? counts[m0] : nmax;
+            ++k;
+        }
+        if (k == 0) continue;
+        // every CTA in the first wave: per_sm resident CTAs per SM shared by the maps of the launch
+        const int64_t want = ceil_div(ceil_div(nmax * (int64_t)es, 64), kThreads);
+        const int64_t cap = ((int64_t)sms * per_sm + k - 1) / k;
+        const int64_t gx = want < 1 ? 1 : (want > cap ? cap : want);
+        launch(set, dim3((unsigned)gx, (unsigned)k));
+        const int rc = check_launch(what);
+        if (rc) return rc;
+    }
+    return VALUES_OK;
+}
+
+static int radix_histogram_impl(const void* const* maps, const int64_t* counts, int64_t n_maps, int dtype,
+                                uint64_t prefix, int prefix_bits, int digit_bits, unsigned long long* hist,
+                                const unsigned long long* state, void* stream) {
     if (dtype != VALUES_F32 && dtype != VALUES_F64)
         return set_error(VALUES_ERR_INVALID_ARG, "radix_histogram: dtype must be f32 or f64");
     const int bits = dtype == VALUES_F32 ? 32 : 64;
-    if (n < 0 || digit_bits < 1 || digit_bits > kMaxDigitBits || prefix_bits < 0 ||
+    if (n_maps < 0 || digit_bits < 1 || digit_bits > kMaxDigitBits || prefix_bits < 0 ||
         prefix_bits + digit_bits > bits)
         return set_error(VALUES_ERR_INVALID_ARG, "radix_histogram: bad sizes (digit_bits 1..%d, "
                          "prefix_bits + digit_bits <= %d)", kMaxDigitBits, bits);
     if (!hist) return set_error(VALUES_ERR_INVALID_ARG, "radix_histogram: NULL histogram");
-    if (n == 0) return VALUES_OK;
-    if (!data) return set_error(VALUES_ERR_INVALID_ARG, "radix_histogram: NULL input");
+    if (n_maps == 0) return VALUES_OK;
+    if (!maps || !counts) return set_error(VALUES_ERR_INVALID_ARG, "radix_histogram: NULL input");
     cudaStream_t st = (cudaStream_t)stream;
     const int shift = bits - prefix_bits - digit_bits;
-    const int grid = stat_grid(ceil_div(n * (bits / 8), 16));
-    if (dtype == VALUES_F32)
-        radix_hist_kernel<float><<<grid, kThreads, 0, st>>>((const float*)data, n, prefix, prefix_bits, shift, digit_bits, hist, state);
-    else
-        radix_hist_kernel<double><<<grid, kThreads, 0, st>>>((const double*)data, n, prefix, prefix_bits, shift, digit_bits, hist, state);
-    return check_launch("radix_hist_kernel");
+    // 32 KB of shared memory per CTA: six resident CTAs per SM
+    return for_each_map_chunk(maps, counts, n_maps, bits / 8, 6, "radix_hist_kernel", [&](const MapSet& set, dim3 grid) {
+        if (dtype == VALUES_F32)
+            radix_hist_kernel<float><<<grid, kThreads, 0, st>>>(set, prefix, prefix_bits, shift, digit_bits, hist, state);
+        else
+            radix_hist_kernel<double><<<grid, kThreads, 0, st>>>(set, prefix, prefix_bits, shift, digit_bits, hist, state);
+    });
 }
 
 extern "C" int values_radix_histogram(const void* data, int dtype, int64_t n, uint64_t prefix,
                                       int prefix_bits, int digit_bits, unsigned long long* hist,
                                       void* stream) {
-    return radix_histogram_impl(data, dtype, n, prefix, prefix_bits, digit_bits, hist, nullptr, stream);
+    if (n > 0 && !data) return set_error(VALUES_ERR_INVALID_ARG, "radix_histogram: NULL input");
+    return radix_histogram_impl(&data, &n, 1, dtype, prefix, prefix_bits, digit_bits, hist, nullptr, stream);
 }
 
 extern "C" int values_radix_histogram_dev(const void* data, int dtype, int64_t n, const unsigned long long* state,
                                           int digit_bits, unsigned long long* hist, void* stream) {
     if (!state) return set_error(VALUES_ERR_INVALID_ARG, "radix_histogram_dev: NULL state");
-    return radix_histogram_impl(data, dtype, n, 0, 0, digit_bits, hist, state, stream);
+    if (n > 0 && !data) return set_error(VALUES_ERR_INVALID_ARG, "radix_histogram: NULL input");
+    return radix_histogram_impl(&data, &n, 1, dtype, 0, 0, digit_bits, hist, state, stream);
+}
+
+extern "C" int values_radix_histogram_set(const void* const* maps_host, const int64_t* counts_host, int64_t n_maps,
+                                          int dtype, uint64_t prefix, int prefix_bits,
+                                          const unsigned long long* state, int digit_bits,
+                                          unsigned long long* hist, void* stream) {
+    return radix_histogram_impl(maps_host, counts_host, n_maps, dtype, state ? 0 : prefix, state ? 0 : prefix_bits,
+                                digit_bits, hist, state, stream);
 }
 
 extern "C" int values_radix_select(unsigned long long* hist, int digit_bits, unsigned long long* state, void* stream) {
@@ -590,20 +641,33 @@ extern "C" int values_radix_select(unsigned long long* hist, int digit_bits, uns
     return check_launch("radix_select_kernel");
 }
 
-extern "C" int values_min_key_above(const void* data, int dtype, int64_t n, uint64_t key,
-                                    unsigned long long* out, void* stream) {
+static int min_key_above_impl(const void* const* maps, const int64_t* counts, int64_t n_maps, int dtype, uint64_t key,
+                              unsigned long long* out, void* stream) {
     if (dtype != VALUES_F32 && dtype != VALUES_F64)
         return set_error(VALUES_ERR_INVALID_ARG, "min_key_above: dtype must be f32 or f64");
-    if (n < 0 || !out) return set_error(VALUES_ERR_INVALID_ARG, "min_key_above: bad arguments");
-    if (n == 0) return VALUES_OK;
-    if (!data) return set_error(VALUES_ERR_INVALID_ARG, "min_key_above: NULL input");
+    if (n_maps < 0 || !out) return set_error(VALUES_ERR_INVALID_ARG, "min_key_above: bad arguments");
+    if (n_maps == 0) return VALUES_OK;
+    if (!maps || !counts) return set_error(VALUES_ERR_INVALID_ARG, "min_key_above: NULL input");
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = stat_grid(n);
-    if (dtype == VALUES_F32)
-        min_key_above_kernel<float><<<grid, kThreads, 0, st>>>((const float*)data, n, key, out);
-    else
-        min_key_above_kernel<double><<<grid, kThreads, 0, st>>>((const double*)data, n, key, out);
-    return check_launch("min_key_above_kernel");
+    // element loads: sized as if every element were 64 bytes' worth of work per thread quarter
+    return for_each_map_chunk(maps, counts, n_maps, 16, 8, "min_key_above_kernel", [&](const MapSet& set, dim3 grid) {
+        if (dtype == VALUES_F32)
+            min_key_above_kernel<float><<<grid, kThreads, 0, st>>>(set, key, out);
+        else
+            min_key_above_kernel<double><<<grid, kThreads, 0, st>>>(set, key, out);
+    });
+}
+
+extern "C" int values_min_key_above(const void* data, int dtype, int64_t n, uint64_t key,
+                                    unsigned long long* out, void* stream) {
+    if (n < 0) return set_error(VALUES_ERR_INVALID_ARG, "min_key_above: bad arguments");
+    if (n > 0 && !data) return set_error(VALUES_ERR_INVALID_ARG, "min_key_above: NULL input");
+    return min_key_above_impl(&data, &n, 1, dtype, key, out, stream);
+}
+
+extern "C" int values_min_key_above_set(const void* const* maps_host, const int64_t* counts_host, int64_t n_maps,
+                                        int dtype, uint64_t key, unsigned long long* out, void* stream) {
+    return min_key_above_impl(maps_host, counts_host, n_maps, dtype, key, out, stream);
 }
 
 extern "C" size_t values_pair_moments_workspace_bytes(int64_t M, int64_t V) {

@@ -105,11 +105,12 @@ def order_statistic(maps: Sequence[torch.Tensor], k: int, distributed: bool = Fa
     # the digit walk stays on the device: {prefix, prefix_bits, rank, count_eq, count of the top bucket of the
     # first digit}; ONE readback at the end (with distributed=True the histogram all-reduce is on-stream too)
     state = torch.tensor([0, 0, int(k), 0, 0], dtype=torch.int64, device=dev)
+    ptrs, counts, n_maps = _lib.map_set(maps)
     with torch.cuda.device(dev):
         for db in _DIGITS[bits]:
-            for m in maps:
-                _lib.check(_lib.lib.values_radix_histogram_dev(m.data_ptr(), code, m.numel(), state.data_ptr(), db,
-                                                               hist.data_ptr(), _lib.stream_ptr(dev)))
+            # one launch per digit and 96 maps (a launch per map made the walk launch-bound)
+            _lib.check(_lib.lib.values_radix_histogram_set(ptrs, counts, n_maps, code, 0, 0, state.data_ptr(), db,
+                                                           hist.data_ptr(), _lib.stream_ptr(dev)))
             if distributed:
                 _all_reduce(hist, dist.ReduceOp.SUM, group)
             _lib.check(_lib.lib.values_radix_select(hist.data_ptr(), db, state.data_ptr(), _lib.stream_ptr(dev)))
@@ -124,11 +125,10 @@ def _min_key_above(maps: Sequence[torch.Tensor], key: int, bits: int, distribute
     dev = maps[0].device
     out = torch.full((1,), -1, dtype=torch.int64, device=dev)   # 0xffff... as unsigned
     code = _lib.dtype_code(maps[0].dtype)
+    ptrs, counts, n_maps = _lib.map_set(maps)
     with torch.cuda.device(dev):
-        for m in maps:
-            rc = _lib.lib.values_min_key_above(m.data_ptr(), code, m.numel(), key, out.data_ptr(),
-                                               _lib.stream_ptr(dev))
-            _lib.check(rc)
+        _lib.check(_lib.lib.values_min_key_above_set(ptrs, counts, n_maps, code, key, out.data_ptr(),
+                                                     _lib.stream_ptr(dev)))
     if distributed:   # unsigned min through a signed all-reduce: flip the top bit
         out ^= torch.iinfo(torch.int64).min
         _all_reduce(out, dist.ReduceOp.MIN, group)
@@ -179,10 +179,11 @@ def quantile(maps: Union[torch.Tensor, np.ndarray, Sequence], q: float, distribu
         maps = [m.to(torch.float64) for m in maps]
         dt = torch.float64
     np_dtype = _NP_DTYPE[dt]
-    n_t = torch.tensor([sum(m.numel() for m in maps)], dtype=torch.int64, device=dev)
+    n = sum(m.numel() for m in maps)
     if distributed:
+        n_t = torch.tensor([n], dtype=torch.int64, device=dev)
         _all_reduce(n_t, dist.ReduceOp.SUM, group)
-    n = int(n_t.item())
+        n = int(n_t.item())
     if n == 0:
         raise IndexError("quantile of an empty set of maps")
     virtual = _virtual_index(n, q, np_dtype)
@@ -205,11 +206,11 @@ def quantile(maps: Union[torch.Tensor, np.ndarray, Sequence], q: float, distribu
     else:   # fp64: that bucket also holds finite values >= 2^1023; count the all-ones key itself
         last_db = _DIGITS[bits][-1]
         hist = torch.zeros(1 << last_db, dtype=torch.int64, device=dev)
+        ptrs, counts, n_maps = _lib.map_set(maps)
         with torch.cuda.device(dev):
-            for m in maps:
-                _lib.check(_lib.lib.values_radix_histogram(
-                    m.data_ptr(), _lib.dtype_code(dt), m.numel(), nan_key >> last_db, bits - last_db,
-                    last_db, hist.data_ptr(), _lib.stream_ptr(dev)))
+            _lib.check(_lib.lib.values_radix_histogram_set(
+                ptrs, counts, n_maps, _lib.dtype_code(dt), nan_key >> last_db, bits - last_db, None,
+                last_db, hist.data_ptr(), _lib.stream_ptr(dev)))
         if distributed:
             _all_reduce(hist, dist.ReduceOp.SUM, group)
         if int(hist[-1].item()) > 0:
