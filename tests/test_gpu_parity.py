@@ -118,13 +118,21 @@ def test_c2_vs_oracle(vb, vo, n, c, spatial, dtype):
     (16, 4, (64, 64, 40), torch.float32),   # RS = 8 (two sub-batches of 4); variants 2 / 3: RS = 4 / 8 x 3 stages
     (12, 3, (40, 64, 24), torch.float32),   # RS = 4
     (10, 20, (96, 132), torch.float32),     # RS = 5
-    (6, 3, (50, 64), torch.float32),        # RS = 2, ragged last tile
+    (6, 3, (50, 64), torch.float32),        # RS = 3, ragged last tile
+    (3, 4, (24, 40, 20), torch.float32),    # RS = 3, one stage per class
+    (14, 3, (40, 52), torch.float32),       # RS = 2
     (7, 5, (40, 52), torch.float32),        # RS = 1
     (8, 4, (33, 64), torch.bfloat16),
     (16, 4, (24, 40, 26), torch.float64),   # fp64: class-outer ring kernel (per-sample accumulators) vs
     (8, 2, (30, 50), torch.float64),        # the sample-outer kernel (variant 4)
     (5, 2, (32, 32, 32), torch.float64),    # the reference's own 3-D case: 5-member ensemble, fp64
     (10, 3, (40, 36), torch.float64),
+    (2, 2, (24, 24, 20), torch.float64),    # the other fp64 sample counts with a ring instantiation
+    (3, 2, (30, 50), torch.float64),
+    (4, 3, (20, 36), torch.float64),
+    (6, 2, (24, 24, 24), torch.float64),
+    (12, 2, (40, 36), torch.float64),
+    (20, 2, (24, 40), torch.float64),
 ])
 def test_k1_kernels_agree(vb, n, c, spatial, dtype):
     """The bulk-copy (TMA ring) kernel and the register-stream kernel share their arithmetic and

@@ -1267,6 +1267,69 @@ __global__ void __launch_bounds__(kThreads) msr_kernel(const T* __restrict__ pro
     else out[b * V + v] = r;
 }
 
+// the same on 16-byte voxel vectors, four class rows in flight per thread (the element kernel above: 0.34-0.59
+// of the HBM peak on 256^3 / 2048^2 stacks)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) msr_vec_kernel(const T* __restrict__ probs, int64_t C, int64_t V,
+                                                           int64_t sb, int64_t sc, T* __restrict__ out,
+                                                           int64_t blocks_per_vol) {
+    using A = typename In<T>::acc_t;
+    constexpr int VEC = In<T>::VEC;
+    const int64_t b = blockIdx.x / blocks_per_vol;
+    const int64_t v = ((blockIdx.x - b * blocks_per_vol) * kThreads + threadIdx.x) * VEC;
+    if (v >= V) return;
+    const T* p = probs + b * sb + v;
+    const uint64_t pol = l2_evict_first_policy();
+    A m[VEC];
+    {
+        Raw<T, VEC> r;
+        load_raw_stream<T, VEC>(p, r, pol);
+        unpack(r, m);
+    }
+    for (int64_t c = 1; c < C; c += 4) {
+        Raw<T, VEC> r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c + u < C) load_raw_stream<T, VEC>(p + (c + u) * sc, r[u], pol);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (c + u >= C) break;
+            A x[VEC];
+            unpack(r[u], x);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) m[j] = (x[j] > m[j] || x[j] != x[j]) ? x[j] : m[j];   // torch.max propagates NaN
+        }
+    }
+    T* o = out + b * V + v;
+    if constexpr (sizeof(T) == 2) {
+        uint32_t w[VEC / 2];
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn((A)1 - m[j], (A)1 - m[j + 1]);
+            memcpy(&w[j / 2], &h, 4);
+        }
+        *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(o) = make_float4(1.f - m[0], 1.f - m[1], 1.f - m[2], 1.f - m[3]);
+    } else {
+        *reinterpret_cast<double2*>(o) = make_double2(1.0 - m[0], 1.0 - m[1]);
+    }
+}
+
+template <typename T>
+static int launch_msr(const void* probs, int64_t B, int64_t C, int64_t V, int64_t sb, int64_t sc, void* out,
+                      cudaStream_t st) {
+    constexpr int VEC = In<T>::VEC;
+    const bool vec = V % VEC == 0 && sb % VEC == 0 && sc % VEC == 0 &&
+                     reinterpret_cast<uintptr_t>(probs) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+    const int64_t bpv = ceil_div(vec ? V / VEC : V, kThreads);
+    if (bpv * B > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
+    const unsigned grid = (unsigned)(bpv * B);
+    if (vec) msr_vec_kernel<T><<<grid, kThreads, 0, st>>>((const T*)probs, C, V, sb, sc, (T*)out, bpv);
+    else msr_kernel<T><<<grid, kThreads, 0, st>>>((const T*)probs, C, V, sb, sc, (T*)out, bpv);
+    return check_launch("msr_kernel");
+}
+
 template <typename T, int VEC>
 static int launch_smem(const K1Params& prm, int64_t grid, cudaStream_t st) {
     using A = typename In<T>::acc_t;
@@ -1372,6 +1435,7 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, bool shiftable, c
                 if (prm.N % 8 == 0 && v != K1_RING4) return launch_tma<T, NV, 3, 8, 2>(prm, B, st);
                 if (prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4>(prm, B, st);
                 if (prm.N % 5 == 0) return launch_tma<T, NV, 3, 5, 3>(prm, B, st);
+                if (prm.N % 3 == 0) return launch_tma<T, NV, 3, 3, 5>(prm, B, st);
                 if (prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8>(prm, B, st);
                 return launch_tma<T, NV, 3, 1, 8>(prm, B, st);
             }
@@ -1388,6 +1452,13 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, bool shiftable, c
             if (prm.N == 8) return launch_tma<T, NV, 3, 4, 4, 8>(prm, B, st);
             if (prm.N == 10) return launch_tma<T, NV, 2, 5, 3, 10>(prm, B, st);
             if (prm.N == 5) return launch_tma<T, NV, 3, 5, 3, 5>(prm, B, st);
+            // other small ensembles / TTA counts (the shared-memory kernel below: 0.24-0.32 of the HBM peak)
+            if (prm.N == 2) return launch_tma<T, NV, 3, 2, 8, 2>(prm, B, st);
+            if (prm.N == 3) return launch_tma<T, NV, 3, 3, 5, 3>(prm, B, st);
+            if (prm.N == 4) return launch_tma<T, NV, 3, 4, 4, 4>(prm, B, st);
+            if (prm.N == 6) return launch_tma<T, NV, 3, 3, 5, 6>(prm, B, st);
+            if (prm.N == 12) return launch_tma<T, NV, 2, 4, 4, 12>(prm, B, st);
+            if (prm.N == 20) return launch_tma<T, NV, 2, 5, 3, 20>(prm, B, st);
         }
         // odd voxel counts (rows 8 bytes off): the same kernels in SH mode
         if (prm.need_ent && !prm.samax && !aligned && shiftable && prm.variant != K1_SAMPLE_OUTER) {
@@ -1511,23 +1582,10 @@ extern "C" int values_one_minus_msr(const void* probs, int dtype, int64_t B, int
     if (B == 0 || V == 0) return VALUES_OK;
     if (!probs || !out) return set_error(VALUES_ERR_INVALID_ARG, "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t bpv = ceil_div(V, kThreads);
-    if (bpv * B > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
-    const unsigned grid = (unsigned)(bpv * B);
     switch (dtype) {
-        case VALUES_F32:
-            msr_kernel<float><<<grid, kThreads, 0, st>>>((const float*)probs, C, V, stride_b,
-                                                         stride_c, (float*)out, bpv);
-            break;
-        case VALUES_F64:
-            msr_kernel<double><<<grid, kThreads, 0, st>>>((const double*)probs, C, V, stride_b,
-                                                          stride_c, (double*)out, bpv);
-            break;
-        case VALUES_BF16:
-            msr_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(
-                (const __nv_bfloat16*)probs, C, V, stride_b, stride_c, (__nv_bfloat16*)out, bpv);
-            break;
+        case VALUES_F32: return launch_msr<float>(probs, B, C, V, stride_b, stride_c, out, st);
+        case VALUES_F64: return launch_msr<double>(probs, B, C, V, stride_b, stride_c, out, st);
+        case VALUES_BF16: return launch_msr<__nv_bfloat16>(probs, B, C, V, stride_b, stride_c, out, st);
         default: return set_error(VALUES_ERR_INVALID_ARG, "unknown dtype %d", dtype);
     }
-    return check_launch("msr_kernel");
 }
