@@ -1102,7 +1102,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
 template <typename T, int VEC, int U, bool MEAN>
 __global__ void __launch_bounds__(kThreads) k1_argmax_kernel(const K1Params prm) {
     using A = typename In<T>::acc_t;
-    static_assert(VEC * sizeof(T) == 16, "vector path only");
+    static_assert(VEC * sizeof(T) == 16 || VEC == 1, "16-byte vectors, or single elements for unaligned stacks");
     const int64_t b = blockIdx.x / prm.blocks_per_vol;
     const int64_t blk = blockIdx.x - b * prm.blocks_per_vol;
     const int64_t v0 = (blk * kThreads + threadIdx.x) * VEC;
@@ -1120,7 +1120,8 @@ __global__ void __launch_bounds__(kThreads) k1_argmax_kernel(const K1Params prm)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (r0 + u < R) {
-                load_raw_stream<T, VEC>(lp, dst[u], pol);
+                if constexpr (VEC * sizeof(T) == 16) load_raw_stream<T, VEC>(lp, dst[u], pol);
+                else load_raw<T, VEC>(lp, dst[u]);
                 lp += s_in;
                 if (++lpos == L) { lpos = 0; lp += s_out; }
             }
@@ -1184,7 +1185,7 @@ static int launch_argmax(K1Params prm, int64_t B, cudaStream_t st) {
     prm.blocks_per_vol = ceil_div(ceil_div(prm.V, VEC), kThreads);
     const int64_t grid = prm.blocks_per_vol * B;
     if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
-    k1_argmax_kernel<T, VEC, 4, MEAN><<<(unsigned)grid, kThreads, 0, st>>>(prm);
+    k1_argmax_kernel<T, VEC, (VEC == 1 ? 8 : 4), MEAN><<<(unsigned)grid, kThreads, 0, st>>>(prm);
     return check_launch(MEAN ? "k1_argmax_kernel<mean>" : "k1_argmax_kernel<sample>");
 }
 
@@ -1397,8 +1398,9 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, bool shiftable, c
     // The per-sample arg-max wants the rows sample-outer, everything else class-outer: it is its own sweep
     // (1.0 of the HBM peak), and the maps / scores / mean arg-max follow through the ring as if it had not
     // been asked for -- two sweeps at the roofline instead of one shared-memory kernel at 0.26-0.47 of it.
-    if (prm.samax && aligned && prm.variant != K1_SAMPLE_OUTER) {
-        const int rc = launch_argmax<T, NV, false>(prm, B, st);
+    if (prm.samax && prm.variant != K1_SAMPLE_OUTER) {
+        // (unaligned stacks: the same sweep on single elements, lane-consecutive)
+        const int rc = aligned ? launch_argmax<T, NV, false>(prm, B, st) : launch_argmax<T, 1, false>(prm, B, st);
         if (rc) return rc;
         prm.samax = nullptr;
         if (!prm.need_ent && !prm.amax) return VALUES_OK;
@@ -1469,8 +1471,8 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, bool shiftable, c
         }
     }
     // the arg-max of the mean alone (no maps, no scores): its segmented sweep
-    if (!prm.need_ent && aligned && prm.amax && !prm.samax && prm.variant != K1_SAMPLE_OUTER)
-        return launch_argmax<T, NV, true>(prm, B, st);
+    if (!prm.need_ent && prm.amax && !prm.samax && prm.variant != K1_SAMPLE_OUTER)
+        return aligned ? launch_argmax<T, NV, true>(prm, B, st) : launch_argmax<T, 1, true>(prm, B, st);
     // per-sample arg-max next to the maps, unaligned stacks: sample-outer kernel with class sums in shared memory
     int rc = 1;
     if (aligned) {
