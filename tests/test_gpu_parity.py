@@ -475,6 +475,32 @@ def test_c3_filter_pass_is_exact(vb, vo, mean):
         assert res[0][1][i].tolist() == [b[0] for b in r["bounding_box"]], k
 
 
+@pytest.mark.parametrize("M,shape", [(5, (23, 50, 77)), (3, (41, 43, 127)), (4, (20, 30, 61)), (6, (130, 301)),
+                                     (2, (256, 478)), (3, (33, 35, 254))])
+def test_c3_unaligned_rows_take_the_pitched_copy(vb, vo, M, shape):
+    """fp32 maps whose innermost extent is not a multiple of 4 (no tensor map can describe their rows) are
+    copied into a scratch with pitched rows and go through the strip filter + listed passes there: same boxes
+    and scores as the exact march on the maps themselves (path 5) and as the oracle; negative values, a
+    planted near-tie in the last columns, a batch taken as a strided view."""
+    rng = np.random.default_rng(sum(shape) + M)
+    host = (rng.random((M + 1,) + shape) * 2.5 - 0.5).astype(np.float32)
+    lo = tuple(s - 10 for s in shape)
+    sl = tuple(slice(l, l + 10) for l in lo)
+    host[1][sl] += 3.0                                   # the maximum sits against the far corner (last columns)
+    host[2] = host[1] * (1 - 4e-6)
+    store = torch.from_numpy(host).cuda()
+    maps = store[:M] if M % 2 else store[1:M + 1]        # even M: a view that starts one map into the storage
+    href = host[:M] if M % 2 else host[1:M + 1]
+    s0, b0 = vb.patch_max(maps, 10, path=0)
+    s5, b5 = vb.patch_max(maps, 10, path=5)
+    np.testing.assert_allclose(s0.cpu().numpy(), s5.cpu().numpy(), rtol=1e-13, atol=0)
+    assert torch.equal(b0, b5)
+    for i in range(M):
+        r = vo.patch_level_aggregation(href[i], 10)
+        np.testing.assert_allclose(s0[i].item(), r["max_score"], rtol=1e-12)
+        assert b0[i].tolist()[-len(shape):] == [b[0] for b in r["bounding_box"]]
+
+
 @pytest.mark.parametrize("p0", [1, 4, 16, 33])
 def test_c3_filter_pass_other_window_depths(vb, vo, p0):
     """The march kernel and its filter fix only the in-plane window (10 x 10); the window depth p0 is

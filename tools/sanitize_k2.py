@@ -22,6 +22,12 @@ for shape in [(40, 64, 96), (23, 50, 76), (21, 45, 140)]:
         if ref is None:
             ref = (s.clone(), b.clone())
         assert torch.equal(ref[1], b) and torch.allclose(ref[0], s, rtol=1e-13, atol=0), (shape, path)
+for shape in [(23, 50, 77), (21, 30, 61), (70, 131)]:   # rows not 16-byte aligned: the pitched scratch copy
+    maps = torch.rand((3,) + shape, generator=g, device="cuda") * 3.0
+    s0, b0 = vb.patch_max(maps, 10, path=0)
+    s5, b5 = vb.patch_max(maps, 10, path=5)
+    torch.cuda.synchronize()
+    assert torch.equal(b0, b5) and torch.allclose(s0, s5, rtol=1e-13, atol=0), shape
 for shape in [(70, 132), (41, 300)]:     # 2-D images: the filter marches along y
     maps = torch.rand((5,) + shape, generator=g, device="cuda") * 3.0
     s0, b0 = vb.patch_max(maps, 10, path=0)

@@ -320,6 +320,7 @@ struct FusedParams {
     const void* maps;
     int64_t stride_m;
     int64_t D0, D1, D2, O0, O1, O2;
+    int64_t pitch;                // elements between rows (== D2, or D2 rounded up to 4 for the pitched scratch copy)
     int p0, p1, p2;
     int tiles_x, tiles_y, chunks_z, zc;
     int zsub, zc_fine;            // pass 2 splits a pass-1 z-chunk into zsub pieces of zc_fine planes
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
     // x-pass task and y-pass ownership
     const int task_r = tid % MT::R, task_seg = tid / MT::R;
     const int ox = tid % TX, oy0 = (tid / TX) * MT::RUN;
-    const unsigned int D1 = (unsigned int)prm.D1, D2 = (unsigned int)prm.D2;
+    const unsigned int D1 = (unsigned int)prm.D1, D2 = (unsigned int)prm.D2, PT = (unsigned int)prm.pitch;
     for (; work < n_work; work += work_step) {
         int tile, fine;
         if (!listed) { tile = prm.use_list ? work : blockIdx.x; fine = 0; }
@@ -763,12 +764,12 @@ __global__ void __launch_bounds__(kFusedThreads, MINB) box_march_kernel(const Fu
         const unsigned int x0 = (unsigned int)((tx_i / prm.tx_per) * prm.xs_stride + (tx_i % prm.tx_per) * TX);
         const unsigned int y0 = (unsigned int)ty_i * TY;
         const int nplanes = (int)(zo1 - zo0) + p0 - 1;
-        const unsigned int plane_elems = D1 * D2;
+        const unsigned int plane_elems = D1 * PT;
         const T* src = reinterpret_cast<const T*>(prm.maps) + m * prm.stride_m + zo0 * (int64_t)plane_elems;
         unsigned int off[MT::NSLOT];     // clamped in-plane offsets of this thread's input rows
 #pragma unroll
         for (int i = 0; i < MT::NSLOT; ++i)
-            off[i] = min(y0 + g + i * MT::G, D1 - 1) * D2 + min(x0 + cx, D2 - 1);
+            off[i] = min(y0 + g + i * MT::G, D1 - 1) * PT + min(x0 + cx, D2 - 1);
         ACC zs[MT::NSLOT];
         T nw[MT::NSLOT], od[MT::NSLOT];
 #pragma unroll
@@ -1479,7 +1480,7 @@ static int make_map_tensor(const FusedParams& prm, int64_t M, int rows, int cols
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return set_error(VALUES_ERR_CUDA, "patch_max: cuTensorMapEncodeTiled is not available");
     const cuuint64_t gdim[4] = {(cuuint64_t)prm.D2, (cuuint64_t)prm.D1, (cuuint64_t)prm.D0, (cuuint64_t)M};
-    const cuuint64_t gstr[3] = {(cuuint64_t)prm.D2 * 4, (cuuint64_t)prm.D1 * prm.D2 * 4, (cuuint64_t)prm.stride_m * 4};
+    const cuuint64_t gstr[3] = {(cuuint64_t)prm.pitch * 4, (cuuint64_t)prm.D1 * prm.pitch * 4, (cuuint64_t)prm.stride_m * 4};
     const cuuint32_t box[4] = {(cuuint32_t)cols, (cuuint32_t)rows, 1, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(prm.maps), gdim, gstr, box, estr,
@@ -1490,6 +1491,30 @@ static int make_map_tensor(const FusedParams& prm, int64_t M, int rows, int cols
 }
 
 // can the strip filter stream these maps by TMA?  (16-byte aligned rows, planes and maps)
+// Maps whose rows are not 16-byte aligned (an innermost extent that is not a multiple of 4: 478-wide images,
+// 127^3 volumes) cannot be described by a tensor map, and the exact march on every window is 3x the filter
+// path.  They are copied once into a scratch with the rows pitched to a multiple of 4 floats (a warp per row,
+// lane-consecutive loads and stores; the pad is never read as data: the tensor map's extent stays D2 and the
+// march clamps to D2 - 1), and filter + listed passes run on the copy: 2 x 4V bytes for the copy against
+// ~8V saved.
+__global__ void __launch_bounds__(kThreads) pitch_rows_kernel(const float* __restrict__ maps, int64_t stride_m,
+                                                              int64_t rows_per_map, int64_t n_rows, int D2, int pitch,
+                                                              float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kThreads) >> 5;
+    for (int64_t r = warp; r < n_rows; r += nwarps) {
+        const int64_t m = r / rows_per_map;
+        const float* src = maps + m * stride_m + (r - m * rows_per_map) * D2;
+        float* dst = out + r * pitch;
+        for (int x = lane; x < pitch; x += 32) dst[x] = x < D2 ? __ldg(src + x) : 0.f;
+    }
+}
+static int64_t pitched_width(int64_t d2) { return (d2 + 3) / 4 * 4; }
+static size_t pitched_scratch_bytes(int64_t M, const int64_t* shape) {
+    return (size_t)M * (size_t)shape[0] * (size_t)shape[1] * (size_t)pitched_width(shape[2]) * sizeof(float) + 256;
+}
+
 static bool strip_filter_ok(const void* maps, int dtype, int64_t stride_m, const int64_t* shape) {
     return dtype == VALUES_F32 && shape[2] % 4 == 0 && stride_m % 4 == 0 &&
            (reinterpret_cast<uintptr_t>(maps) & 15) == 0 && shape[0] < 0x7fffffffLL && encode_tiled_fn() != nullptr;
@@ -1675,6 +1700,9 @@ extern "C" size_t values_patch_max_workspace_bytes(int64_t M, const int64_t* sha
             if (make_fused_plan(M, shape3_host, patch3_host, path, strip != 0, fp) != VALUES_OK) return 0;
             if (fp.ty) need = std::max(need, fused_workspace_bytes(M, fp));
         }
+        // rows that are not 16-byte aligned: room for the pitched copy the strip filter runs on
+        if (need && path == 0 && shape3_host[2] % 4 != 0 && march_applies(path, shape3_host, patch3_host))
+            need = (need + 255) / 256 * 256 + pitched_scratch_bytes(M, shape3_host);
         if (need) return need;
     }
     PatchPlan pl;
@@ -1706,8 +1734,21 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
         mean_flag ? (double)patch3_host[0] * (double)patch3_host[1] * (double)patch3_host[2] : 1.0;
     if (path != 2) {
         FusedPlan fp;
-        const bool strip = path == 0 && M > 0 && maps && march_applies(path, shape3_host, patch3_host) &&
-                           strip_filter_ok(maps, dtype, stride_m, shape3_host);
+        bool strip = path == 0 && M > 0 && maps && march_applies(path, shape3_host, patch3_host) &&
+                     strip_filter_ok(maps, dtype, stride_m, shape3_host);
+        // fp32 maps with an innermost extent that is not a multiple of 4: the strip filter on a pitched copy,
+        // if the caller's workspace has room for it (values_patch_max_workspace_bytes asks for it)
+        bool pitched = false;
+        if (!strip && path == 0 && M > 0 && maps && dtype == VALUES_F32 && shape3_host[2] % 4 != 0 &&
+            march_applies(path, shape3_host, patch3_host) && encode_tiled_fn() != nullptr) {
+            FusedPlan probe;
+            int rcp = make_fused_plan(M, shape3_host, patch3_host, path, true, probe);
+            if (rcp) return rcp;
+            const size_t base = (fused_workspace_bytes(M, probe) + 255) / 256 * 256;
+            pitched = probe.ty && workspace && workspace_bytes >= base + pitched_scratch_bytes(M, shape3_host) &&
+                      (int64_t)M * shape3_host[0] * shape3_host[1] < (1LL << 40);
+            strip = pitched;
+        }
         int rc = make_fused_plan(M, shape3_host, patch3_host, path, strip, fp);
         if (rc) return rc;
         if (fp.ty) {
@@ -1719,6 +1760,20 @@ extern "C" int values_patch_max(const void* maps, int dtype, int64_t M, int64_t 
             FusedParams prm{};
             prm.maps = maps; prm.stride_m = stride_m;
             prm.D0 = shape3_host[0]; prm.D1 = shape3_host[1]; prm.D2 = shape3_host[2];
+            prm.pitch = prm.D2;
+            if (pitched) {
+                const size_t base = (need + 255) / 256 * 256;
+                uintptr_t sp = (reinterpret_cast<uintptr_t>(workspace) + base + 255) / 256 * 256;
+                float* scratch = reinterpret_cast<float*>(sp);
+                const int64_t rows_per_map = prm.D0 * prm.D1, n_rows = M * rows_per_map;
+                const int pw = (int)pitched_width(prm.D2);
+                const int64_t want = ceil_div(n_rows * 32, kThreads);
+                const unsigned grid = (unsigned)std::min<int64_t>(want, 148 * 16);
+                pitch_rows_kernel<<<grid, kThreads, 0, st>>>((const float*)maps, stride_m, rows_per_map, n_rows,
+                                                            (int)prm.D2, pw, scratch);
+                if ((rc = check_launch("pitch_rows_kernel"))) return rc;
+                prm.maps = scratch; prm.pitch = pw; prm.stride_m = rows_per_map * pw;
+            }
             prm.O0 = fp.O0; prm.O1 = fp.O1; prm.O2 = fp.O2;
             prm.p0 = (int)patch3_host[0]; prm.p1 = (int)patch3_host[1]; prm.p2 = (int)patch3_host[2];
             prm.tiles_x = fp.tiles_x; prm.tiles_y = fp.tiles_y; prm.chunks_z = fp.chunks_z; prm.zc = fp.zc;
