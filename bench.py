@@ -69,6 +69,12 @@ WORKLOADS = {
     "cfg4": dict(name="cfg4: 1024x2048 images, N=10, C=19+1, fp32; all C3 aggregations",
                  N=10, C=20, spatial=(1024, 2048), dtype="f32", pool=6, e2e_pool=2, patch=10, thr=True, cfg=4,
                  batch_sweep=(1, 2, 4, 6, 12)),
+    # not BASELINE configs: shapes whose rows are not 16-byte aligned (every kernel of the step takes its
+    # unaligned form: K1 element-strided ring, K2b pitched copy) and the reference-true 2-D shape of SURVEY 8d
+    "cfg5odd": dict(name="cfg5 on 127^3 volumes (rows at every 16-byte phase), N=16, C=4, fp32; same aggregations",
+                    N=16, C=4, spatial=(127, 127, 127), dtype="f32", pool=32, e2e_pool=4, patch=10, thr=True, cfg=5),
+    "cfg4true": dict(name="cfg4 at the reference-true GTA shape 256x478, N=10, C=24+1, fp32; all C3 aggregations",
+                     N=10, C=25, spatial=(256, 478), dtype="f32", pool=48, e2e_pool=8, patch=10, thr=True, cfg=4),
     "cfg4bf16": dict(name="cfg4: 1024x2048 images, N=10, C=19+1, bf16; all C3 aggregations",
                      N=10, C=20, spatial=(1024, 2048), dtype="bf16", pool=6, e2e_pool=2, patch=10, thr=True, cfg=4,
                      batch_sweep=(1, 2, 4, 6, 12)),

@@ -25,7 +25,7 @@ if [ "$2" = "sanitizers-only" ]; then cat $out/${tag}_sanitizer.txt; exit 0; fi
 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_cfg5_reference_arm.json 2> $out/${tag}_bench.err
 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench_cfg5.json 2>> $out/${tag}_bench.err
 : > $out/${tag}_bench_others.jsonl
-for w in cfg1 cfg2 cfg3 cfg3gauss cfg4 cfg4bf16; do
+for w in cfg1 cfg2 cfg3 cfg3gauss cfg4 cfg4bf16 cfg5odd cfg4true; do
   python bench.py --workload $w --steps 20 --warmup 3 >> $out/${tag}_bench_others.jsonl 2>> $out/${tag}_bench.err
 done
 cat $out/${tag}_pytest_gpu.txt; cat $out/${tag}_sanitizer.txt
