@@ -512,6 +512,16 @@ stitch_box_kernel(const __grid_constant__ CUtensorMap tmap, const StitchParams p
                 }
                 continue;
             }
+            // accumulating on top of earlier sums (DataCarrier3D.concat_data: a handful of patches per call):
+            // a box no listed patch reaches keeps its sums -- no read-modify-write of the untouched volume
+            if (readback) {
+                bool any = false;
+                for (int k = 0; k < total && !any; ++k) {
+                    const int ex = s_list[k].x;
+                    any = x_lo < ex + prm.p0 && x_hi > ex;
+                }
+                if (!any) continue;
+            }
             bool gin[kGroups];
 #pragma unroll
             for (int i = 0; i < kGroups; ++i) gin[i] = gyz[i] && x_lo + gdx[i] < prm.X;
