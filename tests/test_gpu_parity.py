@@ -732,6 +732,27 @@ def test_stitch_one_sample_with_patch_index(vb, vo, stitch_path):
     np.testing.assert_array_equal(cnt.cpu().numpy(), want_cnt)
 
 
+def test_stitch_a_batch_at_a_time_equals_one_call(vb, vo, stitch_path):
+    """DataCarrier3D.concat_data's pattern (data_carrier_3D.py:99-179): the patches of a volume arrive a few at
+    a time and are accumulated on top of the sums; boxes a call does not reach must keep theirs (the box
+    kernel skips them instead of reading and re-storing the whole volume)."""
+    shape, p = (72, 56, 64), 16
+    crops = vo.patch_grid(shape, p, 0.5)
+    g = torch.Generator().manual_seed(31)
+    patches = torch.rand(2, len(crops), 3, p, p, p, generator=g, dtype=torch.float32).cuda()
+    lo = vb.stitching.crops_to_lo(crops, "cuda")
+    want, want_cnt = vb.stitch_volume(patches, crops, shape, path=stitch_path)
+    out = torch.zeros_like(want)
+    cnt = torch.zeros_like(want_cnt)
+    order = torch.randperm(len(crops), generator=g).tolist()
+    order.sort()                                    # list order = summation order: keep it
+    for i in range(0, len(order), 3):
+        sel = order[i:i + 3]
+        vb.stitch_accumulate(patches, lo[sel], out, cnt, patch_index=torch.tensor(sel, dtype=torch.int32, device="cuda"),
+                             accumulate=True, path=stitch_path)
+    assert torch.equal(out, want) and torch.equal(cnt, want_cnt)
+
+
 def test_stitch_many_patches_chunked_list(vb, vo, stitch_path):
     shape, p = (44, 44, 44), 8
     crops = vo.patch_grid(shape, p, 0.25)  # stride 2 -> 19^3 = 6859 patches > list chunk
