@@ -101,9 +101,14 @@ class DataCarrier3D:
             groups.setdefault(image_path, []).append(index)
         for image_path, idxs in groups.items():
             entry = self.data[image_path]
-            lo = np.asarray([[batch["crop_idx"][i][d][0] for d in range(3)] for i in idxs], dtype=np.int32)
-            crop_lo = torch.from_numpy(lo).to(dev)
-            pidx = torch.tensor(idxs, dtype=torch.int32, device=dev)
+            # crop origins and patch indices of the call in ONE host-to-device copy: [3 n] origins, then [n] indices
+            n_sel = len(idxs)
+            meta = np.empty(4 * n_sel, dtype=np.int32)
+            meta[:3 * n_sel] = [batch["crop_idx"][i][d][0] for i in idxs for d in range(3)]
+            meta[3 * n_sel:] = idxs
+            meta_dev = torch.from_numpy(meta).to(dev)
+            crop_lo = meta_dev[:3 * n_sel].view(n_sel, 3)
+            pidx = meta_dev[3 * n_sel:]
             stitch_accumulate(sp.unsqueeze(0), crop_lo, entry["softmax_pred"][pred_idx:pred_idx + 1],
                               entry["_count"] if pred_idx == 0 else None, patch_index=pidx, accumulate=True,
                               weight=self.patch_weight, path=self.stitch_path)
