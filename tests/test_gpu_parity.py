@@ -121,7 +121,10 @@ def test_c2_vs_oracle(vb, vo, n, c, spatial, dtype):
     (6, 3, (50, 64), torch.float32),        # RS = 3, ragged last tile
     (3, 4, (24, 40, 20), torch.float32),    # RS = 3, one stage per class
     (14, 3, (40, 52), torch.float32),       # RS = 2
-    (7, 5, (40, 52), torch.float32),        # RS = 1
+    (7, 5, (40, 52), torch.float32),        # 4-row stages, ragged last stage (4 + 3)
+    (17, 4, (24, 40, 20), torch.float32),   # ... 4 x 4 + 1
+    (11, 3, (33, 64), torch.bfloat16),      # ... 4 + 4 + 3, bf16
+    (1, 6, (40, 52), torch.float32),        # RS = 1
     (8, 4, (33, 64), torch.bfloat16),
     (16, 4, (24, 40, 26), torch.float64),   # fp64: class-outer ring kernel (per-sample accumulators) vs
     (8, 2, (30, 50), torch.float64),        # the sample-outer kernel (variant 4)
@@ -156,7 +159,8 @@ def test_k1_kernels_agree(vb, n, c, spatial, dtype):
     (5, 2, (63, 63, 63), torch.float32),    # RS = 5, many tiles, ragged end
     (10, 20, (61, 77), torch.float32),      # RS = 5, C = 20
     (6, 3, (45, 51), torch.float32),        # RS = 2
-    (7, 5, (33, 39), torch.float32),        # RS = 1
+    (7, 5, (33, 39), torch.float32),        # ragged last stage in the element-strided mode
+    (13, 2, (31, 45), torch.float32),
     (3, 2, (7, 5), torch.float32),          # less than one tile
     (8, 4, (33, 61), torch.bfloat16),       # rows 2 bytes off
     (16, 4, (21, 23, 25), torch.float64),   # fp64: rows 8 bytes off

@@ -29,7 +29,9 @@ cases = [(16, 4, (24, 40, 20), torch.float32), (12, 3, (20, 36), torch.float32),
          (3, 4, (10, 14), torch.float64),
          # rows that are not 16-byte aligned: the ring in its element-strided mode (SH)
          (16, 4, (13, 21, 9), torch.float32), (5, 2, (37, 59), torch.float32), (6, 3, (33, 45), torch.float32),
-         (8, 4, (17, 39), torch.bfloat16), (8, 2, (11, 13, 9), torch.float64), (5, 2, (35, 37), torch.float64)]
+         (8, 4, (17, 39), torch.bfloat16), (8, 2, (11, 13, 9), torch.float64), (5, 2, (35, 37), torch.float64),
+         # ragged last stage (N = 7, 11), aligned and element-strided
+         (11, 3, (24, 40), torch.float32), (7, 2, (21, 39), torch.float32), (7, 3, (16, 40), torch.bfloat16)]
 for n, c, spatial, dtype in cases:
     x = stack(2, n, c, spatial, dtype)
     ref = None

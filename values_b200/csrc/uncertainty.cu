@@ -814,11 +814,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k1_stream_kernel(const K1Param
 // arg-max are bit-identical to the other kernels; the fp64 score sums group the voxels differently.
 // The granules before the first and after the last element of the stack are read as well: the host
 // checks that they lie inside the allocation (dispatch_k1, allocation_range).
-template <typename T, int VEC, int MINB, int RS, int kTmaStages, int NS = 0, bool SH = false>
+// RAG (sample counts no stage size divides: N = 7, 11, 13, 14, 17, ...): the last stage of a class holds the
+// N % RS rows that are left -- `rows` below is uniform, and a compile-time RS without it -- instead of
+// single-row stages with an mbarrier round trip per row.
+template <typename T, int VEC, int MINB, int RS, int kTmaStages, int NS = 0, bool SH = false, bool RAG = false>
 __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Params prm) {
     using A = typename In<T>::acc_t;
     using M = Math<T>;
     static_assert(VEC * sizeof(T) == 16, "vector path only");
+    static_assert(!RAG || NS == 0, "ragged stages: fp32 / bf16 stacks");
     constexpr int kRowBytes = kThreads * 16;
     constexpr int kRowPitch = kRowBytes + (SH ? 16 : 0);
     constexpr int kStageBytes = RS * kRowPitch;
@@ -857,25 +861,27 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                     const char* row = row_c;
                     for (int n = 0; n < N; n += RS) {
                         mbar_wait(empty_bar + stage, phase ^ 1u);
+                        const int rows = RAG ? min(RS, N - n) : RS;
                         if constexpr (SH) {
                             // the 16-byte granules covering [row, row + bytes) of every row of the stage
                             uint32_t total = 0;
                             const char* r2 = row;
 #pragma unroll
                             for (int u = 0; u < RS; ++u, r2 += snb)
-                                total += (((uint32_t)reinterpret_cast<uintptr_t>(r2) & 15u) + bytes + 15u) & ~15u;
+                                if (u < rows) total += (((uint32_t)reinterpret_cast<uintptr_t>(r2) & 15u) + bytes + 15u) & ~15u;
                             mbar_expect_tx(full_bar + stage, total);
 #pragma unroll
                             for (int u = 0; u < RS; ++u, row += snb) {
+                                if (u >= rows) continue;
                                 const uint32_t a = (uint32_t)reinterpret_cast<uintptr_t>(row) & 15u;
                                 bulk_g2s(ring + stage * kStageBytes + u * kRowPitch, row - a, (a + bytes + 15u) & ~15u,
                                          full_bar + stage, policy);
                             }
                         } else {
-                            mbar_expect_tx(full_bar + stage, bytes * RS);
+                            mbar_expect_tx(full_bar + stage, bytes * rows);
 #pragma unroll
                             for (int u = 0; u < RS; ++u, row += snb)
-                                bulk_g2s(ring + stage * kStageBytes + u * kRowBytes, row, bytes, full_bar + stage, policy);
+                                if (u < rows) bulk_g2s(ring + stage * kStageBytes + u * kRowBytes, row, bytes, full_bar + stage, policy);
                         }
                         if (++stage == kTmaStages) { stage = 0; phase ^= 1u; }
                     }
@@ -937,11 +943,13 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                 // rows of a stage are consumed SB at a time (registers), the stage is one mbarrier round trip
                 constexpr int SB = RS > 5 ? RS / 2 : RS;
                 static_assert(RS % SB == 0, "sub-batches");
+                const int rows = RAG ? min(RS, N - n) : RS;
 #pragma unroll
                 for (int h = 0; h < RS; h += SB) {
                     Raw<T, VEC> raw[SB];
 #pragma unroll
                     for (int u = 0; u < SB; ++u) {
+                        if (RAG && h + u >= rows) continue;
                         if constexpr (SH) {
                             const uint32_t a = (ph_vol + (uint32_t)c * ph_sc + (uint32_t)(n + h + u) * ph_sn) & 15u;
                             lds_strided<T, VEC>(ring_tid + stage * kStageBytes + (h + u) * kRowPitch + a, raw[u]);
@@ -954,6 +962,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) k1_tma_kernel(const K1Par
                     if (active) {
 #pragma unroll
                         for (int u = 0; u < SB; ++u) {
+                            if (RAG && h + u >= rows) continue;
                             A p[VEC];
                             unpack(raw[u], p);
                             if (M::kFlagged) bad |= sign_or(raw[u]);
@@ -1374,14 +1383,14 @@ static int launch_stream(K1Params& prm, int64_t B, cudaStream_t st) {
     return check_launch("k1_stream_kernel");
 }
 
-template <typename T, int VEC, int MINB, int RS, int STAGES, int NS = 0, bool SH = false>
+template <typename T, int VEC, int MINB, int RS, int STAGES, int NS = 0, bool SH = false, bool RAG = false>
 static int launch_tma(K1Params& prm, int64_t B, cudaStream_t st) {
     const int64_t tiles = ceil_div(ceil_div(prm.V, VEC), kThreads);
     prm.iter = prm.tiles_per_cta > 0 ? prm.tiles_per_cta : choose_iter(tiles * B, MINB, prm.N * prm.C, sizeof(T) == 8);
     prm.blocks_per_vol = ceil_div(tiles, prm.iter);
     const int64_t grid = prm.blocks_per_vol * B;
     if (grid > 0x7fffffffLL) return set_error(VALUES_ERR_UNSUPPORTED, "grid too large");
-    auto kern = k1_tma_kernel<T, VEC, MINB, RS, STAGES, NS, SH>;
+    auto kern = k1_tma_kernel<T, VEC, MINB, RS, STAGES, NS, SH, RAG>;
     const size_t smem = (size_t)STAGES * RS * (kThreads * 16 + (SH ? 16 : 0));
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return set_error(VALUES_ERR_CUDA, "cudaFuncSetAttribute(k1_tma_kernel) failed");
@@ -1415,8 +1424,9 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, bool shiftable, c
                 if (shiftable && prm.variant != K1_STREAM) {
                     if (prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4, 0, true>(prm, B, st);
                     if (prm.N % 5 == 0) return launch_tma<T, NV, 3, 5, 3, 0, true>(prm, B, st);
-                    if (prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8, 0, true>(prm, B, st);
-                    return launch_tma<T, NV, 3, 1, 8, 0, true>(prm, B, st);
+                    if (prm.N == 2) return launch_tma<T, NV, 3, 2, 8, 0, true>(prm, B, st);
+                    if (prm.N == 1) return launch_tma<T, NV, 3, 1, 8, 0, true>(prm, B, st);
+                    return launch_tma<T, NV, 3, 4, 4, 0, true, true>(prm, B, st);   // ragged last stage
                 }
             }
             return launch_stream<T, 1, 4, 4, false>(prm, B, st);
@@ -1438,8 +1448,10 @@ static int dispatch_k1(K1Params& prm, int64_t B, bool aligned, bool shiftable, c
                 if (prm.N % 4 == 0) return launch_tma<T, NV, 3, 4, 4>(prm, B, st);
                 if (prm.N % 5 == 0) return launch_tma<T, NV, 3, 5, 3>(prm, B, st);
                 if (prm.N % 3 == 0) return launch_tma<T, NV, 3, 3, 5>(prm, B, st);
-                if (prm.N % 2 == 0) return launch_tma<T, NV, 3, 2, 8>(prm, B, st);
-                return launch_tma<T, NV, 3, 1, 8>(prm, B, st);
+                if (prm.N == 2) return launch_tma<T, NV, 3, 2, 8>(prm, B, st);
+                if (prm.N == 1) return launch_tma<T, NV, 3, 1, 8>(prm, B, st);
+                // N = 7, 11, 13, 14, 17, ...: 4-row stages with a ragged last one (single-row stages: 0.65-0.72)
+                return launch_tma<T, NV, 3, 4, 4, 0, false, true>(prm, B, st);
             }
         }
         if (prm.N % 4 == 0) return launch_stream<T, NV, 4, 3, true>(prm, B, st);
