@@ -49,6 +49,22 @@ def test_workspace_queries_are_pure_host_functions():
     assert _lib.lib.values_patch_max_workspace_bytes(3, _lib.i64x3([8, 8, 8]), pa, 0) == 0  # patch > image
     assert _lib.lib.values_patch_max_workspace_bytes(3, sh, pa, 1) == 0  # unknown implementation
     assert _lib.lib.values_map_reduce_workspace_bytes(3, 1000) > 0
+    # maps whose innermost extent is not a multiple of 4 get room for the pitched scratch copy the strip
+    # filter runs on (M x D0 x D1 x round_up(D2, 4) floats); aligned shapes and the exact path do not
+    aligned = _lib.lib.values_patch_max_workspace_bytes(3, _lib.i64x3([40, 40, 64]), pa, 0)
+    odd = _lib.lib.values_patch_max_workspace_bytes(3, _lib.i64x3([40, 40, 63]), pa, 0)
+    assert odd >= aligned - 4096 + 3 * 40 * 40 * 64 * 4 and aligned < 3 * 40 * 40 * 64 * 4
+    assert _lib.lib.values_patch_max_workspace_bytes(3, _lib.i64x3([40, 40, 63]), pa, 5) < 3 * 40 * 40 * 64 * 4
+
+
+def test_map_set_tables():
+    """The *_set entry points take HOST arrays of device pointers and counts (include/values_b200.h)."""
+    from values_b200 import _lib
+
+    maps = [torch.zeros(5), torch.zeros(0), torch.zeros(7, 3)]      # CPU tensors: only the table is built here
+    ptrs, counts, n = _lib.map_set(maps)
+    assert n == 3 and list(counts) == [5, 0, 21]
+    assert ptrs[0] == maps[0].data_ptr() and ptrs[2] == maps[2].data_ptr()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
